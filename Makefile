@@ -1,0 +1,19 @@
+# Builds libmmpgo.so (the C-ABI CUDA library) in-tree for sm_100a and the C oracle helpers.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fopenmp,-O3 -Iinclude
+SRC := dpgo_b200/csrc/mmpgo_kernels.cu dpgo_b200/csrc/mmpgo_setup.cu dpgo_b200/csrc/mmpgo_driver.cu dpgo_b200/csrc/mmpgo_capi.cu
+OBJ := $(SRC:.cu=.o)
+LIB := dpgo_b200/libmmpgo.so
+
+all: $(LIB)
+
+%.o: %.cu dpgo_b200/csrc/mmpgo_kernels.cuh dpgo_b200/csrc/mmpgo_driver.cuh dpgo_b200/csrc/so3_project.cuh include/mmpgo.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -Xcompiler -fopenmp -lgomp -cudart shared
+
+clean:
+	rm -f $(OBJ) $(LIB)
+.PHONY: all clean

@@ -1,0 +1,211 @@
+// extern "C" surface of libmmpgo; see include/mmpgo.h for the contract.
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "mmpgo_driver.cuh"
+
+namespace mmpgo {
+static thread_local std::string g_err;
+void set_error(const std::string &s) { g_err = s; }
+}  // namespace mmpgo
+
+using mmpgo::Handle;
+
+struct mmpgo_handle_s {
+  Handle h;
+};
+
+#define H_OR_FAIL(hh)                                   \
+  if (!(hh)) {                                          \
+    mmpgo::set_error("null handle");                    \
+    return MMPGO_ERR_ARG;                               \
+  }                                                     \
+  Handle *h = &(hh)->h;                                 \
+  if (cudaSetDevice(h->opt.device) != cudaSuccess) {    \
+    mmpgo::set_error("cudaSetDevice failed");           \
+    return MMPGO_ERR_CUDA;                              \
+  }
+
+extern "C" {
+
+const char *mmpgo_version(void) { return "mmpgo-b200 0.1 (sm_100a, fp64)"; }
+const char *mmpgo_last_error(void) { return mmpgo::g_err.c_str(); }
+
+void mmpgo_default_options(mmpgo_options *o) {
+  std::memset(o, 0, sizeof(*o));
+  o->algorithm = MMPGO_ALG_HASH;
+  o->scheme = MMPGO_SCHEME_AMM;
+  o->loss = MMPGO_LOSS_NONE;
+  o->preconditioner = MMPGO_PRECON_BLOCK_JACOBI;
+  o->regularizer = 1e-11;       // dist_pgo.cpp:120
+  o->loss_reg = 0.25;           // :107
+  o->accepted_delta = 5e-4;
+  o->eta[0] = 5e-4; o->eta[1] = 2.5e-2;
+  o->psi = 1e-10; o->phi = 1e-6;
+  o->max_soft_restart_hits[0] = 10; o->max_soft_restart_hits[1] = 25;
+  o->oscillation_cnt_period = 15;
+  o->max_oscillations = 12;
+  o->grad_norm_tol = 1e-3;
+  o->preconditioned_grad_norm_tol = 1e-4;
+  o->rel_func_decrease_tol = 1e-6;
+  o->stepsize_tol = 1e-4;
+  o->max_iterations = 10;
+  o->max_iterations_accepted = 1;
+  o->max_tCG_iterations = 10000;
+  o->STPCG_kappa = 0.05; o->STPCG_theta = 0.9;
+  o->dense_solve_max_n = 2048;
+  o->translation_solve_tol = 1e-12;
+  o->translation_solve_max_iters = 4000;
+  o->device = 0;
+}
+
+int mmpgo_create(const mmpgo_options *opts, mmpgo_handle *out) {
+  if (!opts || !out) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
+  if (opts->loss < 0 || opts->loss > 3 || opts->preconditioner < 0 || opts->preconditioner > 2 ||
+      opts->algorithm < 0 || opts->algorithm > 1 || opts->scheme < 0 || opts->scheme > 1) {
+    mmpgo::set_error("invalid enum value in options");
+    return MMPGO_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    mmpgo::set_error("no CUDA device: libmmpgo has no CPU fallback");
+    return MMPGO_ERR_CUDA;
+  }
+  if (opts->device < 0 || opts->device >= ndev) { mmpgo::set_error("bad device ordinal"); return MMPGO_ERR_ARG; }
+  if (cudaSetDevice(opts->device) != cudaSuccess) { mmpgo::set_error("cudaSetDevice failed"); return MMPGO_ERR_CUDA; }
+  mmpgo_handle_s *hs = new (std::nothrow) mmpgo_handle_s();
+  if (!hs) { mmpgo::set_error("out of host memory"); return MMPGO_ERR_ARG; }
+  hs->h.opt = *opts;
+  std::memset(&hs->h.ctr, 0, sizeof(hs->h.ctr));
+  if (cudaStreamCreateWithFlags(&hs->h.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete hs;
+    mmpgo::set_error("cudaStreamCreate failed");
+    return MMPGO_ERR_CUDA;
+  }
+  *out = hs;
+  return MMPGO_OK;
+}
+
+int mmpgo_destroy(mmpgo_handle hh) {
+  if (!hh) return MMPGO_OK;
+  cudaSetDevice(hh->h.opt.device);
+  cudaStreamSynchronize(hh->h.stream);
+  mmpgo::driver_free(&hh->h);
+  cudaStreamDestroy(hh->h.stream);
+  delete hh;
+  return MMPGO_OK;
+}
+
+int mmpgo_set_graph(mmpgo_handle hh, int32_t d, int64_t num_poses, int32_t num_nodes, int32_t node_begin,
+                    int32_t node_end, int64_t num_edges, const int32_t *edge_i, const int32_t *edge_j,
+                    const double *R, const double *t, const double *kappa, const double *tau) {
+  H_OR_FAIL(hh);
+  if (!edge_i || !edge_j || !R || !t || !kappa || !tau) { mmpgo::set_error("null edge array"); return MMPGO_ERR_ARG; }
+  try {
+    return mmpgo::driver_set_graph(h, d, num_poses, num_nodes, node_begin, node_end, num_edges, edge_i, edge_j, R,
+                                   t, kappa, tau);
+  } catch (const std::exception &e) {
+    mmpgo::set_error(e.what());
+    return MMPGO_ERR_ARG;
+  }
+}
+
+#define GUARDED(call)                              \
+  try {                                            \
+    return (call);                                 \
+  } catch (const std::exception &e) {              \
+    mmpgo::set_error(e.what());                    \
+    return MMPGO_ERR_ARG;                          \
+  }
+
+int mmpgo_initialize(mmpgo_handle hh, const double *X, int64_t ldx) {
+  H_OR_FAIL(hh);
+  if (!X) { mmpgo::set_error("null X"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::driver_initialize(h, X, ldx));
+}
+int mmpgo_update(mmpgo_handle hh) { H_OR_FAIL(hh); GUARDED(mmpgo::driver_update(h)); }
+int mmpgo_iterate(mmpgo_handle hh) { H_OR_FAIL(hh); GUARDED(mmpgo::driver_iterate(h)); }
+int mmpgo_communicate(mmpgo_handle hh) { H_OR_FAIL(hh); GUARDED(mmpgo::driver_communicate(h)); }
+
+int mmpgo_get_poses(mmpgo_handle hh, double *X, int64_t ldx) {
+  H_OR_FAIL(hh);
+  if (!X || ldx < (int64_t)(h->d + 1) * h->N) { mmpgo::set_error("bad X / ldx"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::driver_get_poses(h, X, ldx));
+}
+
+int mmpgo_get_node_scalars(mmpgo_handle hh, int32_t node, mmpgo_node_scalars *out) {
+  H_OR_FAIL(hh);
+  if (!out || !h->graph_set || node < h->node_begin || node >= h->node_end) {
+    mmpgo::set_error("node not local");
+    return MMPGO_ERR_ARG;
+  }
+  const mmpgo::NodeState &s = h->st[node - h->node_begin];
+  const mmpgo::NodeInfo &ni = h->info[node - h->node_begin];
+  std::memset(out, 0, sizeof(*out));
+  out->fobj = s.fobj; out->f = s.f; out->Gk = s.Gk; out->gradFnorm = s.gradFnorm;
+  out->Fk[0] = s.Fk[0]; out->Fk[1] = s.Fk[1];
+  out->s = s.s_cur; out->s_next = s.s_next; out->gamma = s.gamma;
+  out->iters = s.iters;
+  out->soft_restart_hits[0] = s.soft_restart_hits[0]; out->soft_restart_hits[1] = s.soft_restart_hits[1];
+  out->num_oscillations = s.num_oscillations;
+  out->refined = s.refined ? 1 : 0; out->restarts = s.restarts;
+  out->tcg_iterations = s.tcg_iterations; out->tnt_iterations = s.tnt_iterations;
+  out->n0 = ni.n0; out->n1 = ni.n1; out->m0 = ni.m0; out->m1 = ni.m1;
+  return MMPGO_OK;
+}
+
+int mmpgo_get_weights(mmpgo_handle hh, int32_t node, double *w, int64_t capacity, int64_t *count) {
+  H_OR_FAIL(hh);
+  if (!count || !h->graph_set) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::driver_get_weights(h, node, w, capacity, count));
+}
+
+int mmpgo_evaluate_f(mmpgo_handle hh, const double *X, int64_t ldx, double *fobj) {
+  H_OR_FAIL(hh);
+  if (!X || !fobj || ldx < (int64_t)(h->d + 1) * h->N) { mmpgo::set_error("bad X / ldx"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::driver_evaluate_f(h, X, ldx, fobj));
+}
+
+int mmpgo_current_objective(mmpgo_handle hh, double *fobj, double *grad_sqnorm) {
+  H_OR_FAIL(hh);
+  if (!fobj || !grad_sqnorm) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::driver_current_objective(h, fobj, grad_sqnorm));
+}
+
+int mmpgo_star_objective(mmpgo_handle hh, double *F, double *fobj, int32_t *restarts) {
+  H_OR_FAIL(hh);
+  if (F) *F = h->starF;
+  if (fobj) *fobj = h->star_fobj;
+  if (restarts) *restarts = h->star_restarts;
+  return MMPGO_OK;
+}
+
+int mmpgo_get_counters(mmpgo_handle hh, mmpgo_counters *out) {
+  H_OR_FAIL(hh);
+  if (!out) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }
+  *out = h->ctr;
+  return MMPGO_OK;
+}
+int mmpgo_reset_counters(mmpgo_handle hh) {
+  H_OR_FAIL(hh);
+  std::memset(&h->ctr, 0, sizeof(h->ctr));
+  return MMPGO_OK;
+}
+int mmpgo_synchronize(mmpgo_handle hh) {
+  H_OR_FAIL(hh);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) { mmpgo::set_error("stream sync failed"); return MMPGO_ERR_CUDA; }
+  return MMPGO_OK;
+}
+void *mmpgo_stream(mmpgo_handle hh) { return hh ? (void *)hh->h.stream : nullptr; }
+
+int mmpgo_graph_sizes(mmpgo_handle hh, int64_t *sizes /* [8] */) {
+  H_OR_FAIL(hh);
+  if (!sizes || !h->graph_set) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
+  sizes[0] = h->NO; sizes[1] = h->NH; sizes[2] = h->n_intra_entries; sizes[3] = h->n_inter_he;
+  sizes[4] = h->n_edges_owned; sizes[5] = h->n_tiles; sizes[6] = h->A; sizes[7] = h->d;
+  return MMPGO_OK;
+}
+
+}  // extern "C"

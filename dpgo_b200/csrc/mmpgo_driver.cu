@@ -1,0 +1,837 @@
+// Batched host control flow of the per-node drivers: every robot node of the
+// handle advances in lock step through the same kernel launches, with per-node
+// scalars (objective values, step lengths, restart decisions) owned by the host.
+//
+// Restates  DPGOHash::{initialize,update,amm_pgo,mm_pgo,iterate,communicate}
+//             C++/DPGO/src/DPGOHash.cpp:20-628, include/DPGO/DPGOHash.h:28-86
+//           DPGOStar::{initialize,update_n,amm_pgo_n,mm_pgo_n,pm_pgo_n,iterate}
+//             C++/DPGO/src/DPGOStar.cpp:109-711
+//           Optimization::Riemannian::TNT      Optimization/Riemannian/TNT.h:242-693
+//           Optimization::LinearAlgebra::STPCG Optimization/LinearAlgebra/IterativeSolvers.h:166-426
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "mmpgo_driver.cuh"
+
+namespace mmpgo {
+
+#define CK(x)                                                                    \
+  do {                                                                           \
+    cudaError_t e_ = (x);                                                        \
+    if (e_ != cudaSuccess) {                                                     \
+      set_error(std::string(#x) + ": " + cudaGetErrorString(e_));                \
+      return MMPGO_ERR_CUDA;                                                     \
+    }                                                                            \
+  } while (0)
+#define RC(x)                    \
+  do {                           \
+    int rc_ = (x);               \
+    if (rc_) return rc_;         \
+  } while (0)
+
+typedef std::vector<int> Mask;
+
+static inline int PBof(const Handle *h) { return (h->d + 1) * h->d; }
+
+static bool any(const Mask &m) {
+  for (int v : m) if (v) return true;
+  return false;
+}
+static bool all(const Mask &m) {
+  for (int v : m) if (!v) return false;
+  return true;
+}
+static Mask mask_and(const Mask &a, const Mask &b) {
+  Mask r(a.size());
+  for (size_t i = 0; i < a.size(); ++i) r[i] = a[i] && b[i];
+  return r;
+}
+
+// Tiles view with an uploaded node mask (nullptr when all nodes are active).
+static int make_tiles(Handle *h, const Mask &m, Tiles *tl, int *dst = nullptr) {
+  tl->n_tiles = h->n_tiles;
+  tl->node = h->d_tile_node; tl->start = h->d_tile_start; tl->cnt = h->d_tile_cnt;
+  if (all(m)) { tl->active = nullptr; return 0; }
+  int *d = dst ? dst : h->d_active;
+  CK(cudaMemcpyAsync(d, m.data(), sizeof(int) * m.size(), cudaMemcpyHostToDevice, h->stream));
+  tl->active = d;
+  return 0;
+}
+
+// per-node sums of the tile partials -> host
+static int reduce_to_host(Handle *h, const double **out) {
+  launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
+  h->ctr.launches++;
+  CK(cudaMemcpyAsync(h->h_pinned, h->d_node_scal, sizeof(double) * h->A * NS, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h->h_pinned;
+  return 0;
+}
+static int upload_coef(Handle *h, const std::vector<double> &c) {
+  CK(cudaMemcpyAsync(h->d_coef, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+template <int D> struct Drv {
+  static constexpr int PB = (D + 1) * D;
+
+  static GPassArgs gargs(Handle *h, const double *diag = nullptr) {
+    GPassArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.rowptr = h->d_rowptr; a.col = h->d_col; a.blk = h->d_blk;
+    a.diag = diag ? diag : h->d_gdiag; a.partials = h->d_partials;
+    return a;
+  }
+
+  // tr(x^T (g + 1/2 G x)) per node  (evaluate_G without the offset f)
+  static int eval_G(Handle *h, const double *x, const double *g, const Mask &m, std::vector<double> &val) {
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    GPassArgs a = gargs(h);
+    a.x = x; a.g = g;
+    launch_gpass<D>(G_EVAL, tl, a, h->stream);
+    h->ctr.launches++; h->ctr.intra_passes++;
+    const double *s; RC(reduce_to_host(h, &s));
+    val.assign(h->A, 0.0);
+    for (int n = 0; n < h->A; ++n) if (m[n]) val[n] = s[n * NS];
+    return 0;
+  }
+
+  // ---- K2b: G00 u = rhs, then xio.t = -u      (recover_translations, DPGOProblem.h:275-294)
+  static int solve_t(Handle *h, double *xio, const Mask &m, bool warm) {
+    const Mask md = mask_and(m, h->dense_mask), mp = mask_and(m, h->pcg_mask);
+    h->ctr.solve_calls++;
+    if (any(md)) {
+      CK(cudaMemcpyAsync(h->d_active2, md.data(), sizeof(int) * md.size(), cudaMemcpyHostToDevice, h->stream));
+      launch_dense_solve<D>(h->A, h->d_node_off, h->d_dense_off, h->d_active2, h->d_ginv, h->rhs_t, xio,
+                            h->max_dense_n0, h->stream);
+      h->ctr.launches++;
+    }
+    if (any(mp)) {
+      Tiles tl; RC(make_tiles(h, mp, &tl, h->d_active2));
+      SolveArgs sa;
+      sa.rowptr = h->d_rowptr; sa.col = h->d_col; sa.a00 = h->d_a00; sa.d00 = h->d_d00;
+      sa.node_tile_begin = h->d_node_tb; sa.node_tile_end = h->d_node_te;
+      sa.state = h->d_pcg_state;
+      sa.tol2 = h->opt.translation_solve_tol * h->opt.translation_solve_tol;
+      VecArgs va; std::memset(&va, 0, sizeof(va));
+      if (warm) {
+        va.a = xio; va.o1 = h->tsol;
+        launch_vec<D>(V_GET_T, tl, va, h->stream);
+      } else {
+        va.o1 = h->tsol;
+        launch_vec<D>(V_ZERO_C, tl, va, h->stream);
+      }
+      launch_pcg_init<D>(tl, sa, h->rhs_t, h->tsol, h->tsol, h->pr, h->pz, h->pp, h->d_partials, h->stream);
+      launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
+      launch_pcg_scalar(h->A, h->d_node_scal, h->d_pcg_state, 0, sa.tol2, h->stream);
+      h->ctr.launches += 4;
+      int it = 0;
+      const int chunk = 8;
+      bool done = false;
+      while (!done && it < h->opt.translation_solve_max_iters) {
+        for (int c = 0; c < chunk; ++c, ++it) {
+          launch_pcg_spmv<D>(tl, sa, h->pp, h->pap, h->d_partials, 0, h->stream);
+          launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
+          launch_pcg_scalar(h->A, h->d_node_scal, h->d_pcg_state, 1, sa.tol2, h->stream);
+          launch_pcg_update<D>(tl, sa, h->tsol, h->pr, h->pz, h->pp, h->pap, h->d_partials, h->stream);
+          launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
+          launch_pcg_scalar(h->A, h->d_node_scal, h->d_pcg_state, 2, sa.tol2, h->stream);
+          launch_pcg_dir<D>(tl, sa, h->pz, h->pp, h->d_partials, h->stream);
+          h->ctr.launches += 7;
+          h->ctr.solve_iters++;
+        }
+        CK(cudaMemcpyAsync(h->h_pinned, h->d_pcg_state, sizeof(double) * h->A * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        done = true;
+        for (int n = 0; n < h->A; ++n) if (mp[n] && h->h_pinned[n * 8 + 6] != 0.0) done = false;
+      }
+      va.a = h->tsol; va.o1 = xio;
+      launch_vec<D>(V_SET_T, tl, va, h->stream);
+      h->ctr.launches++;
+    }
+    return 0;
+  }
+
+  // t = -G00^{-1} (g_t + G01 Y)   for the rotation rows currently in xio
+  static int recover_t(Handle *h, double *xio, const double *g, const Mask &m, bool warm = true) {
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    GPassArgs a = gargs(h);
+    a.x = xio; a.g = g; a.out = h->rhs_t;
+    launch_gpass<D>(G_RHS_T, tl, a, h->stream);
+    h->ctr.launches++; h->ctr.intra_passes++;
+    return solve_t(h, xio, m, warm);
+  }
+
+  // K3 wrapper
+  static int proximal(Handle *h, const double *xa, const double *xb, const double *dfa, const double *dfb,
+                      const double *ga, const double *gb, double *gex, double *xout, const double *xref,
+                      const Mask &m, std::vector<double> *dist2) {
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    ProxArgs a; std::memset(&a, 0, sizeof(a));
+    a.xa = xa; a.xb = xb; a.dfa = dfa; a.dfb = dfb; a.ga = ga; a.gb = gb; a.gamma = h->d_gamma;
+    a.tnv = h->d_tnv; a.xref = xref; a.xout = xout; a.gex = gex; a.partials = h->d_partials;
+    launch_prox<D>(tl, a, h->stream);
+    h->ctr.launches++; h->ctr.prox_passes++;
+    if (dist2) {
+      const double *s; RC(reduce_to_host(h, &s));
+      dist2->assign(h->A, 0.0);
+      for (int n = 0; n < h->A; ++n) (*dist2)[n] = s[n * NS];
+    }
+    return 0;
+  }
+
+  static int vec(Handle *h, int op, const Mask &m, const double *a_, const double *b_, double *o1, double *o2,
+                 double *o3, double *o4, const double *y) {
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    VecArgs a; std::memset(&a, 0, sizeof(a));
+    a.a = a_; a.b = b_; a.o1 = o1; a.o2 = o2; a.o3 = o3; a.o4 = o4; a.y = y;
+    a.pinv = h->d_pinv; a.precon = h->opt.preconditioner; a.coef = h->d_coef; a.partials = h->d_partials;
+    launch_vec<D>(op, tl, a, h->stream);
+    h->ctr.launches++; h->ctr.vector_passes++;
+    return 0;
+  }
+
+  // Hess[x](p): tdot = -G00^{-1} G01 p_Y; Hp = Proj(Y, (G [tdot; p_Y])_Y - sym(nab Y^T) p_Y)
+  // returns per-node p.Hp, Hp.Hp, p.p        (DPGOProblem.cpp:552-577)
+  static int hess_vec(Handle *h, const double *x, double *p, double *Hp, const Mask &m, std::vector<double> &pHp,
+                      std::vector<double> &HpHp, std::vector<double> &pp) {
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    GPassArgs a = gargs(h);
+    a.x = p; a.g = nullptr; a.out = h->rhs_t;
+    launch_gpass<D>(G_RHS_T, tl, a, h->stream);
+    h->ctr.launches++; h->ctr.intra_passes++;
+    RC(solve_t(h, p, m, false));
+    RC(make_tiles(h, m, &tl));
+    a = gargs(h);
+    a.x = p; a.xref = x; a.nab = h->nab; a.out = Hp;
+    launch_gpass<D>(G_HV, tl, a, h->stream);
+    h->ctr.launches++; h->ctr.intra_passes++;
+    const double *s; RC(reduce_to_host(h, &s));
+    pHp.assign(h->A, 0.0); HpHp.assign(h->A, 0.0); pp.assign(h->A, 0.0);
+    for (int n = 0; n < h->A; ++n) { pHp[n] = s[n * NS]; HpHp[n] = s[n * NS + 1]; pp[n] = s[n * NS + 2]; }
+    return 0;
+  }
+
+  // ---- Steihaug-Toint truncated PCG, all nodes of `m` in lock step.  Result in h->cg_s.
+  static int stpcg(Handle *h, const double *x, const Mask &m, const std::vector<double> &Delta,
+                   std::vector<double> &hMnorm, std::vector<int> &inner) {
+    const int A = h->A;
+    const mmpgo_options &o = h->opt;
+    const double eps = 1e-8;                                      // IterativeSolvers.h:179
+    std::vector<double> rv(A, 0), sk_M_pk(A, 0), sk_M_2(A, 0), pk_M_2(A, 0), target(A, 0), coef((size_t)A * MAXC, 0.0);
+    Mask act = m;
+    hMnorm.assign(A, 0.0); inner.assign(A, 0);
+    RC(vec(h, V_CG_INIT, m, h->grad, nullptr, h->cg_s, h->cg_r, h->cg_v, h->cg_p, x));
+    const double *s; RC(reduce_to_host(h, &s));
+    for (int n = 0; n < A; ++n) if (m[n]) {
+      rv[n] = s[n * NS];
+      pk_M_2[n] = rv[n];
+      const double r0 = std::sqrt(rv[n]);
+      target[n] = r0 * std::min(o.STPCG_kappa, std::pow(r0, o.STPCG_theta));
+    }
+    std::vector<double> kap, HpHp, pp;
+    while (any(act)) {
+      for (int n = 0; n < A; ++n) if (act[n]) {
+        if (inner[n] >= o.max_tCG_iterations || std::sqrt(rv[n]) <= target[n]) {
+          act[n] = 0; hMnorm[n] = std::sqrt(sk_M_2[n]);
+        }
+      }
+      if (!any(act)) break;
+      RC(hess_vec(h, x, h->cg_p, h->cg_Hp, act, kap, HpHp, pp));
+      Mask fin(A, 0), cont(A, 0), kern(A, 0);
+      for (int n = 0; n < A; ++n) if (act[n]) {
+        if (std::sqrt(HpHp[n]) / std::sqrt(pp[n]) < eps) { kern[n] = 1; continue; }
+        const double alpha = rv[n] / kap[n];
+        const double skp1 = sk_M_2[n] + 2 * alpha * sk_M_pk[n] + alpha * alpha * pk_M_2[n];
+        if (kap[n] <= 0 || skp1 > Delta[n] * Delta[n]) {
+          fin[n] = 1;
+          coef[(size_t)n * MAXC + 2] = (-sk_M_pk[n] + std::sqrt(sk_M_pk[n] * sk_M_pk[n] +
+                                        pk_M_2[n] * (Delta[n] * Delta[n] - sk_M_2[n]))) / pk_M_2[n];
+        } else {
+          cont[n] = 1;
+          coef[(size_t)n * MAXC + 0] = alpha;
+          coef[(size_t)n * MAXC + 4] = skp1;
+        }
+      }
+      if (any(kern)) {
+        // search direction in the kernel of H: follow it to the boundary (IterativeSolvers.h:305-333)
+        RC(vec(h, V_DOTS, kern, h->cg_p, h->cg_r, nullptr, nullptr, nullptr, nullptr, nullptr));
+        RC(reduce_to_host(h, &s));
+        for (int n = 0; n < A; ++n) if (kern[n]) {
+          double sgn = 1.0, smp = sk_M_pk[n];
+          if (s[n * NS] < 0) { sgn = -1.0; smp = -smp; }
+          const double sigma = (-smp + std::sqrt(smp * smp + pk_M_2[n] * (Delta[n] * Delta[n] - sk_M_2[n]))) / pk_M_2[n];
+          coef[(size_t)n * MAXC + 2] = sgn * sigma;
+          fin[n] = 1;
+        }
+      }
+      RC(upload_coef(h, coef));
+      if (any(fin)) {
+        RC(vec(h, V_CG_FINAL, fin, h->cg_p, nullptr, h->cg_s, nullptr, nullptr, nullptr, nullptr));
+        for (int n = 0; n < A; ++n) if (fin[n]) { act[n] = 0; hMnorm[n] = Delta[n]; }
+      }
+      if (any(cont)) {
+        RC(vec(h, V_CG_STEP, cont, h->cg_p, h->cg_Hp, h->cg_s, h->cg_r, h->cg_v, nullptr, x));
+        RC(reduce_to_host(h, &s));
+        for (int n = 0; n < A; ++n) if (cont[n]) {
+          const double alpha = coef[(size_t)n * MAXC + 0];
+          const double rk_vk = s[n * NS];
+          const double beta = rk_vk / (alpha * kap[n]);
+          sk_M_2[n] = coef[(size_t)n * MAXC + 4];
+          sk_M_pk[n] = beta * (sk_M_pk[n] + alpha * pk_M_2[n]);
+          pk_M_2[n] = rk_vk + beta * beta * pk_M_2[n];
+          rv[n] = rk_vk;
+          coef[(size_t)n * MAXC + 1] = beta;
+          inner[n]++;
+          h->ctr.tcg_iterations++;
+        }
+        RC(upload_coef(h, coef));
+        RC(vec(h, V_CG_DIR, cont, h->cg_v, nullptr, h->cg_p, nullptr, nullptr, nullptr, nullptr));
+      }
+    }
+    return 0;
+  }
+
+  // ---- truncated-Newton trust region on the nodes of `m`, in place on x.  fval: G(x) without offset.
+  static int tnt(Handle *h, double *x, const double *g, const Mask &m, std::vector<double> &fx) {
+    const int A = h->A;
+    const mmpgo_options &o = h->opt;
+    const double sqrt_eps = std::sqrt(std::numeric_limits<double>::epsilon());
+    std::vector<double> gnorm(A, 0), pgnorm(A, 0), Delta(A, 1.0);   // Delta0 = 1, TNT.h:81
+    std::vector<int> it(A, 0), acc(A, 0);
+    Mask run = m;
+    RC(eval_G(h, x, g, m, fx));
+    auto quad_model = [&](const Mask &mm) -> int {
+      Tiles tl; RC(make_tiles(h, mm, &tl));
+      GPassArgs a = gargs(h);
+      a.x = x; a.g = g; a.out = h->nab; a.out2 = h->grad;
+      launch_gpass<D>(G_REDGRAD, tl, a, h->stream);
+      h->ctr.launches++; h->ctr.intra_passes++;
+      const double *s; RC(reduce_to_host(h, &s));
+      for (int n = 0; n < A; ++n) if (mm[n]) gnorm[n] = std::sqrt(s[n * NS]);
+      if (o.preconditioner != MMPGO_PRECON_NONE) {
+        RC(vec(h, V_PRECOND, mm, h->grad, nullptr, nullptr, nullptr, nullptr, nullptr, x));
+        RC(reduce_to_host(h, &s));
+        for (int n = 0; n < A; ++n) if (mm[n]) pgnorm[n] = std::sqrt(s[n * NS]);
+      } else {
+        for (int n = 0; n < A; ++n) if (mm[n]) pgnorm[n] = gnorm[n];
+      }
+      return 0;
+    };
+    RC(quad_model(m));
+    std::vector<double> hM, sHs, HsHs, ss, fprop;
+    std::vector<int> inner;
+    while (true) {
+      for (int n = 0; n < A; ++n) if (run[n]) {
+        if (it[n] >= o.max_iterations || acc[n] >= o.max_iterations_accepted) run[n] = 0;
+        else if (gnorm[n] < o.grad_norm_tol) run[n] = 0;
+        else if (pgnorm[n] < o.preconditioned_grad_norm_tol) run[n] = 0;
+      }
+      if (!any(run)) break;
+      RC(stpcg(h, x, run, Delta, hM, inner));
+      // trial point: retract, recover translations, evaluate
+      RC(vec(h, V_COPY, run, x, nullptr, h->xprop, nullptr, nullptr, nullptr, nullptr));
+      RC(vec(h, V_RETRACT, run, x, h->cg_s, h->xprop, nullptr, nullptr, nullptr, nullptr));
+      RC(recover_t(h, h->xprop, g, run));
+      RC(eval_G(h, h->xprop, g, run, fprop));
+      // predicted decrease needs grad.h and h.Hess h
+      RC(vec(h, V_DOTS, run, h->grad, h->cg_s, nullptr, nullptr, nullptr, nullptr, nullptr));
+      const double *s; RC(reduce_to_host(h, &s));
+      std::vector<double> gh(A, 0);
+      for (int n = 0; n < A; ++n) gh[n] = s[n * NS];
+      RC(hess_vec(h, x, h->cg_s, h->cg_Hp, run, sHs, HsHs, ss));
+      Mask accm(A, 0), requad(A, 0);
+      for (int n = 0; n < A; ++n) if (run[n]) {
+        h->st[n].tcg_iterations += inner[n];
+        h->st[n].tnt_iterations++;
+        h->ctr.tnt_iterations++;
+        const double h_norm = std::sqrt(ss[n]);
+        const double dm = -gh[n] - 0.5 * sHs[n];
+        const double df = fx[n] - fprop[n];
+        // the reference compares f values that include the constant offset f_k; the
+        // relative decrease uses |f(x)| with that offset (TNT.h:523)
+        const double rel = df / (sqrt_eps + std::fabs(fx[n] + h->st[n].f));
+        const double rho = df / dm;
+        const bool ok = !std::isnan(rho) && rho > 0.05;               // eta1, TNT.h:84
+        bool stop = false;
+        if (ok) {
+          acc[n]++; accm[n] = 1; fx[n] = fprop[n];
+          if (rel < o.rel_func_decrease_tol || h_norm < o.stepsize_tol) stop = true;
+          else if (acc[n] < o.max_iterations_accepted && it[n] + 1 < o.max_iterations) requad[n] = 1;
+        }
+        if (!stop) {
+          if (!std::isnan(rho) && rho >= 0.9) Delta[n] = std::max(2.5 * hM[n], Delta[n]);   // eta2, alpha2
+          else if (std::isnan(rho) || rho < 0.05) {
+            Delta[n] = 0.25 * hM[n];                                                        // alpha1
+            if (Delta[n] < 1e-6) stop = true;                                               // Delta_tolerance
+          }
+        }
+        it[n]++;
+        if (stop) run[n] = 0;
+      }
+      if (any(accm)) RC(vec(h, V_COPY, accm, h->xprop, nullptr, x, nullptr, nullptr, nullptr, nullptr));
+      requad = mask_and(requad, run);
+      if (any(requad)) RC(quad_model(requad));
+    }
+    return 0;
+  }
+
+  // ---- update()  -------------------------------------------------------------------
+  static int update(Handle *h) {
+    const int A = h->A;
+    const mmpgo_options &o = h->opt;
+    Mask m(A, 0);
+    for (int n = 0; n < A; ++n) m[n] = !h->st[n].updated;
+    if (!any(m)) return 0;
+    const bool star = o.algorithm == MMPGO_ALG_STAR;
+    const bool trivial = o.loss == MMPGO_LOSS_NONE;
+    // rotate history: the "current" slot becomes "previous"
+    h->icur ^= 1;
+    double *gk = h->g[h->icur], *Dfk = h->Df[h->icur];
+    const double *Xk = h->X[h->ik], *Xkm1 = h->X[h->ikm1];
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    // DPGOStar::update_n always uses the *_f0 forms (DPGOStar.cpp:337-358)
+    std::vector<int> first(A);
+    for (int n = 0; n < A; ++n) first[n] = star || h->st[n].iters == 0;
+    const bool use_diff = !first[0];
+    InterArgs ia; std::memset(&ia, 0, sizeof(ia));
+    ia.rowptr = h->d_xrowptr; ia.rec = h->d_xrec; ia.xa = Xk; ia.xb = use_diff ? Xkm1 : nullptr;
+    ia.dinter = h->d_dinter; ia.gamma = nullptr; ia.use_diff = use_diff ? 1 : 0;
+    ia.loss = o.loss; ia.loss_reg = o.loss_reg; ia.xi = o.regularizer;
+    ia.g = gk; ia.partials = h->d_partials;
+    if (!trivial) {
+      std::swap(h->w_cur, h->w_prev);
+      ia.w_prev = h->w_prev; ia.w_out = h->w_cur;
+    }
+    launch_inter<D>(trivial ? I_TRIVIAL : I_ROBUST, tl, ia, h->stream);
+    h->ctr.launches++; h->ctr.inter_passes++;
+    const double *s; RC(reduce_to_host(h, &s));
+    std::vector<double> i0(A), i1(A), i2(A), i3(A), i4(A), i5(A);
+    for (int n = 0; n < A; ++n) { i0[n] = s[n*NS]; i1[n] = s[n*NS+1]; i2[n] = s[n*NS+2]; i3[n] = s[n*NS+3]; i4[n] = s[n*NS+4]; i5[n] = s[n*NS+5]; }
+    // gradient pass: Dfobj = g + G x
+    GPassArgs a = gargs(h);
+    a.x = Xk; a.g = gk; a.out = Dfk;
+    RC(make_tiles(h, m, &tl));
+    launch_gpass<D>(G_GRAD, tl, a, h->stream);
+    h->ctr.launches++; h->ctr.intra_passes++;
+    RC(reduce_to_host(h, &s));
+    const double xi = o.regularizer;
+    for (int n = 0; n < A; ++n) if (m[n]) {
+      NodeState &st = h->st[n];
+      const double xgGx = s[n*NS], grad2 = s[n*NS+1], xGx = s[n*NS+2];
+      double fobj, f;
+      if (trivial) {
+        if (first[n]) {
+          f = -i0[n];                    // f0 = 1/2 tr(Z^T P0 Z) = -q(z)        (DPGOProblem.cpp:279)
+          fobj = xgGx + f;               // evaluate_G(Xak, g, f)               (DPGOHash.cpp:111-115)
+        } else {
+          fobj = st.Gk + i0[n];          // G + 1/2 tr(Y^T Q Y)                  (DPGOProblem.cpp:530-531)
+          // f = fobj + 1/2 tr(Z^T P Z);  P = -(intra M) - offdiag(inter) + xi    (:532)
+          const double xAx = xGx - (2.0 * i2[n] + xi * i3[n]);   // x^T (intra M) x
+          f = fobj + (-0.5 * xAx - i1[n] + 0.5 * xi * i3[n]);
+        }
+      } else {
+        const double fobjE = i0[n];
+        if (first[n]) {
+          // f0 = 1/2 fobjE + tr(X^T(1/2 D X - DfobjE))                          (DPGOProblem.cpp:233-244)
+          f = 0.5 * fobjE + (0.5 * i4[n] - i3[n]);
+          fobj = f + xgGx;
+        } else {
+          // fobj = G - 1/2 fobjE0 - 1/2 tr(Y^T(DfobjE0 + 1/2 Q Y)) + 1/2 fobjE      (:387-399)
+          fobj = st.Gk - 0.5 * st.fobjE - 0.5 * (i1[n] + (i2[n] + xi * i5[n])) + 0.5 * fobjE;
+          f = fobj - xgGx;
+        }
+        st.fobjE = fobjE;
+      }
+      st.fobj_prev = st.fobj;
+      st.fobj = fobj; st.f = f;
+      const int iter = st.iters;
+      if (star) st.Gk = fobj;                                                       // DPGOStar.cpp:343
+      if (iter == 0) { st.Fk[0] = st.Fk[1] = fobj; st.Gk = fobj; }                  // DPGOHash.cpp:143-147
+      st.gradFnorm = std::sqrt(grad2);
+      if (o.scheme == MMPGO_SCHEME_AMM) {
+        if (iter == 0) { st.s_cur = 1.0; if (!star) { st.oscillations.clear(); st.oscillations.push_back(1); } }
+        else st.s_cur = st.s_next;
+        st.s_next = 0.5 + 0.5 * std::sqrt(4.0 * st.s_cur * st.s_cur + 1.0);          // :177
+        st.gamma = (st.s_cur - 1.0) / st.s_next;                                    // :179
+        if (!star) {
+          if (fobj <= st.Fk[1]) st.soft_restart_hits[0] = st.soft_restart_hits[0] > 2 ? st.soft_restart_hits[0] - 2 : 0;
+          else st.soft_restart_hits[0]++;
+          if (iter > 0) {
+            if (fobj <= st.fobj_prev) { st.soft_restart_hits[1] = 0; st.oscillations.push_back(1); }
+            else { st.soft_restart_hits[1]++; st.oscillations.push_back(0); }
+            st.num_oscillations += st.oscillations[iter] != st.oscillations[iter - 1];
+          }
+          if (iter > o.oscillation_cnt_period) {
+            const int k = iter - o.oscillation_cnt_period;
+            st.num_oscillations -= st.oscillations[k] != st.oscillations[k - 1];
+          }
+          st.Fk[0] = st.Fk[0] * (1 - o.eta[0]) + fobj * o.eta[0];
+          st.Fk[1] = std::max(fobj, st.Fk[1] * (1 - o.eta[1]) + fobj * o.eta[1]);
+        }
+      } else if (!star) {
+        st.Fk[0] = st.Fk[1] = fobj;
+      }
+      if (star) st.Fk[0] = st.Fk[1] = fobj;                                         // DPGOStar.cpp:384-385
+      st.updated = true;
+    }
+    return 0;
+  }
+
+  static void upload_gamma(Handle *h) {
+    std::vector<double> gm(h->A);
+    for (int n = 0; n < h->A; ++n) gm[n] = h->st[n].iters == 0 ? 0.0 : h->st[n].gamma;
+    cudaMemcpyAsync(h->d_gamma, gm.data(), sizeof(double) * h->A, cudaMemcpyHostToDevice, h->stream);
+  }
+
+  // extrapolated proximal step of amm_pgo / amm_pgo_n: fills Xakh, gex (and Dfex for robust losses)
+  static int amm_proximal(Handle *h, const Mask &m, std::vector<double> *dist2) {
+    const mmpgo_options &o = h->opt;
+    const bool trivial = o.loss == MMPGO_LOSS_NONE;
+    const double *Xk = h->X[h->ik], *Xkm1 = h->X[h->ikm1];
+    const double *gk = h->g[h->icur], *gkm1 = h->g[h->icur ^ 1];
+    const double *Dfk = h->Df[h->icur], *Dfkm1 = h->Df[h->icur ^ 1];
+    const bool it0 = h->st[0].iters == 0;
+    upload_gamma(h);
+    if (it0) {
+      return proximal(h, Xk, nullptr, Dfk, nullptr, gk, nullptr, h->gex, h->Xakh, Xk, m, dist2);
+    }
+    if (trivial) {
+      // g and Df are linear in Z: extrapolate them with gamma (DPGOHash.cpp:259-262)
+      return proximal(h, Xk, Xkm1, Dfk, Dfkm1, gk, gkm1, h->gex, h->Xakh, Xk, m, dist2);
+    }
+    // robust: evaluate_g_and_Df at the extrapolated point (DPGOHash.cpp:264, DPGOProblem.cpp:683-749)
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    InterArgs ia; std::memset(&ia, 0, sizeof(ia));
+    ia.rowptr = h->d_xrowptr; ia.rec = h->d_xrec; ia.xa = Xk; ia.xb = Xkm1; ia.dinter = h->d_dinter;
+    ia.gamma = h->d_gamma; ia.use_diff = 0; ia.loss = o.loss; ia.loss_reg = o.loss_reg; ia.xi = o.regularizer;
+    ia.w_out = h->w_tmp; ia.g = h->gex; ia.yex = h->Yex; ia.partials = h->d_partials;
+    launch_inter<D>(I_ROBUST, tl, ia, h->stream);
+    h->ctr.launches++; h->ctr.inter_passes++;
+    GPassArgs a = gargs(h);
+    a.x = h->Yex; a.g = h->gex; a.out = h->Dfex;
+    launch_gpass<D>(G_GRAD, tl, a, h->stream);
+    h->ctr.launches++; h->ctr.intra_passes++;
+    return proximal(h, h->Yex, nullptr, h->Dfex, nullptr, nullptr, nullptr, nullptr, h->Xakh, Xk, m, dist2);
+  }
+
+  // ---- DPGOHash::amm_pgo for all nodes (DPGOHash.cpp:230-444)
+  static int hash_amm(Handle *h) {
+    const int A = h->A;
+    const mmpgo_options &o = h->opt;
+    const Mask allm(A, 1);
+    const double *Xk = h->X[h->ik];
+    double *Xak = h->X[h->iak];
+    const double *gk = h->g[h->icur], *Dfk = h->Df[h->icur];
+    Mask refined(A, 0);
+    for (int n = 0; n < A; ++n) {
+      const NodeState &st = h->st[n];
+      refined[n] = (((st.gradFnorm * st.gradFnorm / st.fobj) > o.accepted_delta) ||
+                    (st.num_oscillations >= o.max_oscillations)) &&
+                   o.max_iterations > 0 && o.max_iterations_accepted > 0;
+      h->st[n].refined = refined[n];
+    }
+    std::vector<double> dist2, Gkh, Gk, fx;
+    RC(amm_proximal(h, allm, &dist2));
+    RC(eval_G(h, h->Xakh, gk, allm, Gkh));
+    std::vector<double> minG(A);
+    for (int n = 0; n < A; ++n) { Gkh[n] += h->st[n].f; minG[n] = h->st[n].Fk[0] - o.psi * dist2[n]; }
+    // Xak.R = Xakh.R ; t = recover(g_extrapolated)
+    RC(vec(h, V_COPY, allm, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
+    RC(recover_t(h, Xak, h->gex, allm));
+    if (any(refined)) RC(tnt(h, Xak, h->gex, refined, fx));
+    RC(eval_G(h, Xak, gk, allm, Gk));
+    for (int n = 0; n < A; ++n) h->st[n].Gk = Gk[n] + h->st[n].f;
+    // adaptive restart (DPGOHash.cpp:385-389)
+    Mask redo(A, 0);
+    for (int n = 0; n < A; ++n) redo[n] = Gkh[n] > minG[n];
+    if (any(redo)) {
+      RC(proximal(h, Xk, nullptr, Dfk, nullptr, nullptr, nullptr, nullptr, h->Xakh, nullptr, redo, nullptr));
+      std::vector<double> v; RC(eval_G(h, h->Xakh, gk, redo, v));
+      for (int n = 0; n < A; ++n) if (redo[n]) Gkh[n] = v[n] + h->st[n].f;
+    }
+    Mask hard(A, 0), restart(A, 0), use_gk(A, 0);
+    for (int n = 0; n < A; ++n) {
+      const NodeState &st = h->st[n];
+      hard[n] = st.Gk > st.Fk[0];
+      const bool soft = (st.Gk > st.Fk[1] && st.soft_restart_hits[0] >= o.max_soft_restart_hits[0]) ||
+                        (st.Gk > st.fobj && st.soft_restart_hits[1] > o.max_soft_restart_hits[1]);
+      restart[n] = hard[n] || soft;
+    }
+    if (any(restart)) {
+      Mask from_h(A, 0), from_prox(A, 0);
+      for (int n = 0; n < A; ++n) if (restart[n]) {
+        h->st[n].restarts++;
+        use_gk[n] = 1;
+        if (Gkh[n] <= h->st[n].fobj) from_h[n] = 1; else from_prox[n] = 1;
+      }
+      if (any(from_h)) RC(vec(h, V_COPY, from_h, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
+      if (any(from_prox)) RC(proximal(h, Xk, nullptr, Dfk, nullptr, nullptr, nullptr, nullptr, Xak, nullptr, from_prox, nullptr));
+      RC(recover_t(h, Xak, gk, restart));
+      const Mask rr = mask_and(restart, refined);
+      Mask rn(A, 0);
+      for (int n = 0; n < A; ++n) rn[n] = restart[n] && !refined[n];
+      if (any(rr)) {
+        RC(tnt(h, Xak, gk, rr, fx));
+        for (int n = 0; n < A; ++n) if (rr[n]) h->st[n].Gk = fx[n] + h->st[n].f;
+      }
+      if (any(rn)) {
+        std::vector<double> v; RC(eval_G(h, Xak, gk, rn, v));
+        for (int n = 0; n < A; ++n) if (rn[n]) h->st[n].Gk = v[n] + h->st[n].f;
+      }
+      for (int n = 0; n < A; ++n) if (restart[n]) {
+        if (hard[n]) h->st[n].s_next = std::max(0.5 * h->st[n].s_next, 1.0);
+        h->st[n].soft_restart_hits[0] /= 3;
+        h->st[n].soft_restart_hits[1] = 0;
+      }
+    }
+    // final safeguard (DPGOHash.cpp:434-441)
+    Mask safe(A, 0);
+    for (int n = 0; n < A; ++n) {
+      const NodeState &st = h->st[n];
+      safe[n] = (st.Fk[0] - st.Gk) < o.phi * (st.Fk[0] - Gkh[n]);
+    }
+    if (any(safe)) {
+      RC(vec(h, V_COPY_ROT, safe, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
+      const Mask s1 = mask_and(safe, use_gk);
+      Mask s2(A, 0);
+      for (int n = 0; n < A; ++n) s2[n] = safe[n] && !use_gk[n];
+      if (any(s1)) RC(recover_t(h, Xak, gk, s1));
+      if (any(s2)) RC(recover_t(h, Xak, h->gex, s2));
+      std::vector<double> v; RC(eval_G(h, Xak, gk, safe, v));
+      for (int n = 0; n < A; ++n) if (safe[n]) h->st[n].Gk = v[n] + h->st[n].f;
+    }
+    return 0;
+  }
+
+  // ---- DPGOHash::mm_pgo for all nodes (DPGOHash.cpp:446-581)
+  static int hash_mm(Handle *h) {
+    const int A = h->A;
+    const mmpgo_options &o = h->opt;
+    const Mask allm(A, 1);
+    const double *Xk = h->X[h->ik];
+    double *Xak = h->X[h->iak];
+    const double *gk = h->g[h->icur], *Dfk = h->Df[h->icur];
+    Mask refined(A, 0), plain(A, 0);
+    for (int n = 0; n < A; ++n) {
+      const NodeState &st = h->st[n];
+      refined[n] = ((st.gradFnorm * st.gradFnorm / st.fobj) > o.accepted_delta) && o.max_iterations > 0 &&
+                   o.max_iterations_accepted > 0;
+      plain[n] = !refined[n];
+      h->st[n].refined = refined[n];
+    }
+    RC(proximal(h, Xk, nullptr, Dfk, nullptr, nullptr, nullptr, nullptr, h->Xakh, nullptr, allm, nullptr));
+    RC(recover_t(h, h->Xakh, gk, allm));
+    RC(vec(h, V_COPY, allm, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
+    std::vector<double> fx;
+    if (any(refined)) {
+      RC(tnt(h, Xak, gk, refined, fx));
+      for (int n = 0; n < A; ++n) if (refined[n]) h->st[n].Gk = fx[n] + h->st[n].f;
+    }
+    if (any(plain)) {
+      std::vector<double> v; RC(eval_G(h, Xak, gk, plain, v));
+      for (int n = 0; n < A; ++n) if (plain[n]) h->st[n].Gk = v[n] + h->st[n].f;
+    }
+    return 0;
+  }
+
+  // global objective of a candidate iterate held in pose blocks (own + halo rows)
+  static int edge_objective(Handle *h, const double *x, double *f) {
+    int nb = 0;
+    launch_edge_objective<D>(h->n_edges_owned, h->d_erec, x, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
+                             &nb, h->stream);
+    launch_sum_blocks(nb, h->d_block_partials, h->d_scalar, h->stream);
+    h->ctr.launches += 2; h->ctr.inter_passes++;
+    CK(cudaMemcpyAsync(h->h_pinned, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *f = h->h_pinned[0];
+    return 0;
+  }
+  static int diff2(Handle *h, const double *a, const double *b, double *out) {
+    const Mask allm(h->A, 1);
+    RC(vec(h, V_DIFFNORM, allm, a, b, nullptr, nullptr, nullptr, nullptr, nullptr));
+    const double *s; RC(reduce_to_host(h, &s));
+    double t = 0.0;
+    for (int n = 0; n < h->A; ++n) t += s[n * NS];
+    *out = t;
+    return 0;
+  }
+
+  // ---- DPGOStar::iterate (DPGOStar.cpp:126-213), single-handle form (all nodes local)
+  static int star_iterate(Handle *h) {
+    const int A = h->A;
+    const mmpgo_options &o = h->opt;
+    const Mask allm(A, 1);
+    const double *Xk = h->X[h->ik];
+    double *Xak = h->X[h->iak];      // X^{k+1} candidate ("Xkp")
+    const double *gk = h->g[h->icur], *Dfk = h->Df[h->icur];
+    Mask refined(A, 0), plain(A, 0);
+    for (int n = 0; n < A; ++n) {
+      const NodeState &st = h->st[n];
+      refined[n] = (st.gradFnorm * st.gradFnorm / st.fobj) > o.accepted_delta;     // DPGOStar.cpp:515-516
+      plain[n] = !refined[n];
+      h->st[n].refined = refined[n];
+    }
+    std::vector<double> fx;
+    // amm_pgo_n for all nodes
+    RC(amm_proximal(h, allm, nullptr));
+    RC(vec(h, V_COPY, allm, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
+    RC(recover_t(h, Xak, h->gex, allm));
+    if (any(refined) && o.max_iterations > 0 && o.max_iterations_accepted > 0) RC(tnt(h, Xak, h->gex, refined, fx));
+    double fobjh, fobj, dh, dp;
+    RC(edge_objective(h, h->Xakh, &fobjh));
+    RC(diff2(h, h->Xakh, Xk, &dh));
+    if (fobjh > h->starF - o.psi * dh) {
+      // pm_pgo_n: plain proximal from Xk (DPGOStar.cpp:685-711)
+      RC(proximal(h, Xk, nullptr, Dfk, nullptr, nullptr, nullptr, nullptr, h->Xakh, nullptr, allm, nullptr));
+      RC(edge_objective(h, h->Xakh, &fobjh));
+    }
+    RC(edge_objective(h, Xak, &fobj));
+    RC(diff2(h, Xak, Xk, &dp));
+    if (fobj > h->starF - o.psi * dp) {
+      // global restart: mm_pgo_n for all nodes + halve s (DPGOStar.cpp:159-169)
+      h->star_restarts++;
+      RC(vec(h, V_COPY_ROT, allm, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
+      RC(recover_t(h, Xak, gk, allm));
+      if (any(refined) && o.max_iterations > 0 && o.max_iterations_accepted > 0) {
+        RC(tnt(h, Xak, gk, refined, fx));
+        for (int n = 0; n < A; ++n) if (refined[n]) h->st[n].Gk = fx[n] + h->st[n].f;
+      }
+      if (any(plain)) {
+        std::vector<double> v; RC(eval_G(h, Xak, gk, plain, v));
+        for (int n = 0; n < A; ++n) if (plain[n]) h->st[n].Gk = v[n] + h->st[n].f;
+      }
+      for (int n = 0; n < A; ++n) { h->st[n].s_next = std::max(0.5 * h->st[n].s_next, 1.0); h->st[n].restarts++; }
+      RC(edge_objective(h, Xak, &fobj));
+    }
+    if (h->starF - fobj < o.phi * (h->starF - fobjh)) {
+      RC(vec(h, V_COPY_ROT, allm, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
+      RC(recover_t(h, Xak, gk, allm));
+      RC(edge_objective(h, Xak, &fobj));
+    }
+    h->star_fobj = fobj;
+    h->starF = h->starF * (1 - o.eta[0]) + fobj * o.eta[0];
+    return 0;
+  }
+
+  static int iterate(Handle *h) {
+    for (int n = 0; n < h->A; ++n)
+      if (!h->st[n].updated) { set_error("iterate() before update()"); return MMPGO_ERR_STATE; }
+    if (h->opt.algorithm == MMPGO_ALG_STAR) RC(star_iterate(h));
+    else if (h->opt.scheme == MMPGO_SCHEME_AMM) RC(hash_amm(h));
+    else RC(hash_mm(h));
+    for (int n = 0; n < h->A; ++n) { h->st[n].iters++; h->st[n].updated = false; }
+    return 0;
+  }
+
+  // publish X^{k+1}: the reference copies Xak into the head of Xk at the end of iterate()
+  // (DPGOHash.cpp:612-616) and neighbours pick it up in communicate(); on the device the
+  // three pose buffers rotate instead.
+  static int communicate(Handle *h) {
+    const int old_km1 = h->ikm1;
+    h->ikm1 = h->ik; h->ik = h->iak; h->iak = old_km1;
+    return 0;
+  }
+};
+
+// ---- layout conversion between the reference's global X and device pose blocks ------
+static void pack_pose(int d, const double *X, int64_t ldx, int64_t N, int64_t gid, double *blk) {
+  for (int c = 0; c < d; ++c) blk[c] = X[gid + c * ldx];
+  for (int r = 0; r < d; ++r)
+    for (int c = 0; c < d; ++c) blk[(1 + r) * d + c] = X[N + d * gid + r + c * ldx];
+}
+static void unpack_pose(int d, double *X, int64_t ldx, int64_t N, int64_t gid, const double *blk) {
+  for (int c = 0; c < d; ++c) X[gid + c * ldx] = blk[c];
+  for (int r = 0; r < d; ++r)
+    for (int c = 0; c < d; ++c) X[N + d * gid + r + c * ldx] = blk[(1 + r) * d + c];
+}
+static void pack_all(Handle *h, const double *X, int64_t ldx, std::vector<double> &buf) {
+  const int PB = PBof(h);
+  buf.resize((size_t)h->NP * PB);
+  for (int p = 0; p < h->NO; ++p) pack_pose(h->d, X, ldx, h->N, h->own_gid[p], &buf[(size_t)p * PB]);
+  for (int k = 0; k < h->NH; ++k) pack_pose(h->d, X, ldx, h->N, h->halo_gid[k], &buf[(size_t)(h->NO + k) * PB]);
+}
+
+int driver_initialize(Handle *h, const double *X, int64_t ldx) {
+  if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
+  if (ldx < (int64_t)(h->d + 1) * h->N) { set_error("ldx too small"); return MMPGO_ERR_ARG; }
+  std::vector<double> buf;
+  pack_all(h, X, ldx, buf);
+  h->ik = 0; h->ikm1 = 1; h->iak = 2; h->icur = 0;
+  for (int k = 0; k < 3; ++k)
+    CK(cudaMemcpyAsync(h->X[k], buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->Xakh, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->xprop, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (auto &s : h->st) { s = NodeState(); s.updated = false; }
+  h->star_restarts = 0;
+  if (h->opt.algorithm == MMPGO_ALG_STAR) {
+    double f = 0.0;
+    int rc = h->d == 2 ? Drv<2>::edge_objective(h, h->X[h->ik], &f) : Drv<3>::edge_objective(h, h->X[h->ik], &f);
+    if (rc) return rc;
+    h->star_fobj = f; h->starF = f;                                   // DPGOStar.cpp:120-122
+  }
+  h->initialized = true;
+  return 0;
+}
+
+int driver_update(Handle *h) {
+  if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
+  return h->d == 2 ? Drv<2>::update(h) : Drv<3>::update(h);
+}
+int driver_iterate(Handle *h) {
+  if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
+  return h->d == 2 ? Drv<2>::iterate(h) : Drv<3>::iterate(h);
+}
+int driver_communicate(Handle *h) {
+  if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
+  return h->d == 2 ? Drv<2>::communicate(h) : Drv<3>::communicate(h);
+}
+
+int driver_get_poses(Handle *h, double *X, int64_t ldx) {
+  if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
+  const int PB = PBof(h);
+  std::vector<double> buf((size_t)h->NO * PB);
+  CK(cudaMemcpyAsync(buf.data(), h->X[h->ik], buf.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < h->NO; ++p) unpack_pose(h->d, X, ldx, h->N, h->own_gid[p], &buf[(size_t)p * PB]);
+  return 0;
+}
+
+int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *count) {
+  if (node < h->node_begin || node >= h->node_end) { set_error("node not local"); return MMPGO_ERR_ARG; }
+  const NodeInfo &ni = h->info[node - h->node_begin];
+  *count = (int64_t)ni.inter_he.size();
+  if (!w) return 0;
+  if (cap < *count) { set_error("weight buffer too small"); return MMPGO_ERR_ARG; }
+  std::vector<double> all((size_t)h->n_inter_he);
+  if (h->opt.loss == MMPGO_LOSS_NONE) {
+    for (int64_t k = 0; k < *count; ++k) w[k] = 1.0;
+    return 0;
+  }
+  CK(cudaMemcpyAsync(all.data(), h->w_cur, all.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int64_t k = 0; k < *count; ++k) w[k] = all[ni.inter_he[k]];
+  return 0;
+}
+
+int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f) {
+  if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
+  std::vector<double> buf;
+  pack_all(h, X, ldx, buf);
+  CK(cudaMemcpyAsync(h->xeval, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return h->d == 2 ? Drv<2>::edge_objective(h, h->xeval, f) : Drv<3>::edge_objective(h, h->xeval, f);
+}
+
+int driver_current_objective(Handle *h, double *f, double *g2) {
+  if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
+  // sum_a fobj_a = F (DPGOStar.cpp:719-722 vs DPGOHash.cpp:108-118); |grad F|^2 = sum_a |gradF_a|^2
+  double sf = 0.0, sg = 0.0;
+  for (const auto &s : h->st) { sf += s.fobj; sg += s.gradFnorm * s.gradFnorm; }
+  *f = sf; *g2 = sg;
+  return 0;
+}
+
+}  // namespace mmpgo

@@ -1,0 +1,128 @@
+// Host-side driver state of libmmpgo (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mmpgo.h"
+#include "mmpgo_kernels.cuh"
+
+namespace mmpgo {
+
+// DPGOResult (C++/DPGO/include/DPGO/DPGO_types.h:204-322), the scalars only;
+// iterates k and k-1 live on the device.
+struct NodeState {
+  bool updated = true;
+  int iters = 0;
+  int soft_restart_hits[2] = {0, 0};
+  std::vector<int> oscillations;
+  int num_oscillations = 0;
+  double gamma = 0.0;
+  double s_cur = 1.0, s_next = 1.0;
+  double Fk[2] = {0.0, 0.0};
+  double Gk = 0.0;
+  double fobj = 0.0, fobj_prev = 0.0, f = 0.0;
+  double fobjE = 0.0;
+  double gradFnorm = 0.0;
+  bool refined = false;
+  int restarts = 0, tcg_iterations = 0, tnt_iterations = 0;
+};
+
+struct NodeInfo {
+  int n0 = 0, n1 = 0, m0 = 0, m1 = 0;
+  int64_t first_gid = 0;
+  std::vector<int> inter_he;   // half-edge ids in inter_measurements() order
+  bool dense = false;
+};
+
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+};
+
+struct Handle {
+  mmpgo_options opt;
+  int d = 0;
+  cudaStream_t stream = nullptr;
+  bool graph_set = false, initialized = false;
+  // graph / partition
+  int64_t N = 0;
+  int num_nodes = 0, node_begin = 0, node_end = 0, A = 0;
+  std::vector<int> node_off;          // [A+1] own pose offsets
+  std::vector<int64_t> own_gid;       // [NO] global id of own pose
+  std::vector<int64_t> halo_gid;      // [NH] global id of halo pose
+  std::vector<int> halo_owner;        // [NH] owning node
+  int NO = 0, NH = 0, NP = 0;
+  std::vector<NodeInfo> info;
+  std::vector<NodeState> st;
+  int64_t n_intra_entries = 0, n_inter_he = 0, n_edges_owned = 0;
+  // tiles
+  int n_tiles = 0;
+  std::vector<int> h_tile_node, h_node_tb, h_node_te;
+  int *d_tile_node = nullptr, *d_tile_start = nullptr, *d_tile_cnt = nullptr;
+  int *d_node_tb = nullptr, *d_node_te = nullptr, *d_node_off = nullptr;
+  int *d_active = nullptr;            // [A] current mask
+  int *d_active2 = nullptr;
+  // static operators
+  int *d_rowptr = nullptr, *d_col = nullptr;
+  double *d_blk = nullptr, *d_gdiag = nullptr, *d_dintra = nullptr, *d_dinter = nullptr;
+  double *d_tnv = nullptr, *d_pinv = nullptr;
+  double *d_a00 = nullptr, *d_d00 = nullptr;
+  int *d_xrowptr = nullptr;
+  InterRec *d_xrec = nullptr;
+  EdgeRec *d_erec = nullptr;
+  double *d_ginv = nullptr;
+  long long *d_dense_off = nullptr;
+  int max_dense_n0 = 0;
+  bool any_dense = false, any_pcg = false;
+  std::vector<int> dense_mask, pcg_mask;
+  // pose vectors (NP x PB)
+  double *X[3] = {nullptr, nullptr, nullptr};   // rotating: Xk, Xkm1, Xak
+  int ik = 0, ikm1 = 1, iak = 2;
+  double *Xakh = nullptr, *Yex = nullptr, *xprop = nullptr, *xeval = nullptr;
+  // own-sized vectors
+  double *g[2] = {nullptr, nullptr}, *Df[2] = {nullptr, nullptr};
+  int icur = 0;
+  double *gex = nullptr, *Dfex = nullptr, *nab = nullptr, *grad = nullptr;
+  double *cg_s = nullptr, *cg_r = nullptr, *cg_v = nullptr, *cg_p = nullptr, *cg_Hp = nullptr;
+  // compact (NO x D)
+  double *rhs_t = nullptr, *tsol = nullptr, *pr = nullptr, *pz = nullptr, *pp = nullptr, *pap = nullptr;
+  double *d_pcg_state = nullptr;
+  // per half-edge
+  double *w_cur = nullptr, *w_prev = nullptr, *w_tmp = nullptr;
+  // scalars
+  double *d_partials = nullptr, *d_node_scal = nullptr, *d_coef = nullptr, *d_gamma = nullptr;
+  double *d_block_partials = nullptr, *d_scalar = nullptr;
+  double *h_pinned = nullptr;   // pinned staging (A*NS + A*MAXC + misc)
+  int *h_pinned_i = nullptr;
+  // AMM-PGO* global state (DPGOStar.cpp:126-213)
+  double starF = 0.0, star_fobj = 0.0;
+  int star_restarts = 0;
+  // halo exchange
+  int rank = 0, world = 1;
+  std::vector<int> node_owner;
+  std::vector<int64_t> send_counts, recv_counts;
+  int *d_send_idx = nullptr, *d_recv_idx = nullptr;
+  int64_t n_send = 0, n_recv = 0;
+  double *d_send = nullptr, *d_recv = nullptr;
+  mmpgo_counters ctr;
+  std::vector<void *> allocs;
+};
+
+int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne, int64_t E, const int32_t *ei,
+                     const int32_t *ej, const double *R, const double *t, const double *kappa,
+                     const double *tau);
+int driver_initialize(Handle *h, const double *X, int64_t ldx);
+int driver_update(Handle *h);
+int driver_iterate(Handle *h);
+int driver_communicate(Handle *h);
+int driver_get_poses(Handle *h, double *X, int64_t ldx);
+int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *count);
+int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f);
+int driver_current_objective(Handle *h, double *f, double *g2);
+void driver_free(Handle *h);
+void set_error(const std::string &s);
+
+}  // namespace mmpgo

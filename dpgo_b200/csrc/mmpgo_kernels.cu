@@ -1,0 +1,1153 @@
+// Hand-written sm_100a FP64 kernels of the MM-PGO / AMM-PGO iteration.
+// See mmpgo_kernels.cuh for the data model and DESIGN.md for the rooflines.
+#include "mmpgo_kernels.cuh"
+#include "so3_project.cuh"
+
+namespace mmpgo {
+
+template <int D> struct Dim {
+  static constexpr int R = D + 1;
+  static constexpr int PB = (D + 1) * D;
+  static constexpr int BB = (D + 1) * (D + 1);
+  static constexpr int SYM = (D + 1) * (D + 2) / 2;
+  static constexpr int TNV = 1 + D + D * D;
+};
+
+__device__ __forceinline__ int symidx(int r, int c) {
+  return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r;
+}
+
+// Deterministic block reduction of K scalars per thread: fixed shuffle tree
+// inside each warp, then warp 0 adds the warp results in warp order.
+template <int K, int NT>
+__device__ __forceinline__ void block_reduce_store(double (&v)[K], double *dst) {
+  constexpr int NW = (NT + 31) / 32;
+  __shared__ double red[NW][K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) red[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) x += red[w][threadIdx.x];
+    dst[threadIdx.x] = x;
+  }
+}
+
+// P = V - sym(V Y^T) Y for one pose, row r of the d x d block  (SOdProduct.h:64-103)
+template <int D>
+__device__ __forceinline__ void proj_row(const double *V, const double *Y, int r, double *out) {
+  // S[r][c] = 0.5 (V_r . Y_c + Y_r . V_c)
+  double S[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      a += V[r * D + k] * Y[c * D + k];
+      b += Y[r * D + k] * V[c * D + k];
+    }
+    S[c] = 0.5 * (a + b);
+  }
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc += S[c] * Y[c * D + k];
+    out[k] = V[r * D + k] - acc;
+  }
+}
+
+// =============================================================================
+// K2: block-CSR pass.  (d+1) threads per pose, thread `row` owns one output row.
+// =============================================================================
+template <int D, int MODE>
+__global__ void __launch_bounds__(TILE *(D + 1))
+k_gpass(Tiles tl, GPassArgs a) {
+  constexpr int R = Dim<D>::R, PB = Dim<D>::PB, BB = Dim<D>::BB, SYM = Dim<D>::SYM;
+  constexpr int NT = TILE * R;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int pl = threadIdx.x / R, row = threadIdx.x % R;
+  const int cnt = tl.cnt[tile];
+  const int p = tl.start[tile] + pl;
+  const bool valid = pl < cnt;
+  // which input rows participate: G_RHS_T uses rotation rows only (G01)
+  constexpr int K0 = (MODE == G_RHS_T) ? 1 : 0;
+  const bool row_on = (MODE == G_RHS_T) ? (row == 0)
+                    : (MODE == G_REDGRAD || MODE == G_HV) ? (row >= 1) : true;
+
+  double acc[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) acc[c] = 0.0;
+  double xp[PB];
+  if (valid) {
+    const double *xpp = a.x + (size_t)p * PB;
+#pragma unroll
+    for (int k = 0; k < PB; ++k) xp[k] = xpp[k];
+  }
+  if (valid && row_on) {
+    const int e0 = a.rowptr[p], e1 = a.rowptr[p + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int q = __ldg(a.col + e);
+      const double *b = a.blk + (size_t)e * BB + row * R;
+      const double *xq = a.x + (size_t)q * PB;
+      double br[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) br[k] = __ldg(b + k);
+#pragma unroll
+      for (int k = K0; k < R; ++k) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = fma(br[k], __ldg(xq + k * D + c), acc[c]);
+      }
+    }
+    const double *dg = a.diag + (size_t)p * SYM;
+#pragma unroll
+    for (int k = K0; k < R; ++k) {
+      const double dv = dg[symidx(row, k)];
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[c] = fma(dv, xp[k * D + c], acc[c]);
+    }
+  }
+
+  double sc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (MODE == G_EVAL) {
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double gv = a.g ? a.g[(size_t)p * PB + row * D + c] : 0.0;
+        sc[0] += xp[row * D + c] * (gv + 0.5 * acc[c]);
+      }
+    }
+    block_reduce_store<1, NT>(reinterpret_cast<double(&)[1]>(sc), a.partials + (size_t)tile * NS);
+    return;
+  }
+  if (MODE == G_RHS_T) {
+    if (valid && row == 0) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double gv = a.g ? a.g[(size_t)p * PB + c] : 0.0;
+        a.out[(size_t)p * D + c] = gv + acc[c];
+      }
+    }
+    return;
+  }
+  // modes that need the whole pose block of the result: stage in shared memory
+  __shared__ double sV[TILE][PB];
+  if (MODE == G_GRAD) {
+    double v[D];
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double gv = a.g[(size_t)p * PB + row * D + c];
+        v[c] = gv + acc[c];
+        a.out[(size_t)p * PB + row * D + c] = v[c];
+        sV[pl][row * D + c] = v[c];
+        sc[0] += xp[row * D + c] * (gv + 0.5 * acc[c]);
+        sc[2] += xp[row * D + c] * acc[c];
+        sc[3] += xp[row * D + c] * gv;
+      }
+    }
+    __syncthreads();
+    if (valid) {
+      if (row == 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) sc[1] += v[c] * v[c];
+      } else {
+        double pr[D];
+        proj_row<D>(&sV[pl][D], xp + D, row - 1, pr);
+#pragma unroll
+        for (int c = 0; c < D; ++c) sc[1] += pr[c] * pr[c];
+      }
+    }
+    block_reduce_store<4, NT>(sc, a.partials + (size_t)tile * NS);
+    return;
+  }
+  if (MODE == G_REDGRAD) {
+    if (valid && row >= 1) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double v = a.g[(size_t)p * PB + row * D + c] + acc[c];
+        a.out[(size_t)p * PB + row * D + c] = v;
+        sV[pl][row * D + c] = v;
+      }
+    }
+    __syncthreads();
+    if (valid && row >= 1) {
+      double pr[D];
+      proj_row<D>(&sV[pl][D], xp + D, row - 1, pr);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        a.out2[(size_t)p * PB + row * D + c] = pr[c];
+        sc[0] += pr[c] * pr[c];
+      }
+    }
+    block_reduce_store<1, NT>(reinterpret_cast<double(&)[1]>(sc), a.partials + (size_t)tile * NS);
+    return;
+  }
+  if (MODE == G_HV) {
+    // xp holds the direction p = [tdot; Rdot]; Y and nab come from xref / nab
+    double Y[D * D], NB[D * D];
+    if (valid) {
+      const double *yp = a.xref + (size_t)p * PB + D;
+      const double *np = a.nab + (size_t)p * PB + D;
+#pragma unroll
+      for (int k = 0; k < D * D; ++k) { Y[k] = yp[k]; NB[k] = np[k]; }
+    }
+    if (valid && row >= 1) {
+      // E_r = acc - (sym(nab Y^T) Rdot)_r     (SymBlockDiagProduct, SOdProduct.h:64-89)
+      const int r = row - 1;
+      double S[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double u = 0.0, w = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          u += NB[r * D + k] * Y[c * D + k];
+          w += Y[r * D + k] * NB[c * D + k];
+        }
+        S[c] = 0.5 * (u + w);
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) t += S[c] * xp[(1 + c) * D + k];
+        sV[pl][row * D + k] = acc[k] - t;
+      }
+    }
+    __syncthreads();
+    if (valid) {
+      if (row >= 1) {
+        double pr[D];
+        proj_row<D>(&sV[pl][D], Y, row - 1, pr);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          a.out[(size_t)p * PB + row * D + c] = pr[c];
+          const double pv = xp[row * D + c];
+          sc[0] += pv * pr[c];
+          sc[1] += pr[c] * pr[c];
+          sc[2] += pv * pv;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) a.out[(size_t)p * PB + c] = 0.0;
+      }
+    }
+    block_reduce_store<3, NT>(reinterpret_cast<double(&)[3]>(sc), a.partials + (size_t)tile * NS);
+    return;
+  }
+}
+
+template <int D> void launch_gpass(int mode, const Tiles &tl, const GPassArgs &a, cudaStream_t s) {
+  const dim3 grid(tl.n_tiles), block(TILE * (D + 1));
+  switch (mode) {
+    case G_EVAL: k_gpass<D, G_EVAL><<<grid, block, 0, s>>>(tl, a); break;
+    case G_GRAD: k_gpass<D, G_GRAD><<<grid, block, 0, s>>>(tl, a); break;
+    case G_RHS_T: k_gpass<D, G_RHS_T><<<grid, block, 0, s>>>(tl, a); break;
+    case G_REDGRAD: k_gpass<D, G_REDGRAD><<<grid, block, 0, s>>>(tl, a); break;
+    case G_HV: k_gpass<D, G_HV><<<grid, block, 0, s>>>(tl, a); break;
+  }
+}
+template void launch_gpass<2>(int, const Tiles &, const GPassArgs &, cudaStream_t);
+template void launch_gpass<3>(int, const Tiles &, const GPassArgs &, cudaStream_t);
+
+// =============================================================================
+// K1: inter-node edge pass.  One thread per own pose; its half-edges are
+// contiguous 128-byte records.
+// =============================================================================
+__device__ __forceinline__ double irls_weight(int loss, double e, double delta, double &rho) {
+  // DPGOProblem.cpp:647-675; rho is the edge's contribution to fobjE
+  if (loss == 0) { rho = 0.5 * e; return 1.0; }
+  if (loss == 1) {  // Huber
+    const double sq = sqrt(delta);
+    const double resc = sqrt(fmax(e, delta));
+    rho = 0.5 * fmin(2.0 * sq * resc - delta, e);
+    return sq / resc;
+  }
+  if (loss == 2) {  // Geman-McClure
+    const double s = e + delta;
+    rho = 0.5 * delta * (e / s);
+    return (delta * delta) / (s * s);
+  }
+  const double w = exp(-e / delta);  // Welsch
+  rho = 0.5 * (delta - delta * w);
+  return w;
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(TILE) k_inter(Tiles tl, InterArgs a) {
+  constexpr int PB = Dim<D>::PB, SYM = Dim<D>::SYM;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int pl = threadIdx.x;
+  const int p = tl.start[tile] + pl;
+  const bool valid = pl < tl.cnt[tile];
+  const double gam = (a.gamma && a.xb) ? a.gamma[node] : 0.0;
+  double sc[6] = {0, 0, 0, 0, 0, 0};
+  if (valid) {
+    // own pose: z (possibly extrapolated), previous z0, v (= z or z - z0)
+    double z[PB], z0[PB], acc[PB];
+    const double *pa = a.xa + (size_t)p * PB;
+#pragma unroll
+    for (int k = 0; k < PB; ++k) { z[k] = pa[k]; z0[k] = 0.0; acc[k] = 0.0; }
+    if (a.xb) {
+      const double *pb = a.xb + (size_t)p * PB;
+#pragma unroll
+      for (int k = 0; k < PB; ++k) z0[k] = pb[k];
+      if (a.gamma) {
+#pragma unroll
+        for (int k = 0; k < PB; ++k) z[k] = z[k] + gam * (z[k] - z0[k]);
+      }
+    }
+    if (a.yex) {
+#pragma unroll
+      for (int k = 0; k < PB; ++k) a.yex[(size_t)p * PB + k] = z[k];
+    }
+    const int e0 = a.rowptr[p], e1 = a.rowptr[p + 1];
+    for (int he = e0; he < e1; ++he) {
+      const InterRec *r = a.rec + he;
+      const int q = r->other;
+      const int own_i = r->own_is_i;
+      const double tau = r->tau, kap = r->kappa;
+      double t[D], Rm[D * D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) t[k] = r->t[k];
+#pragma unroll
+      for (int k = 0; k < D * D; ++k) Rm[k] = r->R[k];
+      double zq[PB], zq0[PB];
+      const double *qa = a.xa + (size_t)q * PB;
+#pragma unroll
+      for (int k = 0; k < PB; ++k) { zq[k] = qa[k]; zq0[k] = 0.0; }
+      if (a.xb) {
+        const double *qb = a.xb + (size_t)q * PB;
+#pragma unroll
+        for (int k = 0; k < PB; ++k) zq0[k] = qb[k];
+        if (a.gamma) {
+#pragma unroll
+          for (int k = 0; k < PB; ++k) zq[k] = zq[k] + gam * (zq[k] - zq0[k]);
+        }
+      }
+      // role-resolved views: (xi, xj) of the edge i -> j
+      const double *xi = own_i ? z : zq, *xj = own_i ? zq : z;
+      const double *xi0 = own_i ? z0 : zq0, *xj0 = own_i ? zq0 : z0;
+      if (MODE == I_TRIVIAL) {
+        // off-diagonal block product (M-form, DPGO_utils.cpp:1964-2028 for S)
+        //   own = i: [-tau t_j ; -tau t t_j - kappa R Y_j]
+        //   own = j: [-tau (t_i + t^T Y_i) ; -kappa R^T Y_i]
+        double c[PB];
+        if (own_i) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) c[k] = -tau * zq[k];
+#pragma unroll
+          for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              double s = 0.0;
+#pragma unroll
+              for (int cc = 0; cc < D; ++cc) s += Rm[rr * D + cc] * zq[(1 + cc) * D + k];
+              c[(1 + rr) * D + k] = -tau * t[rr] * zq[k] - kap * s;
+            }
+        } else {
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            double s = zq[k];
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) s += t[cc] * zq[(1 + cc) * D + k];
+            c[k] = -tau * s;
+          }
+#pragma unroll
+          for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              double s = 0.0;
+#pragma unroll
+              for (int cc = 0; cc < D; ++cc) s += Rm[cc * D + rr] * zq[(1 + cc) * D + k];
+              c[(1 + rr) * D + k] = -kap * s;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PB; ++k) acc[k] += c[k];
+        // q(v) = sum_e [1/2 v_o.(M_on v_n) - 1/4 v_n^T M_nn v_n] - 1/4 v_o^T Dinter v_o - xi/2 |v_o|^2
+        // with v = z (first update: f0 = -q(z)) or v = z - z0 (Q-term), see DESIGN.md
+        double vo[PB], vn[PB];
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+          vo[k] = a.use_diff ? z[k] - z0[k] : z[k];
+          vn[k] = a.use_diff ? zq[k] - zq0[k] : zq[k];
+        }
+        double cross = 0.0, nn = 0.0;
+        if (a.use_diff) {
+          // recompute the block product on v
+          if (own_i) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) cross += vo[k] * (-tau * vn[k]);
+#pragma unroll
+            for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+              for (int k = 0; k < D; ++k) {
+                double s = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < D; ++cc) s += Rm[rr * D + cc] * vn[(1 + cc) * D + k];
+                cross += vo[(1 + rr) * D + k] * (-tau * t[rr] * vn[k] - kap * s);
+              }
+          } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              double s = vn[k];
+#pragma unroll
+              for (int cc = 0; cc < D; ++cc) s += t[cc] * vn[(1 + cc) * D + k];
+              cross += vo[k] * (-tau * s);
+            }
+#pragma unroll
+            for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+              for (int k = 0; k < D; ++k) {
+                double s = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < D; ++cc) s += Rm[cc * D + rr] * vn[(1 + cc) * D + k];
+                cross += vo[(1 + rr) * D + k] * (-kap * s);
+              }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < PB; ++k) cross += vo[k] * c[k];
+        }
+        // v_n^T M_nn v_n : neighbour is j (own = i): tau|t|^2 + kappa|Y|^2;
+        //                  neighbour is i (own = j): tau|t + t_e^T Y|^2 + kappa|Y|^2
+        double ny = 0.0;
+#pragma unroll
+        for (int k = D; k < PB; ++k) ny += vn[k] * vn[k];
+        double nt = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double s = vn[k];
+          if (!own_i) {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) s += t[cc] * vn[(1 + cc) * D + k];
+          }
+          nt += s * s;
+        }
+        nn = tau * nt + kap * ny;
+        sc[0] += 0.5 * cross - 0.25 * nn;
+      } else {  // I_ROBUST: evaluate_E  (B-form residuals, DPGO_utils.cpp:2176-2207)
+        double rt[D], rR[D * D];
+        double e = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double s = xi[k] - xj[k];
+#pragma unroll
+          for (int cc = 0; cc < D; ++cc) s += t[cc] * xi[(1 + cc) * D + k];
+          rt[k] = s;
+          e += tau * s * s;
+        }
+#pragma unroll
+        for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            double s = -xj[(1 + rr) * D + k];
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) s += Rm[cc * D + rr] * xi[(1 + cc) * D + k];
+            rR[rr * D + k] = s;
+            e += kap * s * s;
+          }
+        double rho;
+        const double w = irls_weight(a.loss, e, a.loss_reg, rho);
+        sc[0] += rho;
+        if (a.w_out) a.w_out[he] = w;
+        if (a.e_out) a.e_out[he] = e;
+        // weighted gradient rows of the own endpoint
+        const double wt = w * tau, wk = w * kap;
+        if (own_i) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) acc[k] += wt * rt[k];
+#pragma unroll
+          for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              double s = 0.0;
+#pragma unroll
+              for (int cc = 0; cc < D; ++cc) s += Rm[rr * D + cc] * rR[cc * D + k];
+              acc[(1 + rr) * D + k] += wt * t[rr] * rt[k] + wk * s;
+            }
+        } else {
+#pragma unroll
+          for (int k = 0; k < D; ++k) acc[k] -= wt * rt[k];
+#pragma unroll
+          for (int k = 0; k < D * D; ++k) acc[D + k] -= wk * rR[k];
+        }
+        if (a.use_diff) {
+          // history terms of evaluate_g_and_f (DPGOProblem.cpp:389-397):
+          //   s1 += w0_e <B_e y, B_e z0>     (tr(Y^T DfobjE0), each edge once per node)
+          //   s2 += y_i^T Mii y_i + y_j^T Mjj y_j    (1/2 of tr(Y^T Q Y) without xi)
+          // here xi/xj are the CURRENT (unextrapolated) points, y = z - z0.
+          double yi[PB], yj[PB];
+#pragma unroll
+          for (int k = 0; k < PB; ++k) { yi[k] = xi[k] - xi0[k]; yj[k] = xj[k] - xj0[k]; }
+          double dot = 0.0, qd = 0.0, nyi = 0.0, nyj = 0.0, ntj = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            double sy = yi[k] - yj[k], s0 = xi0[k] - xj0[k], si = yi[k];
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) {
+              sy += t[cc] * yi[(1 + cc) * D + k];
+              s0 += t[cc] * xi0[(1 + cc) * D + k];
+              si += t[cc] * yi[(1 + cc) * D + k];
+            }
+            dot += tau * sy * s0;
+            qd += tau * si * si;
+            ntj += yj[k] * yj[k];
+          }
+#pragma unroll
+          for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              double sy = -yj[(1 + rr) * D + k], s0 = -xj0[(1 + rr) * D + k];
+#pragma unroll
+              for (int cc = 0; cc < D; ++cc) {
+                sy += Rm[cc * D + rr] * yi[(1 + cc) * D + k];
+                s0 += Rm[cc * D + rr] * xi0[(1 + cc) * D + k];
+              }
+              dot += kap * sy * s0;
+            }
+#pragma unroll
+          for (int k = D; k < PB; ++k) { nyi += yi[k] * yi[k]; nyj += yj[k] * yj[k]; }
+          sc[1] += a.w_prev[he] * dot;
+          sc[2] += qd + kap * nyi + tau * ntj + kap * nyj;
+        }
+      }
+    }
+    // pose-local part: D-type diagonal products and the g row
+    const double *dg = a.dinter + (size_t)p * SYM;
+    double dz[PB];
+#pragma unroll
+    for (int rr = 0; rr < D + 1; ++rr)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < D + 1; ++cc) s += dg[symidx(rr, cc)] * z[cc * D + k];
+        dz[rr * D + k] = s;
+      }
+    if (MODE == I_TRIVIAL) {
+      // g = S Z = C - (Dinter + xi) x
+      double vo[PB];
+#pragma unroll
+      for (int k = 0; k < PB; ++k) vo[k] = a.use_diff ? z[k] - z0[k] : z[k];
+      double vdv = 0.0, vv = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < D + 1; ++rr)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double s = 0.0;
+#pragma unroll
+          for (int cc = 0; cc < D + 1; ++cc) s += dg[symidx(rr, cc)] * vo[cc * D + k];
+          vdv += vo[rr * D + k] * s;
+          vv += vo[rr * D + k] * vo[rr * D + k];
+        }
+      sc[0] += -0.25 * vdv - 0.5 * a.xi * vv;
+#pragma unroll
+      for (int k = 0; k < PB; ++k) {
+        const double gk = acc[k] - (dz[k] + a.xi * z[k]);
+        a.g[(size_t)p * PB + k] = gk;
+        sc[1] += z[k] * acc[k];      // x.C
+        sc[2] += z[k] * dz[k];       // x^T Dinter x
+        sc[3] += z[k] * z[k];        // |x|^2
+      }
+    } else {
+      // g = DfobjE_own - D x,  D = 2 Dinter + xi   (DPGOProblem.cpp:233-239)
+      double ydy = 0.0, yy = 0.0;
+      if (a.use_diff) {
+#pragma unroll
+        for (int k = 0; k < PB; ++k) { const double y = z[k] - z0[k]; yy += y * y; }
+      }
+#pragma unroll
+      for (int k = 0; k < PB; ++k) {
+        const double dx = 2.0 * dz[k] + a.xi * z[k];
+        a.g[(size_t)p * PB + k] = acc[k] - dx;
+        sc[3] += z[k] * acc[k];      // x.DfobjE
+        sc[4] += z[k] * dx;          // x^T D x
+      }
+      sc[5] += yy;                   // |y_own|^2 for the 2 xi term of Q
+      (void)ydy;
+    }
+  }
+  block_reduce_store<6, TILE>(sc, a.partials + (size_t)tile * NS);
+}
+
+template <int D> void launch_inter(int mode, const Tiles &tl, const InterArgs &a, cudaStream_t s) {
+  if (mode == I_TRIVIAL) k_inter<D, I_TRIVIAL><<<tl.n_tiles, TILE, 0, s>>>(tl, a);
+  else k_inter<D, I_ROBUST><<<tl.n_tiles, TILE, 0, s>>>(tl, a);
+}
+template void launch_inter<2>(int, const Tiles &, const InterArgs &, cudaStream_t);
+template void launch_inter<3>(int, const Tiles &, const InterArgs &, cudaStream_t);
+
+// =============================================================================
+// K3: fused Nesterov extrapolation + proximal step + SO(d) polar projection.
+// One thread per pose.                (DPGOHash.cpp:255-262, DPGOProblem.cpp:600-632)
+// =============================================================================
+template <int D>
+__global__ void __launch_bounds__(TILE) k_prox(Tiles tl, ProxArgs a) {
+  constexpr int PB = Dim<D>::PB, TNV = Dim<D>::TNV;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int p = tl.start[tile] + threadIdx.x;
+  const bool valid = threadIdx.x < tl.cnt[tile];
+  double sc[1] = {0.0};
+  if (valid) {
+    const double gam = (a.xb && a.gamma) ? a.gamma[node] : 0.0;
+    double y0[PB], df[PB];
+#pragma unroll
+    for (int k = 0; k < PB; ++k) {
+      y0[k] = a.xa[(size_t)p * PB + k];
+      df[k] = a.dfa[(size_t)p * PB + k];
+    }
+    if (a.xb) {
+#pragma unroll
+      for (int k = 0; k < PB; ++k) y0[k] = y0[k] + gam * (y0[k] - a.xb[(size_t)p * PB + k]);
+    }
+    if (a.dfb) {
+#pragma unroll
+      for (int k = 0; k < PB; ++k) df[k] = df[k] + gam * (df[k] - a.dfb[(size_t)p * PB + k]);
+    }
+    if (a.gex) {
+#pragma unroll
+      for (int k = 0; k < PB; ++k) {
+        double gv = a.ga[(size_t)p * PB + k];
+        if (a.gb) gv = gv + gam * (gv - a.gb[(size_t)p * PB + k]);
+        a.gex[(size_t)p * PB + k] = gv;
+      }
+    }
+    const double *c = a.tnv + (size_t)p * TNV;
+    const double T = c[0];
+    const double *N = c + 1, *V = c + 1 + D;
+    // M = V' Y0 - Df_Y + N^T Df_t
+    double M[D * D], Yn[D * D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) s += V[r * D + cc] * y0[(1 + cc) * D + k];
+        M[r * D + k] = s - df[(1 + r) * D + k] + N[r] * df[k];
+      }
+    project_to_SOd<D>(M, Yn);
+    // t = t0 - N (Y - Y0) - T Df_t
+    double out[PB];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < D; ++r) s += N[r] * (Yn[r * D + k] - y0[(1 + r) * D + k]);
+      out[k] = y0[k] - s - T * df[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) out[D + k] = Yn[k];
+#pragma unroll
+    for (int k = 0; k < PB; ++k) {
+      a.xout[(size_t)p * PB + k] = out[k];
+      if (a.xref) {
+        const double dlt = out[k] - a.xref[(size_t)p * PB + k];
+        sc[0] += dlt * dlt;
+      }
+    }
+  }
+  block_reduce_store<1, TILE>(sc, a.partials + (size_t)tile * NS);
+}
+template <int D> void launch_prox(const Tiles &tl, const ProxArgs &a, cudaStream_t s) {
+  k_prox<D><<<tl.n_tiles, TILE, 0, s>>>(tl, a);
+}
+template void launch_prox<2>(const Tiles &, const ProxArgs &, cudaStream_t);
+template void launch_prox<3>(const Tiles &, const ProxArgs &, cudaStream_t);
+
+// =============================================================================
+// Per-pose vector operations of the truncated-CG / trust-region bookkeeping.
+// =============================================================================
+template <int D>
+__device__ __forceinline__ void apply_precon(const VecArgs &a, int p, const double *r, const double *Y,
+                                             double *v) {
+  // DPGOProblem::precondition (DPGOProblem.cpp:579-598): M^{-1} r, then tangent projection
+  double u[D * D];
+  if (a.precon == 0) {
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) v[k] = r[k];
+    return;
+  }
+  if (a.precon == 1) {
+#pragma unroll
+    for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+      for (int k = 0; k < D; ++k) u[rr * D + k] = a.pinv[(size_t)p * D * D + rr * D + rr] * r[rr * D + k];
+  } else {
+    const double *B = a.pinv + (size_t)p * D * D;
+#pragma unroll
+    for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) s += B[rr * D + cc] * r[cc * D + k];
+        u[rr * D + k] = s;
+      }
+  }
+#pragma unroll
+  for (int rr = 0; rr < D; ++rr) proj_row<D>(u, Y, rr, v + rr * D);
+}
+
+template <int D, int OP>
+__global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
+  constexpr int PB = Dim<D>::PB, DD = D * D;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int p = tl.start[tile] + threadIdx.x;
+  const bool valid = threadIdx.x < tl.cnt[tile];
+  const double *cf = a.coef ? a.coef + (size_t)node * MAXC : nullptr;
+  double sc[3] = {0, 0, 0};
+  if (valid) {
+    const size_t o = (size_t)p * PB + D;  // rotation rows
+    if (OP == V_CG_INIT) {
+      // a = grad; o1 = s, o2 = r, o3 = v, o4 = p
+      double r[DD], v[DD], Y[DD];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { r[k] = a.a[o + k]; Y[k] = a.y[o + k]; }
+      apply_precon<D>(a, p, r, Y, v);
+#pragma unroll
+      for (int k = 0; k < DD; ++k) {
+        a.o1[o + k] = 0.0; a.o2[o + k] = r[k]; a.o3[o + k] = v[k]; a.o4[o + k] = -v[k];
+        sc[0] += r[k] * v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) { a.o1[o - D + k] = 0.0; a.o4[o - D + k] = 0.0; }
+    } else if (OP == V_CG_STEP) {
+      // a = p, b = Hp; o1 = s, o2 = r, o3 = v; coef[0] = alpha
+      const double al = cf[0];
+      double r[DD], v[DD], Y[DD];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) {
+        a.o1[o + k] = a.o1[o + k] + al * a.a[o + k];
+        r[k] = a.o2[o + k] + al * a.b[o + k];
+        Y[k] = a.y[o + k];
+      }
+      apply_precon<D>(a, p, r, Y, v);
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { a.o2[o + k] = r[k]; a.o3[o + k] = v[k]; sc[0] += r[k] * v[k]; }
+    } else if (OP == V_CG_DIR) {
+      // a = v; o1 = p; coef[1] = beta
+      const double be = cf[1];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) a.o1[o + k] = -a.a[o + k] + be * a.o1[o + k];
+    } else if (OP == V_CG_FINAL) {
+      // o1 = s, a = p; coef[2] = sigma (sign folded in by the host)
+      const double sg = cf[2];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) a.o1[o + k] = a.o1[o + k] + sg * a.a[o + k];
+    } else if (OP == V_RETRACT) {
+      // a = x, b = s; o1 = xprop (rotation rows)
+      double M[DD], Yn[DD];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) M[k] = a.a[o + k] + a.b[o + k];
+      project_to_SOd<D>(M, Yn);
+#pragma unroll
+      for (int k = 0; k < DD; ++k) a.o1[o + k] = Yn[k];
+    } else if (OP == V_DOTS) {
+#pragma unroll
+      for (int k = 0; k < DD; ++k) {
+        const double x = a.a[o + k], y = a.b[o + k];
+        sc[0] += x * y; sc[1] += x * x; sc[2] += y * y;
+      }
+    } else if (OP == V_COPY_ROT) {
+#pragma unroll
+      for (int k = 0; k < DD; ++k) a.o1[o + k] = a.a[o + k];
+    } else if (OP == V_COPY) {
+#pragma unroll
+      for (int k = 0; k < PB; ++k) a.o1[o - D + k] = a.a[o - D + k];
+    } else if (OP == V_PRECOND) {
+      double r[DD], v[DD], Y[DD];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { r[k] = a.a[o + k]; Y[k] = a.y[o + k]; }
+      apply_precon<D>(a, p, r, Y, v);
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { if (a.o1) a.o1[o + k] = v[k]; sc[0] += v[k] * v[k]; }
+    } else if (OP == V_SET_T) {
+      // a = compact solution (NO x D); o1.t = -a
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.o1[o - D + k] = -a.a[(size_t)p * D + k];
+    } else if (OP == V_DIFFNORM) {
+#pragma unroll
+      for (int k = 0; k < PB; ++k) {
+        const double dlt = a.a[o - D + k] - a.b[o - D + k];
+        sc[0] += dlt * dlt;
+      }
+    } else if (OP == V_GET_T) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = -a.a[o - D + k];
+    } else if (OP == V_ZERO_C) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = 0.0;
+    }
+  }
+  if (OP == V_CG_INIT || OP == V_CG_STEP || OP == V_DOTS || OP == V_PRECOND || OP == V_DIFFNORM)
+    block_reduce_store<3, TILE>(sc, a.partials + (size_t)tile * NS);
+}
+
+template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cudaStream_t s) {
+#define MMPGO_VEC_CASE(OP) case OP: k_vec<D, OP><<<tl.n_tiles, TILE, 0, s>>>(tl, a); break;
+  switch (op) {
+    MMPGO_VEC_CASE(V_CG_INIT) MMPGO_VEC_CASE(V_CG_STEP) MMPGO_VEC_CASE(V_CG_DIR)
+    MMPGO_VEC_CASE(V_CG_FINAL) MMPGO_VEC_CASE(V_RETRACT) MMPGO_VEC_CASE(V_DOTS)
+    MMPGO_VEC_CASE(V_COPY_ROT) MMPGO_VEC_CASE(V_COPY) MMPGO_VEC_CASE(V_PRECOND)
+    MMPGO_VEC_CASE(V_SET_T) MMPGO_VEC_CASE(V_DIFFNORM) MMPGO_VEC_CASE(V_GET_T) MMPGO_VEC_CASE(V_ZERO_C)
+  }
+#undef MMPGO_VEC_CASE
+}
+template void launch_vec<2>(int, const Tiles &, const VecArgs &, cudaStream_t);
+template void launch_vec<3>(int, const Tiles &, const VecArgs &, cudaStream_t);
+
+// =============================================================================
+// per-node reduction of tile partials (fixed order => deterministic)
+// =============================================================================
+__global__ void __launch_bounds__(128) k_reduce(const int *tb, const int *te, const double *partials,
+                                                double *node_scal) {
+  const int node = blockIdx.x;
+  const int b = tb[node], e = te[node];
+  const int k = threadIdx.x & 7, lane8 = threadIdx.x >> 3;  // 16 groups of NS=8 slots
+  __shared__ double sm[16][NS];
+  double s = 0.0;
+  for (int t = b + lane8; t < e; t += 16) s += partials[(size_t)t * NS + k];
+  sm[lane8][k] = s;
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    double x = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x += sm[i][threadIdx.x];
+    node_scal[(size_t)node * NS + threadIdx.x] = x;
+  }
+}
+void launch_reduce(int num_nodes, const int *tb, const int *te, const double *partials, double *node_scal,
+                   cudaStream_t s) {
+  k_reduce<<<num_nodes, 128, 0, s>>>(tb, te, partials, node_scal);
+}
+
+// =============================================================================
+// edge-parallel global objective  (DPGOStar::evaluate_f, DPGOStar.cpp:713-761)
+// =============================================================================
+template <int D>
+__global__ void __launch_bounds__(256) k_edge_objective(int64_t n, const EdgeRec *rec, const double *x, int loss,
+                                                        double loss_reg, double *block_partials) {
+  constexpr int PB = Dim<D>::PB;
+  double sc[1] = {0.0};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const EdgeRec *r = rec + e;
+    const double *xi = x + (size_t)r->i * PB, *xj = x + (size_t)r->j * PB;
+    const double tau = r->tau, kap = r->kappa;
+    double et = 0.0, er = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      double s = xi[k] - xj[k];
+#pragma unroll
+      for (int cc = 0; cc < D; ++cc) s += r->t[cc] * xi[(1 + cc) * D + k];
+      et += s * s;
+    }
+    if (loss == 0) {
+      // M-form: kappa (|Y_i|^2 + |Y_j|^2 - 2 <R^T Y_i, Y_j>)   (DPGO_utils.cpp:500-560)
+      double ni = 0.0, nj = 0.0, cr = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double s = 0.0;
+#pragma unroll
+          for (int cc = 0; cc < D; ++cc) s += r->R[cc * D + rr] * xi[(1 + cc) * D + k];
+          cr += s * xj[(1 + rr) * D + k];
+          ni += xi[(1 + rr) * D + k] * xi[(1 + rr) * D + k];
+          nj += xj[(1 + rr) * D + k] * xj[(1 + rr) * D + k];
+        }
+      er = ni + nj - 2.0 * cr;
+      sc[0] += 0.5 * (tau * et + kap * er);
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < D; ++rr)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double s = -xj[(1 + rr) * D + k];
+#pragma unroll
+          for (int cc = 0; cc < D; ++cc) s += r->R[cc * D + rr] * xi[(1 + cc) * D + k];
+          er += s * s;
+        }
+      const double e2 = tau * et + kap * er;
+      if (r->inter) {
+        double rho;
+        irls_weight(loss, e2, loss_reg, rho);
+        sc[0] += rho;
+      } else {
+        sc[0] += 0.5 * e2;
+      }
+    }
+  }
+  block_reduce_store<1, 256>(sc, block_partials + blockIdx.x);
+}
+__global__ void k_sum_blocks(int n, const double *bp, double *out) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += bp[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sm[0];
+}
+template <int D>
+void launch_edge_objective(int64_t n_edges, const EdgeRec *rec, const double *x, int loss, double loss_reg,
+                           double *block_partials, int *n_blocks_out, cudaStream_t s) {
+  int nb = (int)((n_edges + 255) / 256);
+  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb < 1) nb = 1;
+  *n_blocks_out = nb;
+  k_edge_objective<D><<<nb, 256, 0, s>>>(n_edges, rec, x, loss, loss_reg, block_partials);
+}
+template void launch_edge_objective<2>(int64_t, const EdgeRec *, const double *, int, double, double *, int *,
+                                       cudaStream_t);
+template void launch_edge_objective<3>(int64_t, const EdgeRec *, const double *, int, double, double *, int *,
+                                       cudaStream_t);
+void launch_sum_blocks(int n_blocks, const double *bp, double *out, cudaStream_t s) {
+  k_sum_blocks<<<1, 256, 0, s>>>(n_blocks, bp, out);
+}
+
+// =============================================================================
+// K2b: translation solve G00 t = rhs
+// =============================================================================
+// dense path: one warp per output row, t_p = sum_q Ginv[p][q] rhs[q]
+template <int D>
+__global__ void __launch_bounds__(256) k_dense_solve(const int *node_off, const long long *dense_off,
+                                                     const int *node_active, const double *ginv,
+                                                     const double *rhs, double *xout) {
+  constexpr int PB = Dim<D>::PB;
+  const int node = blockIdx.y;
+  if (node_active && !node_active[node]) return;
+  const int n0 = node_off[node + 1] - node_off[node];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n0) return;
+  if (dense_off[node] < 0) return;
+  const double *row = ginv + (size_t)dense_off[node] + (size_t)warp * n0;
+  const double *b = rhs + (size_t)node_off[node] * D;
+  double acc[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) acc[c] = 0.0;
+  for (int q = lane; q < n0; q += 32) {
+    const double gv = row[q];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = fma(gv, b[(size_t)q * D + c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], o);
+  }
+  if (lane == 0) {
+    double *o = xout + (size_t)(node_off[node] + warp) * PB;
+#pragma unroll
+    for (int c = 0; c < D; ++c) o[c] = -acc[c];
+  }
+}
+
+// PCG path (Jacobi-preconditioned CG on the scalar Laplacian, d right-hand sides
+// treated as one system with the Frobenius inner product).
+template <int D>
+__global__ void __launch_bounds__(TILE *D) k_pcg_spmv(Tiles tl, SolveArgs sa, const double *v, double *av,
+                                                      const double *rhs, double *r, double *z, double *pdir,
+                                                      double *partials, int init) {
+  // init: r = rhs - A v ; z = r / d ; p = z ; s0 = r.z ; s1 = rhs.rhs ; s2 = r.r
+  // else: av = A v ; s0 = v.av
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int pl = threadIdx.x / D, c = threadIdx.x % D;
+  const int p = tl.start[tile] + pl;
+  const bool valid = pl < tl.cnt[tile];
+  double sc[3] = {0, 0, 0};
+  if (valid) {
+    double acc = sa.d00[p] * v[(size_t)p * D + c];
+    const int e0 = sa.rowptr[p], e1 = sa.rowptr[p + 1];
+    for (int e = e0; e < e1; ++e) acc = fma(__ldg(sa.a00 + e), v[(size_t)__ldg(sa.col + e) * D + c], acc);
+    if (init) {
+      const double b = rhs[(size_t)p * D + c];
+      const double rv = b - acc;
+      const double zv = rv / sa.d00[p];
+      r[(size_t)p * D + c] = rv;
+      z[(size_t)p * D + c] = zv;
+      pdir[(size_t)p * D + c] = zv;
+      sc[0] = rv * zv;
+      sc[1] = b * b;
+      sc[2] = rv * rv;
+    } else {
+      av[(size_t)p * D + c] = acc;
+      sc[0] = v[(size_t)p * D + c] * acc;
+    }
+  }
+  block_reduce_store<3, TILE * D>(sc, partials + (size_t)tile * NS);
+}
+
+// state slots: 0 rz, 1 pAp, 2 alpha, 3 beta, 4 rr, 5 bb, 6 active, 7 iters
+__global__ void k_pcg_scalar(int num_nodes, const double *node_scal, double *state, int stage, double tol2) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= num_nodes) return;
+  double *st = state + (size_t)a * 8;
+  const double *ns = node_scal + (size_t)a * NS;
+  if (stage == 0) {  // after init
+    st[0] = ns[0]; st[5] = ns[1]; st[4] = ns[2]; st[2] = 0.0; st[3] = 0.0; st[7] = 0.0;
+    st[6] = (ns[0] > 0.0 && ns[2] > tol2 * ns[1]) ? 1.0 : 0.0;
+  } else if (stage == 1) {  // after spmv: alpha
+    st[1] = ns[0];
+    st[2] = (st[6] != 0.0 && ns[0] > 0.0) ? st[0] / ns[0] : 0.0;
+  } else {  // after update: beta, convergence
+    if (st[6] != 0.0) {
+      const double rz_new = ns[0];
+      st[3] = rz_new / st[0];
+      st[0] = rz_new;
+      st[4] = ns[1];
+      st[7] += 1.0;
+      if (ns[1] <= tol2 * st[5] || !(rz_new > 0.0)) { st[6] = 0.0; }
+    } else {
+      st[3] = 0.0;
+      st[2] = 0.0;
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(TILE *D) k_pcg_update(Tiles tl, SolveArgs sa, double *x, double *r, double *z,
+                                                        const double *pdir, const double *ap, double *partials) {
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int pl = threadIdx.x / D, c = threadIdx.x % D;
+  const int p = tl.start[tile] + pl;
+  const bool valid = pl < tl.cnt[tile];
+  const double al = sa.state[(size_t)node * 8 + 2];
+  double sc[2] = {0, 0};
+  if (valid) {
+    const size_t i = (size_t)p * D + c;
+    x[i] = x[i] + al * pdir[i];
+    const double rv = r[i] - al * ap[i];
+    const double zv = rv / sa.d00[p];
+    r[i] = rv;
+    z[i] = zv;
+    sc[0] = rv * zv;
+    sc[1] = rv * rv;
+  }
+  block_reduce_store<2, TILE * D>(sc, partials + (size_t)tile * NS);
+}
+template <int D>
+__global__ void __launch_bounds__(TILE *D) k_pcg_dir(Tiles tl, SolveArgs sa, const double *z, double *pdir) {
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int pl = threadIdx.x / D, c = threadIdx.x % D;
+  const int p = tl.start[tile] + pl;
+  if (pl >= tl.cnt[tile]) return;
+  const double be = sa.state[(size_t)node * 8 + 3];
+  const double on = sa.state[(size_t)node * 8 + 6];
+  const size_t i = (size_t)p * D + c;
+  if (on != 0.0) pdir[i] = z[i] + be * pdir[i];
+}
+
+template <int D>
+void launch_pcg_init(const Tiles &tl, const SolveArgs &sa, const double *rhs, const double *x0, double *x,
+                     double *r, double *z, double *p, double *partials, cudaStream_t s) {
+  (void)x;
+  k_pcg_spmv<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, x0, nullptr, rhs, r, z, p, partials, 1);
+}
+template <int D>
+void launch_pcg_spmv(const Tiles &tl, const SolveArgs &sa, const double *p, double *ap, double *partials,
+                     int first, cudaStream_t s) {
+  (void)first;
+  k_pcg_spmv<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, p, ap, nullptr, nullptr, nullptr, nullptr, partials, 0);
+}
+template <int D>
+void launch_pcg_update(const Tiles &tl, const SolveArgs &sa, double *x, double *r, double *z, const double *p,
+                       const double *ap, double *partials, cudaStream_t s) {
+  k_pcg_update<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, x, r, z, p, ap, partials);
+}
+template <int D>
+void launch_pcg_dir(const Tiles &tl, const SolveArgs &sa, const double *z, double *p, double *partials,
+                    cudaStream_t s) {
+  (void)partials;
+  k_pcg_dir<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, z, p);
+}
+void launch_pcg_scalar(int num_nodes, const double *node_scal, double *state, int stage, double tol2,
+                       cudaStream_t s) {
+  k_pcg_scalar<<<(num_nodes + 127) / 128, 128, 0, s>>>(num_nodes, node_scal, state, stage, tol2);
+}
+#define MMPGO_INST_PCG(D)                                                                                        \
+  template void launch_pcg_init<D>(const Tiles &, const SolveArgs &, const double *, const double *, double *,  \
+                                   double *, double *, double *, double *, cudaStream_t);                       \
+  template void launch_pcg_spmv<D>(const Tiles &, const SolveArgs &, const double *, double *, double *, int,   \
+                                   cudaStream_t);                                                               \
+  template void launch_pcg_update<D>(const Tiles &, const SolveArgs &, double *, double *, double *,            \
+                                     const double *, const double *, double *, cudaStream_t);                   \
+  template void launch_pcg_dir<D>(const Tiles &, const SolveArgs &, const double *, double *, double *,         \
+                                  cudaStream_t);
+MMPGO_INST_PCG(2)
+MMPGO_INST_PCG(3)
+
+template <int D>
+void launch_dense_solve(int num_nodes, const int *node_off, const long long *dense_off, const int *node_active,
+                        const double *ginv, const double *rhs, double *xout, int max_n0, cudaStream_t s) {
+  const dim3 grid((max_n0 * 32 + 255) / 256, num_nodes);
+  k_dense_solve<D><<<grid, 256, 0, s>>>(node_off, dense_off, node_active, ginv, rhs, xout);
+}
+template void launch_dense_solve<2>(int, const int *, const long long *, const int *, const double *, const double *,
+                                    double *, int, cudaStream_t);
+template void launch_dense_solve<3>(int, const int *, const long long *, const int *, const double *, const double *,
+                                    double *, int, cudaStream_t);
+
+// =============================================================================
+// halo pack / unpack
+// =============================================================================
+template <int D>
+__global__ void k_gather_poses(int64_t n, const int *idx, const double *src, double *dst) {
+  constexpr int PB = Dim<D>::PB;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * PB) return;
+  const int64_t p = i / PB;
+  const int k = (int)(i % PB);
+  dst[i] = src[(size_t)idx[p] * PB + k];
+}
+template <int D>
+__global__ void k_scatter_poses(int64_t n, const int *idx, const double *src, double *dst) {
+  constexpr int PB = Dim<D>::PB;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * PB) return;
+  const int64_t p = i / PB;
+  const int k = (int)(i % PB);
+  dst[(size_t)idx[p] * PB + k] = src[i];
+}
+template <int D> void launch_gather_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s) {
+  if (n <= 0) return;
+  const int64_t tot = n * Dim<D>::PB;
+  k_gather_poses<D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(n, idx, src, dst);
+}
+template <int D> void launch_scatter_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s) {
+  if (n <= 0) return;
+  const int64_t tot = n * Dim<D>::PB;
+  k_scatter_poses<D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(n, idx, src, dst);
+}
+template void launch_gather_poses<2>(int64_t, const int *, const double *, double *, cudaStream_t);
+template void launch_gather_poses<3>(int64_t, const int *, const double *, double *, cudaStream_t);
+template void launch_scatter_poses<2>(int64_t, const int *, const double *, double *, cudaStream_t);
+template void launch_scatter_poses<3>(int64_t, const int *, const double *, double *, cudaStream_t);
+
+}  // namespace mmpgo

@@ -1,0 +1,183 @@
+// Internal kernel interface of libmmpgo (sm_100a, FP64).
+//
+// Device data model (DESIGN.md "Data layout in HBM"):
+//   * a pose is one (d+1) x d row-major block: row 0 = t_i, rows 1..d = Y_i = R_i^T
+//     (the reference stores the same numbers as rows i and n0+d*i.. of X,
+//     C++/DPGO/src/DPGO_utils.cpp:413-424); PB = (d+1)*d doubles.
+//   * own poses of all local robot nodes are contiguous [0, NO); copies of
+//     remote neighbours ("halo") follow at [NO, NP).
+//   * the static majoriser G (DPGO_utils.cpp:1542-1641, 1964-2028) is a
+//     block-CSR over own poses: (d+1)x(d+1) off-diagonal blocks per intra-node
+//     half-edge + one packed symmetric diagonal block per pose.
+//   * inter-node half-edges (one per own endpoint) are a CSR of 128-byte
+//     records holding the raw measurement.
+//   * work is cut into tiles of <= TILE poses that never straddle a node, so
+//     every per-node scalar is a fixed-order sum of per-tile partials.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mmpgo {
+
+constexpr int TILE = 64;      // poses per tile / CTA
+constexpr int NS = 8;         // scalar slots per tile
+constexpr int MAXC = 8;       // per-node coefficient slots
+
+struct Tiles {
+  int n_tiles;
+  const int *node;    // [n_tiles] local node of the tile
+  const int *start;   // [n_tiles] first own pose
+  const int *cnt;     // [n_tiles] poses in tile
+  const int *active;  // [num_local_nodes] 0/1 mask (device) or nullptr = all
+};
+
+// ---- K2: block-CSR connection-Laplacian pass -------------------------------
+enum GMode {
+  G_EVAL = 0,     // s0 = sum x.(g + 1/2 G x)                     (evaluate_G, DPGOProblem.cpp:180-203)
+  G_GRAD = 1,     // out = g + G x; s0 as above; s1 = |gradF|^2; s2 = x.Gx; s3 = x.g
+  G_RHS_T = 2,    // rhs_t = g_t + G01 Y  (t rows out, Y rows in)   (DPGOProblem.h:289-290)
+  G_REDGRAD = 3,  // nab = g_Y + (G x)_Y; grad = Proj(Y, nab); s0 = |grad|^2 (DPGOProblem.h:370-393)
+  G_HV = 4        // Hp = Proj(Y, (G p)_Y - sym(nab Y^T) p_Y); s0=p.Hp s1=Hp.Hp s2=p.p (DPGOProblem.cpp:552-577)
+};
+
+struct GPassArgs {
+  const int *rowptr;      // [NO+1]
+  const int *col;         // [nnz] own pose index
+  const double *blk;      // [nnz][(d+1)^2] off-diagonal blocks, row-major
+  const double *diag;     // [NO][SYM] packed lower-triangular diagonal block
+  const double *x;        // input pose-block vector (gathered)
+  const double *g;        // additive vector (may be null)
+  const double *xref;     // G_HV: the point Y (pose blocks); others unused
+  const double *nab;      // G_HV: Euclidean gradient rows
+  double *out;            // vector output (pose blocks or compact t rows for G_RHS_T)
+  double *out2;           // G_REDGRAD: grad
+  double *partials;       // [n_tiles][NS]
+};
+
+// ---- K1: inter-node edge pass ----------------------------------------------
+struct InterRec {         // one own-endpoint half-edge, 128 bytes
+  int32_t other;          // pose index (own or halo) of the other endpoint
+  int32_t own_is_i;       // 1: own pose is the edge's i endpoint
+  double tau, kappa;
+  double t[3];
+  double R[9];            // row-major d x d
+  double pad;
+};
+static_assert(sizeof(InterRec) == 128, "InterRec must be 128 bytes");
+
+enum InterMode {
+  I_TRIVIAL = 0,   // g = S Z, q(v) partials                       (DPGOProblem.cpp:269-287, 516-542)
+  I_ROBUST = 1     // evaluate_E: weights, DfobjE rows, loss value (DPGOProblem.cpp:634-681)
+};
+
+struct InterArgs {
+  const int *rowptr;          // [NO+1] half-edges per own pose
+  const InterRec *rec;
+  const double *xa;           // Z_k      (NP pose blocks)
+  const double *xb;           // Z_{k-1}  (may be null)
+  const double *dinter;       // [NO][SYM] sum of own diagonal blocks of inter edges
+  const double *gamma;        // per-node extrapolation factor (null = 0)
+  int use_diff;               // I_TRIVIAL: v = z - z_prev for q(v); I_ROBUST: add history terms
+  int loss;
+  double loss_reg, xi;
+  const double *w_prev;       // previous IRLS weights per half-edge (I_ROBUST, use_diff)
+  double *w_out;              // IRLS weights per half-edge (may be null)
+  double *e_out;              // squared error per half-edge (may be null)
+  double *g;                  // [NO] pose blocks: g
+  double *yex;                // extrapolated own poses (may be null)
+  double *partials;
+};
+
+// ---- K3: fused extrapolation + proximal + polar projection -------------------
+struct ProxArgs {
+  const double *xa, *xb;      // X_k, X_{k-1} own rows (xb null -> no extrapolation)
+  const double *dfa, *dfb;    // Df_k, Df_{k-1}
+  const double *ga, *gb;      // g_k, g_{k-1} (may be null: no g extrapolation)
+  const double *gamma;        // per node
+  const double *tnv;          // [NO][1 + d + d*d]  T, N, V'
+  const double *xref;         // for s0 = |Xout - xref|^2
+  double *xout;               // X^{k+1/2}
+  double *gex;                // extrapolated g (may be null)
+  double *partials;
+};
+
+// ---- generic per-pose vector ops (tCG / TNT bookkeeping) --------------------
+enum VecOp {
+  V_CG_INIT = 0,   // s=0; r=grad; v=P(r); p=-v;           s0 = r.v, s1 = p.p... (IterativeSolvers.h:204-262)
+  V_CG_STEP = 1,   // s+=a p; r+=a Hp; v=P(r);             s0 = r.v
+  V_CG_DIR = 2,    // p = -v + b p
+  V_CG_FINAL = 3,  // s += sigma p  (p optionally negated first)
+  V_RETRACT = 4,   // xprop.Y = proj(x.Y + s.Y)                 (DPGOProblem.cpp:127-143)
+  V_DOTS = 5,      // s0 = a.b  s1 = a.a  s2 = b.b (rotation rows)
+  V_COPY_ROT = 6,  // out.Y = a.Y
+  V_COPY = 7,      // out = a
+  V_PRECOND = 8,   // out = P(a); s0 = out.out
+  V_SET_T = 9,     // out.t = -tsol
+  V_DIFFNORM = 10, // s0 = |a - b|^2 (all rows)
+  V_GET_T = 11,    // compact o1 = -a.t   (warm start of the translation solve)
+  V_ZERO_C = 12    // compact o1 = 0
+};
+
+struct VecArgs {
+  const double *a, *b, *c;
+  double *o1, *o2, *o3, *o4;
+  const double *y;          // point for tangent projection (pose blocks)
+  const double *pinv;       // [NO][d*d] block-Jacobi inverse or [NO][d] Jacobi
+  int precon;               // 0 none, 1 jacobi, 2 block jacobi
+  const double *coef;       // [num_nodes][MAXC] per-node coefficients
+  double *partials;
+};
+
+// ---- K2b: translation solve --------------------------------------------------
+struct SolveArgs {
+  const int *rowptr, *col;  // G00 pattern (= intra pattern)
+  const double *a00;        // off-diagonal values (-tau)
+  const double *d00;        // diagonal of G00
+  const int *node_tile_begin, *node_tile_end;
+  double *state;            // [num_nodes][8]: rz, pAp, alpha, beta, rr, bb, active, iters
+  double tol2;
+};
+
+// ---- edge-parallel global objective (AMM-PGO*, DPGOStar.cpp:713-761) ----------
+struct EdgeRec {            // 128 bytes
+  int32_t i, j;             // pose indices (own / halo numbering)
+  double tau, kappa;
+  double t[3];
+  double R[9];
+  int32_t inter;            // 1: inter-node edge (robust kernel applies)
+  int32_t pad;
+};
+static_assert(sizeof(EdgeRec) == 128, "EdgeRec must be 128 bytes");
+
+template <int D> void launch_gpass(int mode, const Tiles &tl, const GPassArgs &a, cudaStream_t s);
+template <int D> void launch_inter(int mode, const Tiles &tl, const InterArgs &a, cudaStream_t s);
+template <int D> void launch_prox(const Tiles &tl, const ProxArgs &a, cudaStream_t s);
+template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cudaStream_t s);
+void launch_reduce(int num_nodes, const int *node_tile_begin, const int *node_tile_end,
+                   const double *partials, double *node_scal, cudaStream_t s);
+template <int D> void launch_edge_objective(int64_t n_edges, const EdgeRec *rec, const double *x,
+                                            int loss, double loss_reg, double *block_partials,
+                                            int *n_blocks_out, cudaStream_t s);
+void launch_sum_blocks(int n_blocks, const double *block_partials, double *out, cudaStream_t s);
+
+// translation solve building blocks
+template <int D> void launch_dense_solve(int num_nodes, const int *node_off, const long long *node_dense_off,
+                                         const int *node_active, const double *ginv, const double *rhs,
+                                         double *xout /*pose blocks, row 0 = -Ginv rhs*/, int max_n0,
+                                         cudaStream_t s);
+void launch_pcg_scalar(int num_nodes, const double *node_scal, double *state, int stage, double tol2,
+                       cudaStream_t s);
+template <int D> void launch_pcg_init(const Tiles &tl, const SolveArgs &sa, const double *rhs, const double *x0,
+                                      double *x, double *r, double *z, double *p, double *partials, cudaStream_t s);
+template <int D> void launch_pcg_spmv(const Tiles &tl, const SolveArgs &sa, const double *p, double *ap,
+                                      double *partials, int first, cudaStream_t s);
+template <int D> void launch_pcg_update(const Tiles &tl, const SolveArgs &sa, double *x, double *r, double *z,
+                                        const double *p, const double *ap, double *partials, cudaStream_t s);
+template <int D> void launch_pcg_dir(const Tiles &tl, const SolveArgs &sa, const double *z, double *p,
+                                     double *partials, cudaStream_t s);
+
+// halo pack / unpack (DPGOHash::receive wire format, DPGOHash.cpp:45-82)
+template <int D> void launch_gather_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);
+template <int D> void launch_scatter_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);
+
+}  // namespace mmpgo

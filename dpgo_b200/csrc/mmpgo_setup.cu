@@ -1,0 +1,414 @@
+// Graph upload: partition, local indexing and the static operators of every
+// local robot node, regenerated per edge instead of as Eigen sparse matrices.
+//
+// Restates the *output semantics* of
+//   DPGO::read_g2o            C++/DPGO/src/DPGO_utils.cpp:140-202 (partition)
+//   generate_data_info        :326-438  (own poses by ascending id, neighbours)
+//   simplify_quadratic_data_matrix :1398-2288 and simplify_regular_data_matrix
+//   (Static) :2290-2967       (G, D, H -> T, N, V')
+//   DPGOProblem::DPGOProblem  C++/DPGO/src/DPGOProblem.cpp:11-125 (L_ = chol(G00),
+//   preconditioner)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "mmpgo_driver.cuh"
+
+namespace mmpgo {
+
+#define CK(x)                                                                    \
+  do {                                                                           \
+    cudaError_t e_ = (x);                                                        \
+    if (e_ != cudaSuccess) {                                                     \
+      set_error(std::string(#x) + ": " + cudaGetErrorString(e_));                \
+      return MMPGO_ERR_CUDA;                                                     \
+    }                                                                            \
+  } while (0)
+
+template <typename T> static int dalloc(Handle *h, T **p, size_t n) {
+  void *q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  CK(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  h->allocs.push_back(q);
+  *p = static_cast<T *>(q);
+  return 0;
+}
+template <typename T> static int upload(Handle *h, T **p, const std::vector<T> &v) {
+  int rc = dalloc(h, p, v.size());
+  if (rc) return rc;
+  if (!v.empty()) CK(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void driver_free(Handle *h) {
+  for (void *p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  h->h_pinned = nullptr;
+}
+
+// the `index` lambda of read_g2o, DPGO_utils.cpp:147-158
+struct Partition {
+  int64_t q, inc_n, inc;
+  Partition(int64_t N, int P) : q(N / P), inc_n(N - (int64_t)P * (N / P)), inc((N - (int64_t)P * (N / P)) * (N / P + 1)) {}
+  inline void operator()(int64_t g, int &node, int64_t &pose) const {
+    if (g < inc) { node = (int)(g / (q + 1)); pose = g % (q + 1); }
+    else { const int64_t i = g - inc; node = (int)(i / q + inc_n); pose = i % q; }
+  }
+  inline int64_t first_gid(int node) const {
+    return node < inc_n ? (int64_t)node * (q + 1) : inc + (int64_t)(node - inc_n) * q;
+  }
+};
+
+static inline int symi(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+
+// Per-edge blocks of M_e, rows/cols [t, Y_0..Y_{d-1}]  (DPGO_utils.cpp:1542-1641)
+static void edge_blocks(int d, const double *R, const double *t, double kap, double tau, double *Mii,
+                        double *Mjj, double *Mij) {
+  const int Rr = d + 1;
+  std::memset(Mii, 0, sizeof(double) * Rr * Rr);
+  std::memset(Mjj, 0, sizeof(double) * Rr * Rr);
+  std::memset(Mij, 0, sizeof(double) * Rr * Rr);
+  Mii[0] = tau; Mjj[0] = tau; Mij[0] = -tau;
+  for (int k = 0; k < d; ++k) {
+    Mii[1 + k] = tau * t[k];
+    Mii[(1 + k) * Rr] = tau * t[k];
+    Mjj[(1 + k) * Rr + 1 + k] = kap;
+    Mij[(1 + k) * Rr] = -tau * t[k];
+    for (int c = 0; c < d; ++c) {
+      Mii[(1 + k) * Rr + 1 + c] = tau * t[k] * t[c] + (k == c ? kap : 0.0);
+      Mij[(1 + k) * Rr + 1 + c] = -kap * R[k * d + c];
+    }
+  }
+}
+
+// dense SPD inverse via Cholesky (the reference factors G00 with CHOLMOD,
+// DPGOProblem.cpp:93); nodes small enough keep G00^{-1} explicitly.
+static bool dense_spd_inverse(int n, std::vector<double> &A) {
+  std::vector<double> L((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      double s = A[(size_t)i * n + j];
+      const double *li = &L[(size_t)i * n], *lj = &L[(size_t)j * n];
+      for (int k = 0; k < j; ++k) s -= li[k] * lj[k];
+      if (i == j) {
+        if (s <= 0.0) return false;
+        L[(size_t)i * n + i] = std::sqrt(s);
+      } else {
+        L[(size_t)i * n + j] = s / L[(size_t)j * n + j];
+      }
+    }
+  }
+  std::vector<double> Lt((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) Lt[(size_t)j * n + i] = L[(size_t)i * n + j];
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int c = 0; c < n; ++c) {
+    std::vector<double> y(n, 0.0);
+    for (int i = c; i < n; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      const double *li = &L[(size_t)i * n];
+      for (int k = c; k < i; ++k) s -= li[k] * y[k];
+      y[i] = s / li[i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = y[i];
+      const double *lt = &Lt[(size_t)i * n];
+      for (int k = i + 1; k < n; ++k) s -= lt[k] * y[k];
+      y[i] = s / lt[i];
+    }
+    for (int i = 0; i < n; ++i) A[(size_t)i * n + c] = y[i];
+  }
+  // symmetrise
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) {
+      const double v = 0.5 * (A[(size_t)i * n + j] + A[(size_t)j * n + i]);
+      A[(size_t)i * n + j] = v;
+      A[(size_t)j * n + i] = v;
+    }
+  return true;
+}
+
+static bool small_inverse(int d, const double *M, double *out) {
+  // Gauss-Jordan on a d x d SPD block
+  double a[9], b[9];
+  for (int i = 0; i < d * d; ++i) { a[i] = M[i]; b[i] = 0.0; }
+  for (int i = 0; i < d; ++i) b[i * d + i] = 1.0;
+  for (int c = 0; c < d; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < d; ++r) if (std::fabs(a[r * d + c]) > std::fabs(a[piv * d + c])) piv = r;
+    if (a[piv * d + c] == 0.0) return false;
+    if (piv != c) for (int k = 0; k < d; ++k) { std::swap(a[c * d + k], a[piv * d + k]); std::swap(b[c * d + k], b[piv * d + k]); }
+    const double iv = 1.0 / a[c * d + c];
+    for (int k = 0; k < d; ++k) { a[c * d + k] *= iv; b[c * d + k] *= iv; }
+    for (int r = 0; r < d; ++r) if (r != c) {
+      const double f = a[r * d + c];
+      for (int k = 0; k < d; ++k) { a[r * d + k] -= f * a[c * d + k]; b[r * d + k] -= f * b[c * d + k]; }
+    }
+  }
+  for (int i = 0; i < d * d; ++i) out[i] = b[i];
+  return true;
+}
+
+int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne, int64_t E, const int32_t *ei,
+                     const int32_t *ej, const double *R, const double *t, const double *kappa,
+                     const double *tau) {
+  if (d != 2 && d != 3) { set_error("d must be 2 or 3"); return MMPGO_ERR_ARG; }
+  if (N <= 0 || num_nodes <= 0 || nb < 0 || ne > num_nodes || nb >= ne || E < 0 || N < num_nodes) {
+    set_error("inconsistent graph sizes");
+    return MMPGO_ERR_ARG;
+  }
+  if (h->graph_set) { set_error("graph already set"); return MMPGO_ERR_STATE; }
+  h->d = d; h->N = N; h->num_nodes = num_nodes; h->node_begin = nb; h->node_end = ne; h->A = ne - nb;
+  const int A = h->A, Rr = d + 1, PB = (d + 1) * d, BB = Rr * Rr, SYM = Rr * (Rr + 1) / 2, TNV = 1 + d + d * d;
+  const Partition part(N, num_nodes);
+  for (int64_t e = 0; e < E; ++e)
+    if (ei[e] < 0 || ej[e] < 0 || ei[e] >= N || ej[e] >= N || ei[e] == ej[e]) {
+      set_error("edge endpoint out of range");
+      return MMPGO_ERR_ARG;
+    }
+
+  // ---- which poses appear in a measurement (generate_data_info only indexes those, :358-372)
+  std::vector<uint8_t> present(N, 0);
+  for (int64_t e = 0; e < E; ++e) { present[ei[e]] = 1; present[ej[e]] = 1; }
+  // own index of every local pose: rank among the node's present poses (:400-415)
+  h->node_off.assign(A + 1, 0);
+  h->info.assign(A, NodeInfo());
+  std::vector<int> dev_index(N, -1);
+  h->own_gid.clear();
+  for (int a = 0; a < A; ++a) {
+    const int node = nb + a;
+    const int64_t g0 = part.first_gid(node), g1 = (node + 1 < num_nodes) ? part.first_gid(node + 1) : N;
+    h->info[a].first_gid = -1;
+    for (int64_t g = g0; g < g1; ++g)
+      if (present[g]) {
+        if (h->info[a].first_gid < 0) h->info[a].first_gid = g;
+        dev_index[g] = (int)h->own_gid.size();
+        h->own_gid.push_back(g);
+      }
+    h->node_off[a + 1] = (int)h->own_gid.size();
+    h->info[a].n0 = h->node_off[a + 1] - h->node_off[a];
+    if (h->info[a].n0 == 0) { set_error("a node has no measurements"); return MMPGO_ERR_ARG; }
+  }
+  h->NO = (int)h->own_gid.size();
+  const int NO = h->NO;
+  std::vector<int> own_node(NO);
+  for (int a = 0; a < A; ++a) for (int p = h->node_off[a]; p < h->node_off[a + 1]; ++p) own_node[p] = a;
+
+  // ---- classify edges, collect halo poses
+  std::vector<int> en_i(E), en_j(E);
+  std::vector<int64_t> halo;
+  for (int64_t e = 0; e < E; ++e) {
+    int64_t pp;
+    part(ei[e], en_i[e], pp);
+    part(ej[e], en_j[e], pp);
+    const bool li = en_i[e] >= nb && en_i[e] < ne, lj = en_j[e] >= nb && en_j[e] < ne;
+    if (li && !lj) halo.push_back(ej[e]);
+    if (lj && !li) halo.push_back(ei[e]);
+  }
+  std::sort(halo.begin(), halo.end());
+  halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+  h->halo_gid = halo;
+  h->NH = (int)halo.size();
+  h->NP = NO + h->NH;
+  h->halo_owner.resize(h->NH);
+  for (int k = 0; k < h->NH; ++k) {
+    int nd; int64_t pp;
+    part(halo[k], nd, pp);
+    h->halo_owner[k] = nd;
+    dev_index[halo[k]] = NO + k;
+  }
+
+  // ---- count rows
+  std::vector<int> rowcnt(NO, 0), xrowcnt(NO, 0);
+  int64_t n_owned = 0;
+  for (int64_t e = 0; e < E; ++e) {
+    const bool li = en_i[e] >= nb && en_i[e] < ne, lj = en_j[e] >= nb && en_j[e] < ne;
+    if (!li && !lj) continue;
+    if (en_i[e] == en_j[e]) {
+      rowcnt[dev_index[ei[e]]]++; rowcnt[dev_index[ej[e]]]++;
+      h->info[en_i[e] - nb].m0++;
+      n_owned++;
+    } else {
+      if (li) { xrowcnt[dev_index[ei[e]]]++; h->info[en_i[e] - nb].m1++; n_owned++; }
+      if (lj) { xrowcnt[dev_index[ej[e]]]++; h->info[en_j[e] - nb].m1++; }
+    }
+  }
+  std::vector<int> rowptr(NO + 1, 0), xrowptr(NO + 1, 0);
+  for (int p = 0; p < NO; ++p) { rowptr[p + 1] = rowptr[p] + rowcnt[p]; xrowptr[p + 1] = xrowptr[p] + xrowcnt[p]; }
+  const int64_t nnz = rowptr[NO], nxe = xrowptr[NO];
+  h->n_intra_entries = nnz; h->n_inter_he = nxe; h->n_edges_owned = n_owned;
+  std::vector<int> col(nnz), fill(NO, 0), xfill(NO, 0);
+  std::vector<double> blk((size_t)nnz * BB), dintra((size_t)NO * SYM, 0.0), dinter((size_t)NO * SYM, 0.0);
+  std::vector<InterRec> xrec(nxe);
+  std::vector<EdgeRec> erec(n_owned);
+  // neighbour sets per node for n1
+  std::vector<std::vector<int64_t>> nbrs(A);
+  int64_t eo = 0;
+  double Mii[16], Mjj[16], Mij[16];
+  for (int64_t e = 0; e < E; ++e) {
+    const bool li = en_i[e] >= nb && en_i[e] < ne, lj = en_j[e] >= nb && en_j[e] < ne;
+    if (!li && !lj) continue;
+    const double *Re = R + (size_t)e * d * d, *te = t + (size_t)e * d;
+    edge_blocks(d, Re, te, kappa[e], tau[e], Mii, Mjj, Mij);
+    const int pi = dev_index[ei[e]], pj = dev_index[ej[e]];
+    const bool intra = en_i[e] == en_j[e];
+    if (intra || li) {
+      EdgeRec &r = erec[eo++];
+      std::memset(&r, 0, sizeof(r));
+      r.i = pi; r.j = pj; r.tau = tau[e]; r.kappa = kappa[e]; r.inter = intra ? 0 : 1;
+      for (int k = 0; k < d; ++k) r.t[k] = te[k];
+      for (int k = 0; k < d * d; ++k) r.R[k] = Re[k];
+    }
+    if (intra) {
+      int s = rowptr[pi] + fill[pi]++;
+      col[s] = pj;
+      std::memcpy(&blk[(size_t)s * BB], Mij, sizeof(double) * BB);
+      s = rowptr[pj] + fill[pj]++;
+      col[s] = pi;
+      for (int r = 0; r < Rr; ++r) for (int c = 0; c < Rr; ++c) blk[(size_t)s * BB + r * Rr + c] = Mij[c * Rr + r];
+      for (int r = 0; r < Rr; ++r) for (int c = 0; c <= r; ++c) {
+        dintra[(size_t)pi * SYM + symi(r, c)] += Mii[r * Rr + c];
+        dintra[(size_t)pj * SYM + symi(r, c)] += Mjj[r * Rr + c];
+      }
+    } else {
+      for (int side = 0; side < 2; ++side) {
+        const bool own_i = side == 0;
+        if (own_i ? !li : !lj) continue;
+        const int po = own_i ? pi : pj, pn = own_i ? pj : pi;
+        const int a = (own_i ? en_i[e] : en_j[e]) - nb;
+        const int s = xrowptr[po] + xfill[po]++;
+        InterRec &r = xrec[s];
+        std::memset(&r, 0, sizeof(r));
+        r.other = pn; r.own_is_i = own_i ? 1 : 0; r.tau = tau[e]; r.kappa = kappa[e];
+        for (int k = 0; k < d; ++k) r.t[k] = te[k];
+        for (int k = 0; k < d * d; ++k) r.R[k] = Re[k];
+        h->info[a].inter_he.push_back(s);
+        nbrs[a].push_back(own_i ? ej[e] : ei[e]);
+        const double *Md = own_i ? Mii : Mjj;
+        for (int rr = 0; rr < Rr; ++rr) for (int c = 0; c <= rr; ++c) dinter[(size_t)po * SYM + symi(rr, c)] += Md[rr * Rr + c];
+      }
+    }
+  }
+  for (int a = 0; a < A; ++a) {
+    std::sort(nbrs[a].begin(), nbrs[a].end());
+    h->info[a].n1 = (int)(std::unique(nbrs[a].begin(), nbrs[a].end()) - nbrs[a].begin());
+  }
+
+  // ---- pose-local constants: G diagonal, H -> T, N, V', preconditioner, G00
+  const double xi = h->opt.regularizer;
+  std::vector<double> gdiag((size_t)NO * SYM), tnv((size_t)NO * TNV), pinv((size_t)NO * d * d, 0.0), d00(NO), a00(nnz);
+  for (int p = 0; p < NO; ++p) {
+    double Hm[16], Gm[16];
+    for (int r = 0; r < Rr; ++r) for (int c = 0; c < Rr; ++c) {
+      const double di = dintra[(size_t)p * SYM + symi(r, c)], dx = dinter[(size_t)p * SYM + symi(r, c)];
+      Gm[r * Rr + c] = di + 2.0 * dx + (r == c ? xi : 0.0);          // :2212-2243
+      Hm[r * Rr + c] = 2.0 * di + 2.0 * dx + (r == c ? 1.5 * xi : 0.0); // :1679-1755, 2038-2096
+    }
+    for (int r = 0; r < Rr; ++r) for (int c = 0; c <= r; ++c) gdiag[(size_t)p * SYM + symi(r, c)] = Gm[r * Rr + c];
+    double *c_ = &tnv[(size_t)p * TNV];
+    const double T = 1.0 / Hm[0];                                      // T = T.inverse(), :2280
+    c_[0] = T;
+    for (int k = 0; k < d; ++k) c_[1 + k] = T * Hm[1 + k];             // N = T * N, :2282
+    for (int r = 0; r < d; ++r) for (int c = 0; c < d; ++c)            // V' = H_RR - H_Rt T H_tR, :2962-2964
+      c_[1 + d + r * d + c] = Hm[(1 + r) * Rr + 1 + c] - Hm[(1 + r) * Rr] * (T * Hm[1 + c]);
+    d00[p] = Gm[0];
+    double g11[9];
+    for (int r = 0; r < d; ++r) for (int c = 0; c < d; ++c) g11[r * d + c] = Gm[(1 + r) * Rr + 1 + c];
+    if (h->opt.preconditioner == MMPGO_PRECON_BLOCK_JACOBI) {
+      if (!small_inverse(d, g11, &pinv[(size_t)p * d * d])) { set_error("singular G11 block"); return MMPGO_ERR_ARG; }
+    } else {
+      for (int r = 0; r < d; ++r) pinv[(size_t)p * d * d + r * d + r] = 1.0 / g11[r * d + r];  // DPGOProblem.cpp:96-98
+    }
+  }
+  for (int64_t s = 0; s < nnz; ++s) a00[s] = blk[(size_t)s * BB];
+
+  // ---- tiles (never straddle a node)
+  std::vector<int> tnode, tstart, tcnt;
+  h->h_node_tb.assign(A, 0); h->h_node_te.assign(A, 0);
+  for (int a = 0; a < A; ++a) {
+    h->h_node_tb[a] = (int)tnode.size();
+    for (int p = h->node_off[a]; p < h->node_off[a + 1]; p += TILE) {
+      tnode.push_back(a); tstart.push_back(p); tcnt.push_back(std::min(TILE, h->node_off[a + 1] - p));
+    }
+    h->h_node_te[a] = (int)tnode.size();
+  }
+  h->n_tiles = (int)tnode.size();
+  h->h_tile_node = tnode;
+
+  // ---- dense G00^{-1} for small nodes
+  std::vector<long long> dense_off(A, -1);
+  std::vector<double> ginv;
+  h->dense_mask.assign(A, 0); h->pcg_mask.assign(A, 0);
+  h->max_dense_n0 = 0;
+  for (int a = 0; a < A; ++a) {
+    const int n0 = h->info[a].n0;
+    if (n0 <= h->opt.dense_solve_max_n) {
+      std::vector<double> M((size_t)n0 * n0, 0.0);
+      const int off = h->node_off[a];
+      for (int p = 0; p < n0; ++p) {
+        M[(size_t)p * n0 + p] += d00[off + p];
+        for (int s = rowptr[off + p]; s < rowptr[off + p + 1]; ++s) M[(size_t)p * n0 + (col[s] - off)] += a00[s];
+      }
+      if (!dense_spd_inverse(n0, M)) { set_error("G00 is not positive definite"); return MMPGO_ERR_ARG; }
+      dense_off[a] = (long long)ginv.size();
+      ginv.insert(ginv.end(), M.begin(), M.end());
+      h->info[a].dense = true; h->dense_mask[a] = 1; h->any_dense = true;
+      h->max_dense_n0 = std::max(h->max_dense_n0, n0);
+    } else {
+      h->pcg_mask[a] = 1; h->any_pcg = true;
+    }
+  }
+
+  // ---- upload
+  int rc = 0;
+  if ((rc = upload(h, &h->d_rowptr, rowptr))) return rc;
+  if ((rc = upload(h, &h->d_col, col))) return rc;
+  if ((rc = upload(h, &h->d_blk, blk))) return rc;
+  if ((rc = upload(h, &h->d_gdiag, gdiag))) return rc;
+  if ((rc = upload(h, &h->d_dintra, dintra))) return rc;
+  if ((rc = upload(h, &h->d_dinter, dinter))) return rc;
+  if ((rc = upload(h, &h->d_tnv, tnv))) return rc;
+  if ((rc = upload(h, &h->d_pinv, pinv))) return rc;
+  if ((rc = upload(h, &h->d_a00, a00))) return rc;
+  if ((rc = upload(h, &h->d_d00, d00))) return rc;
+  if ((rc = upload(h, &h->d_xrowptr, xrowptr))) return rc;
+  if ((rc = upload(h, &h->d_xrec, xrec))) return rc;
+  if ((rc = upload(h, &h->d_erec, erec))) return rc;
+  if ((rc = upload(h, &h->d_ginv, ginv))) return rc;
+  if ((rc = upload(h, &h->d_dense_off, dense_off))) return rc;
+  if ((rc = upload(h, &h->d_tile_node, tnode))) return rc;
+  if ((rc = upload(h, &h->d_tile_start, tstart))) return rc;
+  if ((rc = upload(h, &h->d_tile_cnt, tcnt))) return rc;
+  if ((rc = upload(h, &h->d_node_tb, h->h_node_tb))) return rc;
+  if ((rc = upload(h, &h->d_node_te, h->h_node_te))) return rc;
+  if ((rc = upload(h, &h->d_node_off, h->node_off))) return rc;
+  if ((rc = dalloc(h, &h->d_active, (size_t)A))) return rc;
+  if ((rc = dalloc(h, &h->d_active2, (size_t)A))) return rc;
+  const size_t np = (size_t)h->NP * PB, no = (size_t)NO * PB, nc = (size_t)NO * d;
+  for (int k = 0; k < 3; ++k) if ((rc = dalloc(h, &h->X[k], np))) return rc;
+  double **pv[] = {&h->Xakh, &h->Yex, &h->xprop, &h->xeval};
+  for (auto q : pv) if ((rc = dalloc(h, q, np))) return rc;
+  double **ov[] = {&h->g[0], &h->g[1], &h->Df[0], &h->Df[1], &h->gex, &h->Dfex, &h->nab, &h->grad,
+                   &h->cg_s, &h->cg_r, &h->cg_v, &h->cg_p, &h->cg_Hp};
+  for (auto q : ov) if ((rc = dalloc(h, q, no))) return rc;
+  double **cv[] = {&h->rhs_t, &h->tsol, &h->pr, &h->pz, &h->pp, &h->pap};
+  for (auto q : cv) if ((rc = dalloc(h, q, nc))) return rc;
+  if ((rc = dalloc(h, &h->d_pcg_state, (size_t)A * 8))) return rc;
+  double **wv[] = {&h->w_cur, &h->w_prev, &h->w_tmp};
+  for (auto q : wv) if ((rc = dalloc(h, q, (size_t)nxe))) return rc;
+  if ((rc = dalloc(h, &h->d_partials, (size_t)h->n_tiles * NS))) return rc;
+  if ((rc = dalloc(h, &h->d_node_scal, (size_t)A * NS))) return rc;
+  if ((rc = dalloc(h, &h->d_coef, (size_t)A * MAXC))) return rc;
+  if ((rc = dalloc(h, &h->d_gamma, (size_t)A))) return rc;
+  if ((rc = dalloc(h, &h->d_block_partials, (size_t)148 * 8 + 8))) return rc;
+  if ((rc = dalloc(h, &h->d_scalar, (size_t)8))) return rc;
+  CK(cudaMallocHost((void **)&h->h_pinned, sizeof(double) * ((size_t)A * (NS + 8) + 64)));
+  CK(cudaStreamSynchronize(h->stream));
+  h->st.assign(A, NodeState());
+  h->graph_set = true;
+  return 0;
+}
+
+}  // namespace mmpgo

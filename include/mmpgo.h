@@ -1,0 +1,167 @@
+/* mmpgo.h -- C ABI of the B200 MM-PGO / AMM-PGO* / AMM-PGO# iteration.
+ *
+ * One handle = the robot nodes [node_begin, node_end) of one pose graph, bound
+ * to one CUDA device.  All pointers are HOST pointers borrowed for the call
+ * unless the name ends in _dev.  Every function returns 0 on success and a
+ * negative mmpgo_status otherwise (the reference's drivers return int 0 / -1,
+ * C++/DPGO/include/DPGO/DPGOHash.h:20-28); no exceptions cross the boundary.
+ * A handle is not thread-safe; different handles may be driven concurrently.
+ *
+ * Matrix conventions follow the reference: a global iterate X is
+ * ((d+1) N) x d, column-major (Eigen::MatrixXd), rows [t_0..t_{N-1};
+ * R-block_0 .. R-block_{N-1}] with d rows per rotation block
+ * (C++/examples/dist_pgo.cpp:502-511, C++/DPGO/src/DPGOStar.cpp:541-547).
+ *
+ * Each entry point cites the reference interface it replaces.
+ */
+#ifndef MMPGO_H_
+#define MMPGO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmpgo_handle_s *mmpgo_handle;
+
+enum mmpgo_status {
+  MMPGO_OK = 0,
+  MMPGO_ERR_ARG = -1,        /* inconsistent sizes (reference: LOG(ERROR); return -1) */
+  MMPGO_ERR_CUDA = -2,       /* a CUDA call failed; see mmpgo_last_error */
+  MMPGO_ERR_STATE = -3,      /* call order violated (e.g. iterate before update) */
+  MMPGO_ERR_UNSUPPORTED = -4
+};
+
+/* DPGO::Loss, C++/DPGO/include/DPGO/DPGO_types.h:67 */
+enum mmpgo_loss { MMPGO_LOSS_NONE = 0, MMPGO_LOSS_HUBER = 1,
+                  MMPGO_LOSS_GEMAN_MCCLURE = 2, MMPGO_LOSS_WELSCH = 3 };
+/* DPGO::Scheme, DPGO_types.h:70-75 */
+enum mmpgo_scheme { MMPGO_SCHEME_MM = 0, MMPGO_SCHEME_AMM = 1 };
+/* DPGO::Preconditioner, DPGO_types.h:35-40, plus the per-pose d x d
+ * block-Jacobi preconditioner of the device path. */
+enum mmpgo_preconditioner { MMPGO_PRECON_NONE = 0, MMPGO_PRECON_JACOBI = 1,
+                            MMPGO_PRECON_BLOCK_JACOBI = 2 };
+/* Which driver class the handle emulates. */
+enum mmpgo_algorithm { MMPGO_ALG_HASH = 0,   /* DPGOHash: AMM-PGO# / MM-PGO */
+                       MMPGO_ALG_STAR = 1 }; /* DPGOStar: AMM-PGO*          */
+
+/* DPGO::Options (DPGO_types.h:78-201); mmpgo_default_options() fills in the
+ * values `dist_pgo` uses (C++/examples/dist_pgo.cpp:103-120). */
+typedef struct mmpgo_options {
+  int32_t algorithm;             /* mmpgo_algorithm */
+  int32_t scheme;                /* mmpgo_scheme */
+  int32_t loss;                  /* mmpgo_loss */
+  int32_t preconditioner;        /* mmpgo_preconditioner */
+  double regularizer;            /* xi, 1e-11 */
+  double loss_reg;               /* delta, 0.25 */
+  double accepted_delta;         /* 5e-4 */
+  double eta[2];                 /* 5e-4, 2.5e-2 */
+  double psi, phi;               /* 1e-10, 1e-6 */
+  int32_t max_soft_restart_hits[2];   /* 10, 25 */
+  int32_t oscillation_cnt_period;     /* 15 */
+  int32_t max_oscillations;           /* 12 */
+  double grad_norm_tol;               /* 1e-3 */
+  double preconditioned_grad_norm_tol;/* 1e-4 */
+  double rel_func_decrease_tol;       /* 1e-6 */
+  double stepsize_tol;                /* 1e-4 */
+  int32_t max_iterations;             /* TNT outer iterations, 10 */
+  int32_t max_iterations_accepted;    /* 1 */
+  int32_t max_tCG_iterations;         /* 10000 */
+  double STPCG_kappa, STPCG_theta;    /* 0.05, 0.9 */
+  /* device-path knobs (no reference counterpart) */
+  int32_t dense_solve_max_n;     /* nodes with n0 <= this use a dense G00^{-1}; else PCG */
+  double translation_solve_tol;  /* relative residual of the G00 PCG, 1e-12 */
+  int32_t translation_solve_max_iters;
+  int32_t device;                /* CUDA device ordinal */
+  int32_t reserved[7];
+} mmpgo_options;
+
+/* DPGOResult scalars a caller of results() reads (DPGO_types.h:204-322). */
+typedef struct mmpgo_node_scalars {
+  double fobj, f, Gk, gradFnorm, Fk[2], s, s_next, gamma;
+  int32_t iters, soft_restart_hits[2], num_oscillations;
+  int32_t refined, restarts, tcg_iterations, tnt_iterations;
+  int32_t n0, n1, m0, m1;
+  int32_t translation_solve_iters, reserved;
+} mmpgo_node_scalars;
+
+/* Kernel launch / byte accounting used by bench.py (gpu_launches, roofline). */
+typedef struct mmpgo_counters {
+  int64_t launches;               /* kernels launched by this handle */
+  int64_t intra_passes;           /* K2 block-CSR passes */
+  int64_t inter_passes;           /* K1 inter-edge passes */
+  int64_t prox_passes;            /* K3 fused extrapolate+proximal+projection */
+  int64_t solve_calls, solve_iters;   /* K2b G00 solves / PCG iterations */
+  int64_t tcg_iterations, tnt_iterations;
+  int64_t vector_passes;
+  int64_t reserved[7];
+} mmpgo_counters;
+
+const char *mmpgo_version(void);
+const char *mmpgo_last_error(void);
+void mmpgo_default_options(mmpgo_options *opts);
+
+/* Replaces the DPGOHash / DPGOStar constructors (DPGOHash.h:18, DPGOStar.h:16-19). */
+int mmpgo_create(const mmpgo_options *opts, mmpgo_handle *out);
+int mmpgo_destroy(mmpgo_handle h);
+
+/* Replaces DPGO::read_g2o's partition (C++/DPGO/src/DPGO_utils.cpp:140-202),
+ * generate_data_info (:326-438) and the DPGOProblem constructor
+ * (C++/DPGO/src/DPGOProblem.cpp:11-125).  Edges carry GLOBAL pose ids; the
+ * contiguous id-range partition into num_nodes robot nodes is the reference's.
+ * R is row-major d x d per edge, t has d entries per edge. */
+int mmpgo_set_graph(mmpgo_handle h, int32_t d, int64_t num_poses, int32_t num_nodes,
+                    int32_t node_begin, int32_t node_end, int64_t num_edges,
+                    const int32_t *edge_i, const int32_t *edge_j, const double *R,
+                    const double *t, const double *kappa, const double *tau);
+
+/* DPGOHash::initialize (DPGOHash.cpp:20-43) / DPGOStar::initialize
+ * (DPGOStar.cpp:109-124) for all local nodes; X is the GLOBAL iterate, ldx its
+ * leading dimension (>= (d+1) N).  Neighbour copies are taken from X too
+ * (what DPGO::communicate does at dist_pgo.cpp:446). */
+int mmpgo_initialize(mmpgo_handle h, const double *X, int64_t ldx);
+/* DPGOHash::update (DPGOHash.cpp:84-228) / DPGOStar::update (:225-231). */
+int mmpgo_update(mmpgo_handle h);
+/* DPGOHash::iterate (DPGOHash.cpp:583-628) / DPGOStar::iterate (:126-213)
+ * for all local nodes, batched. */
+int mmpgo_iterate(mmpgo_handle h);
+/* DPGOHash::communicate (DPGOHash.h:28-86) / DPGOStar::communicate (:215-223):
+ * publishes the new own poses.  With remote neighbours the caller exchanges
+ * the packed boundary buffers between begin and end (see halo API below). */
+int mmpgo_communicate(mmpgo_handle h);
+
+/* results().Xk (DPGO_types.h:208): writes the rows of the local nodes' own
+ * poses into a GLOBAL-layout X. */
+int mmpgo_get_poses(mmpgo_handle h, double *X, int64_t ldx);
+int mmpgo_get_node_scalars(mmpgo_handle h, int32_t node, mmpgo_node_scalars *out);
+/* DPGOProblem::evaluate_E's DiagReg (DPGOProblem.cpp:647-675): IRLS weight of
+ * every inter-node measurement of `node`, in the order of the node's
+ * inter_measurements() list.  *count receives m1. */
+int mmpgo_get_weights(mmpgo_handle h, int32_t node, double *w, int64_t capacity,
+                      int64_t *count);
+/* DPGOStar::evaluate_f (DPGOStar.cpp:713-761) restricted to the edges owned
+ * by the local nodes (each inter-node edge is owned by the node of its i
+ * endpoint); summing over handles gives F.  X is a full GLOBAL iterate. */
+int mmpgo_evaluate_f(mmpgo_handle h, const double *X, int64_t ldx, double *fobj);
+/* Objective of the CURRENT device iterate, no host<->device pose traffic
+ * (what dist_pgo logs each iteration, dist_pgo.cpp:523-530). */
+int mmpgo_current_objective(mmpgo_handle h, double *fobj, double *grad_sqnorm);
+
+/* AMM-PGO* master-node scalars: F (the running average, DPGOStar.cpp:210),
+ * the last accepted global objective and the number of global restarts. */
+int mmpgo_star_objective(mmpgo_handle h, double *F, double *fobj, int32_t *restarts);
+/* sizes[8] = {own poses, halo poses, block-CSR entries, inter half-edges,
+ * owned edges, tiles, local nodes, d} */
+int mmpgo_graph_sizes(mmpgo_handle h, int64_t *sizes);
+
+int mmpgo_get_counters(mmpgo_handle h, mmpgo_counters *out);
+int mmpgo_reset_counters(mmpgo_handle h);
+int mmpgo_synchronize(mmpgo_handle h);
+/* the CUDA stream all kernels of this handle are launched on (cudaStream_t) */
+void *mmpgo_stream(mmpgo_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMPGO_H_ */
