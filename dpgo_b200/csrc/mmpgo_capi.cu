@@ -182,6 +182,12 @@ int mmpgo_star_objective(mmpgo_handle hh, double *F, double *fobj, int32_t *rest
   return MMPGO_OK;
 }
 
+int mmpgo_profile_pass(mmpgo_handle hh, int32_t kind, int32_t reps, float *ms_avg) {
+  H_OR_FAIL(hh);
+  if (!ms_avg) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::driver_profile_pass(h, kind, reps, ms_avg));
+}
+
 int mmpgo_get_counters(mmpgo_handle hh, mmpgo_counters *out) {
   H_OR_FAIL(hh);
   if (!out) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }

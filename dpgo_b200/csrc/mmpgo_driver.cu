@@ -825,6 +825,67 @@ int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f) {
   return h->d == 2 ? Drv<2>::edge_objective(h, h->xeval, f) : Drv<3>::edge_objective(h, h->xeval, f);
 }
 
+// Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA
+// events (bench.py's live roofline measurement).  kind: 0 G_EVAL, 1 G_GRAD, 2 inter pass,
+// 3 fused proximal, 4 edge objective, 5 G00 SpMV, 6 G_HV, 7 G_RHS_T.
+template <int D> static int profile_pass(Handle *h, int kind, int reps, float *ms_avg) {
+  typedef Drv<D> Dr;
+  const Mask allm(h->A, 1);
+  Tiles tl; RC(make_tiles(h, allm, &tl));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const double *Xk = h->X[h->ik];
+  auto one = [&]() -> int {
+    if (kind == 0 || kind == 1 || kind == 6 || kind == 7) {
+      GPassArgs a = Dr::gargs(h);
+      a.x = Xk; a.g = h->g[h->icur]; a.out = kind == 7 ? h->rhs_t : h->Dfex; a.out2 = h->grad;
+      a.xref = Xk; a.nab = h->Df[h->icur];
+      launch_gpass<D>(kind == 0 ? G_EVAL : kind == 1 ? G_GRAD : kind == 6 ? G_HV : G_RHS_T, tl, a, h->stream);
+    } else if (kind == 2) {
+      InterArgs ia; std::memset(&ia, 0, sizeof(ia));
+      ia.rowptr = h->d_xrowptr; ia.rec = h->d_xrec; ia.xa = Xk; ia.xb = nullptr; ia.dinter = h->d_dinter;
+      ia.loss = h->opt.loss; ia.loss_reg = h->opt.loss_reg; ia.xi = h->opt.regularizer;
+      ia.w_out = h->w_tmp; ia.g = h->gex; ia.partials = h->d_partials;
+      launch_inter<D>(h->opt.loss == MMPGO_LOSS_NONE ? I_TRIVIAL : I_ROBUST, tl, ia, h->stream);
+    } else if (kind == 3) {
+      ProxArgs a; std::memset(&a, 0, sizeof(a));
+      a.xa = Xk; a.xb = h->X[h->ikm1]; a.dfa = h->Df[h->icur]; a.dfb = h->Df[h->icur ^ 1];
+      a.ga = h->g[h->icur]; a.gb = h->g[h->icur ^ 1]; a.gamma = h->d_gamma; a.tnv = h->d_tnv; a.xref = Xk;
+      a.xout = h->xprop; a.gex = h->gex; a.partials = h->d_partials;
+      launch_prox<D>(tl, a, h->stream);
+    } else if (kind == 4) {
+      int nb = 0;
+      launch_edge_objective<D>(h->n_edges_owned, h->d_erec, Xk, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
+                               &nb, h->stream);
+    } else if (kind == 5) {
+      SolveArgs sa;
+      sa.rowptr = h->d_rowptr; sa.col = h->d_col; sa.a00 = h->d_a00; sa.d00 = h->d_d00;
+      sa.node_tile_begin = h->d_node_tb; sa.node_tile_end = h->d_node_te; sa.state = h->d_pcg_state; sa.tol2 = 0;
+      launch_pcg_spmv<D>(tl, sa, h->pp, h->pap, h->d_partials, 0, h->stream);
+    } else {
+      set_error("unknown kernel kind");
+      return MMPGO_ERR_ARG;
+    }
+    h->ctr.launches++;
+    return 0;
+  };
+  for (int w = 0; w < 3; ++w) RC(one());
+  CK(cudaEventRecord(e0, h->stream));
+  for (int r = 0; r < reps; ++r) RC(one());
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_avg = ms / (float)reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg) {
+  if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
+  if (reps <= 0) { set_error("reps must be positive"); return MMPGO_ERR_ARG; }
+  return h->d == 2 ? profile_pass<2>(h, kind, reps, ms_avg) : profile_pass<3>(h, kind, reps, ms_avg);
+}
+
 int driver_current_objective(Handle *h, double *f, double *g2) {
   if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
   // sum_a fobj_a = F (DPGOStar.cpp:719-722 vs DPGOHash.cpp:108-118); |grad F|^2 = sum_a |gradF_a|^2

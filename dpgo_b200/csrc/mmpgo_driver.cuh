@@ -122,6 +122,7 @@ int driver_get_poses(Handle *h, double *X, int64_t ldx);
 int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *count);
 int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f);
 int driver_current_objective(Handle *h, double *f, double *g2);
+int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg);
 void driver_free(Handle *h);
 void set_error(const std::string &s);
 

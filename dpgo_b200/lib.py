@@ -97,6 +97,7 @@ SIGNATURES = {
     "mmpgo_current_objective": (C.c_int, [_P, _dp, _dp]),
     "mmpgo_star_objective": (C.c_int, [_P, _dp, _dp, _ip]),
     "mmpgo_graph_sizes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "mmpgo_profile_pass": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "mmpgo_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "mmpgo_reset_counters": (C.c_int, [_P]),
     "mmpgo_synchronize": (C.c_int, [_P]),

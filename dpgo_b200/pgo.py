@@ -150,6 +150,16 @@ class _Driver:
                 "owned_edges", "tiles", "local_nodes", "d")
         return dict(zip(keys, list(s)))
 
+    KERNEL_KINDS = {"k2_eval": 0, "k2_grad": 1, "k1_inter": 2, "k3_prox": 3, "edge_objective": 4,
+                    "g00_spmv": 5, "k2_hv": 6, "k2_g01": 7}
+
+    def profile_pass(self, kind, reps=20):
+        """Average device milliseconds of one launch of a hot kernel (CUDA events on
+        the library's stream)."""
+        ms = C.c_float()
+        L.check(self.lib.mmpgo_profile_pass(self._h, self.KERNEL_KINDS[kind], reps, C.byref(ms)))
+        return ms.value
+
     def synchronize(self):
         L.check(self.lib.mmpgo_synchronize(self._h))
 
