@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- AMM-PGO* edge-updates/s on the synthetic 1M-pose SE(3) grid (BASELINE.json
+configs[3]) at 1/2/4/8 B200, with the kernel roofline and the CPU baseline beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
+    python bench.py --impl reference --gpus N ...            # restated CPU reference (oracle)
+
+A "step" is one full AMM-PGO* iteration (iterate + communicate + update,
+C++/examples/dist_pgo.cpp:497-521) over the whole graph.  `value` = E * K / seconds with
+the graph and the iterate resident in HBM; `e2e` runs the same iteration through the
+reference-facing call sequence with HOST matrices (initialize(X_host) -> update -> iterate
+-> communicate -> X() back to host) inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "AMM-PGO* edge-updates/s on 1M-pose SE(3) graph"
+UNIT = "edge-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", default="100,100,100", help="nx,ny,nz of the synthetic SE(3) grid")
+    ap.add_argument("--nodes", type=int, default=64)
+    ap.add_argument("--loss", default="trivial")
+    ap.add_argument("--algorithm", default="star", choices=["star", "hash"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload_name(args, N, E):
+    return ("synthetic %s SE(3) grid, %d poses / %d edges, %d robot nodes, %s loss, %s"
+            % (args.grid.replace(",", "x"), N, E, args.nodes, args.loss,
+               "AMM-PGO*" if args.algorithm == "star" else "AMM-PGO#"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip().splitlines()
+                if out:
+                    self.samples.append([x.strip() for x in out[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel_key)
+    return None
+
+
+# ---------------------------------------------------------------------------
+def cpu_baseline_run(args, steps, warmup, sample_grid=(100, 125, 5), sample_nodes=4):
+    """The restated CPU reference (oracle, numpy/scipy, 1 thread) on a bounded sample of the
+    same workload: same per-node size (15625 poses per robot node, slab-shaped), same loss
+    and algorithm; setup (matrix assembly, factorisations) excluded as in dist_pgo."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dpgo_b200 as D
+    from oracle import dist_pgo as odist
+    from oracle import dpgo as odpgo
+    from parity import to_measurements
+    g, _, X0 = D.grid3d(*sample_grid)
+    opts = odpgo.Options(loss=args.loss, preconditioner="BlockJacobi")
+    meas = to_measurements(g)
+    timing = {}
+    iters = max(1, steps)
+    t0 = time.perf_counter()
+    odist.run(meas, g.num_poses, sample_nodes, opts, X0, iters, args.algorithm, log_global=False,
+              timing=timing)
+    wall = time.perf_counter() - t0
+    secs = timing["seconds"]
+    return {
+        "value": g.num_edges * iters / secs, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": "%dx%dx%d SE(3) grid slab (%d poses / %d edges, %d robot nodes of %d poses = the "
+                  "per-node size of the full workload), %d iterations, %.1f s in iterate+update+"
+                  "communicate (setup %.1f s excluded)" % (
+                      sample_grid + (g.num_poses, g.num_edges, sample_nodes, g.num_poses // sample_nodes,
+                                     iters, secs, wall - secs)),
+    }, secs, iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny, nz = (int(v) for v in args.grid.split(","))
+    N, E = nx * ny * nz, 4 * nx * ny * nz
+    steps = max(1, min(args.steps, 3))
+    cb, secs, iters = cpu_baseline_run(args, steps, 0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / iters,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(args, N, E),
+                                        "note": "upstream dist_pgo cannot be built here (no Eigen/SuiteSparse/"
+                                                "glog/Boost); this arm times the restated CPU reference "
+                                                "(oracle/, numpy+scipy) on a bounded sample, %d timed "
+                                                "iterations" % iters},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dpgo_b200 as D
+    from dpgo_b200 import multi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, ny, nz = (int(v) for v in args.grid.split(","))
+    g, _, X0 = D.grid3d(nx, ny, nz)
+    N, E, d = g.num_poses, g.num_edges, g.d
+    opts = D.Options(loss=args.loss, device=local_rank)
+    drv = multi.make_driver(g, args.nodes, opts, args.algorithm, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        D.lib.check(drv.iterate())
+        D.lib.check(drv.communicate())
+        D.lib.check(drv.update())
+
+    assert drv.initialize(X0) == 0
+    D.lib.check(drv.update())
+    for _ in range(args.warmup):
+        step()
+    stream = torch.cuda.ExternalStream(drv.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    drv.reset_counters()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    ctr = drv.counters()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    secs = ms / 1e3
+    value = E * args.steps / secs
+    F, gn = drv.global_objective()
+
+    # ---- per-kernel device times (CUDA events on the library's stream) and the roofline
+    sizes = drv.sizes()
+    E_intra = sizes["bsr_entries"] // 2
+    NO = sizes["own_poses"]
+    HE = sizes["inter_half_edges"]
+    k_ms = {k: drv.profile_pass(k, 20) for k in drv.KERNEL_KINDS}
+    per_step = {
+        "k2": ctr.intra_passes / args.steps, "k1_inter": ctr.inter_passes / args.steps,
+        "k3_prox": ctr.prox_passes / args.steps, "g00_iter": ctr.solve_iters / args.steps,
+    }
+    alg_bytes = {
+        "k2_eval": 120 * E_intra + 192 * NO, "k2_grad": 120 * E_intra + 192 * NO,
+        "k2_hv": 120 * E_intra + 192 * NO, "k2_g01": 120 * E_intra + 192 * NO,
+        "k1_inter": 120 * HE + 192 * NO, "k3_prox": 680 * NO,
+        "g00_spmv": 12 * 2 * E_intra + 4 * 8 * d * NO, "edge_objective": 120 * sizes["owned_edges"] + 96 * NO,
+    }
+    k2_avg = float(np.mean([k_ms["k2_eval"], k_ms["k2_grad"], k_ms["k2_hv"], k_ms["k2_g01"]]))
+    share = {
+        "k2 block-CSR pass": per_step["k2"] * k2_avg,
+        "g00 solve iteration": per_step["g00_iter"] * k_ms["g00_spmv"] * drv.solve_kernels_per_iter(),
+        "k1 inter-edge pass": per_step["k1_inter"] * k_ms["k1_inter"],
+        "k3 fused proximal": per_step["k3_prox"] * k_ms["k3_prox"],
+    }
+    peak, peak_src = measured_peak()
+    dom = "k2_eval"
+    achieved = alg_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "k_gpass<3,G_EVAL> (K2 block-CSR connection-Laplacian pass)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": ncu_traffic("k_gpass"), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes[dom], "launch_ms": k_ms[dom],
+        "kernel_ms": k_ms, "est_ms_per_step_by_kernel": share, "launches_per_step": per_step,
+        "all_kernels_gbs": {k: alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9 for k in k_ms},
+    }
+
+    # ---- e2e: reference-facing call sequence with host matrices inside the timed region
+    e2e = None
+    if world == 1:
+        Xh = np.asfortranarray(X0)
+        torch.cuda.synchronize()
+        assert drv.initialize(Xh) == 0 and drv.update() == 0      # warm the path once
+        drv.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            assert drv.initialize(Xh) == 0                        # H2D of the step's input
+            D.lib.check(drv.update())
+            D.lib.check(drv.iterate())
+            D.lib.check(drv.communicate())
+            Xh = drv.X()                                          # D2H of the step's result
+        drv.synchronize()
+        dt = time.perf_counter() - t0
+        nbytes = (d + 1) * N * d * 8
+        e2e = {"value": E * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": args.e2e_steps,
+               "call_sequence": "initialize(X_host); update(); iterate(); communicate(); X()"}
+    else:
+        e2e = multi.e2e_multi(drv, X0, args.e2e_steps, E, d, N)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _, _ = cpu_baseline_run(args, 2, 0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, N, E),
+                       "l2": "working set (graph %.0f MB + iterates) is larger than the 126 MB L2" % (
+                           (sizes["bsr_entries"] * 132 + HE * 128) / 1e6),
+                       "preconditioner": "BlockJacobi", "nodes_per_gpu": args.nodes // world,
+                       "final_2F": 2 * F, "final_2gradnorm": 2 * gn},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(ctr.launches), "clocks": clk.summary(),
+            "counters_per_step": {"launches": ctr.launches / args.steps, "k2_passes": per_step["k2"],
+                                  "g00_solves": ctr.solve_calls / args.steps,
+                                  "g00_iterations": per_step["g00_iter"],
+                                  "tcg_iterations": ctr.tcg_iterations / args.steps},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -182,6 +182,29 @@ int mmpgo_star_objective(mmpgo_handle hh, double *F, double *fobj, int32_t *rest
   return MMPGO_OK;
 }
 
+int mmpgo_set_sharding(mmpgo_handle hh, int32_t rank, int32_t world_size, const int32_t *rank_node_begin,
+                       mmpgo_exchange_fn exchange, mmpgo_allreduce_fn allreduce, void *user) {
+  H_OR_FAIL(hh);
+  GUARDED(mmpgo::driver_set_sharding(h, rank, world_size, rank_node_begin, exchange, allreduce, user));
+}
+int mmpgo_halo_counts(mmpgo_handle hh, int64_t *send_poses, int64_t *recv_poses) {
+  H_OR_FAIL(hh);
+  if (!send_poses || !recv_poses || (int)h->send_poses.size() != h->world) {
+    mmpgo::set_error("set_sharding first");
+    return MMPGO_ERR_STATE;
+  }
+  for (int q = 0; q < h->world; ++q) { send_poses[q] = h->send_poses[q]; recv_poses[q] = h->recv_poses[q]; }
+  return MMPGO_OK;
+}
+
+int mmpgo_plan_halo(int64_t num_poses, int32_t num_nodes, int64_t num_edges, const int32_t *edge_i,
+                    const int32_t *edge_j, int32_t world_size, const int32_t *rank_node_begin, int32_t rank,
+                    int64_t *send_counts, int64_t *recv_counts, int64_t *send_gids, int64_t send_capacity,
+                    int64_t *recv_gids, int64_t recv_capacity) {
+  GUARDED(mmpgo::plan_halo(num_poses, num_nodes, num_edges, edge_i, edge_j, world_size, rank_node_begin, rank,
+                           send_counts, recv_counts, send_gids, send_capacity, recv_gids, recv_capacity));
+}
+
 int mmpgo_profile_pass(mmpgo_handle hh, int32_t kind, int32_t reps, float *ms_avg) {
   H_OR_FAIL(hh);
   if (!ms_avg) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }

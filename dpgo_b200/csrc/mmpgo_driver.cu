@@ -74,8 +74,30 @@ static int upload_coef(Handle *h, const std::vector<double> &c) {
   return 0;
 }
 
+// sum of host scalars over all ranks (no-op for a single handle)
+static int allreduce(Handle *h, double *v, int n) {
+  if (h->world <= 1) return 0;
+  h->allreduces++;
+  if (h->allreduce_fn(h->cb_user, v, n) != 0) { set_error("allreduce callback failed"); return MMPGO_ERR_ARG; }
+  return 0;
+}
+
 template <int D> struct Drv {
   static constexpr int PB = (D + 1) * D;
+
+  // boundary poses of `x` (an NP-sized pose array) -> peers; their boundary poses -> our halo rows
+  static int halo_exchange(Handle *h, double *x) {
+    if (h->world <= 1) return 0;
+    launch_gather_poses<D>(h->n_send, h->d_send_idx, x, h->d_send, h->stream);
+    h->ctr.launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    h->halo_exchanges++;
+    if (h->exchange_fn(h->cb_user, h->d_send, h->send_dbl.data(), x + (size_t)h->NO * PB, h->recv_dbl.data()) != 0) {
+      set_error("exchange callback failed");
+      return MMPGO_ERR_ARG;
+    }
+    return 0;
+  }
 
   static GPassArgs gargs(Handle *h, const double *diag = nullptr) {
     GPassArgs a;
@@ -638,7 +660,8 @@ template <int D> struct Drv {
   }
 
   // global objective of a candidate iterate held in pose blocks (own + halo rows)
-  static int edge_objective(Handle *h, const double *x, double *f) {
+  static int edge_objective(Handle *h, double *x, double *f, bool exchange = true) {
+    if (exchange) RC(halo_exchange(h, x));
     int nb = 0;
     launch_edge_objective<D>(h->n_edges_owned, h->d_erec, x, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
                              &nb, h->stream);
@@ -647,7 +670,7 @@ template <int D> struct Drv {
     CK(cudaMemcpyAsync(h->h_pinned, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *f = h->h_pinned[0];
-    return 0;
+    return allreduce(h, f, 1);
   }
   static int diff2(Handle *h, const double *a, const double *b, double *out) {
     const Mask allm(h->A, 1);
@@ -656,7 +679,7 @@ template <int D> struct Drv {
     double t = 0.0;
     for (int n = 0; n < h->A; ++n) t += s[n * NS];
     *out = t;
-    return 0;
+    return allreduce(h, out, 1);
   }
 
   // ---- DPGOStar::iterate (DPGOStar.cpp:126-213), single-handle form (all nodes local)
@@ -664,7 +687,7 @@ template <int D> struct Drv {
     const int A = h->A;
     const mmpgo_options &o = h->opt;
     const Mask allm(A, 1);
-    const double *Xk = h->X[h->ik];
+    double *Xk = h->X[h->ik];
     double *Xak = h->X[h->iak];      // X^{k+1} candidate ("Xkp")
     const double *gk = h->g[h->icur], *Dfk = h->Df[h->icur];
     Mask refined(A, 0), plain(A, 0);
@@ -732,7 +755,7 @@ template <int D> struct Drv {
   static int communicate(Handle *h) {
     const int old_km1 = h->ikm1;
     h->ikm1 = h->ik; h->ik = h->iak; h->iak = old_km1;
-    return 0;
+    return halo_exchange(h, h->X[h->ik]);
   }
 };
 
@@ -769,7 +792,8 @@ int driver_initialize(Handle *h, const double *X, int64_t ldx) {
   h->star_restarts = 0;
   if (h->opt.algorithm == MMPGO_ALG_STAR) {
     double f = 0.0;
-    int rc = h->d == 2 ? Drv<2>::edge_objective(h, h->X[h->ik], &f) : Drv<3>::edge_objective(h, h->X[h->ik], &f);
+    int rc = h->d == 2 ? Drv<2>::edge_objective(h, h->X[h->ik], &f, false)
+                       : Drv<3>::edge_objective(h, h->X[h->ik], &f, false);
     if (rc) return rc;
     h->star_fobj = f; h->starF = f;                                   // DPGOStar.cpp:120-122
   }
@@ -822,7 +846,12 @@ int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f) {
   std::vector<double> buf;
   pack_all(h, X, ldx, buf);
   CK(cudaMemcpyAsync(h->xeval, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  return h->d == 2 ? Drv<2>::edge_objective(h, h->xeval, f) : Drv<3>::edge_objective(h, h->xeval, f);
+  // evaluate_f reports the LOCAL partial sum (see mmpgo.h); halo rows come from X itself
+  const int world = h->world;
+  h->world = 1;
+  const int rc = h->d == 2 ? Drv<2>::edge_objective(h, h->xeval, f, false) : Drv<3>::edge_objective(h, h->xeval, f, false);
+  h->world = world;
+  return rc;
 }
 
 // Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA

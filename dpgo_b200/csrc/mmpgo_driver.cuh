@@ -102,11 +102,16 @@ struct Handle {
   int star_restarts = 0;
   // halo exchange
   int rank = 0, world = 1;
-  std::vector<int> node_owner;
-  std::vector<int64_t> send_counts, recv_counts;
-  int *d_send_idx = nullptr, *d_recv_idx = nullptr;
-  int64_t n_send = 0, n_recv = 0;
-  double *d_send = nullptr, *d_recv = nullptr;
+  std::vector<std::pair<int, int>> boundary_pairs;   // (own pose, remote node) per inter half-edge
+  std::vector<int64_t> send_poses, recv_poses;       // per peer rank
+  std::vector<int64_t> send_dbl, recv_dbl;
+  int *d_send_idx = nullptr;
+  int64_t n_send = 0;
+  double *d_send = nullptr;
+  mmpgo_exchange_fn exchange_fn = nullptr;
+  mmpgo_allreduce_fn allreduce_fn = nullptr;
+  void *cb_user = nullptr;
+  int64_t halo_exchanges = 0, allreduces = 0;
   mmpgo_counters ctr;
   std::vector<void *> allocs;
 };
@@ -123,7 +128,12 @@ int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *cou
 int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f);
 int driver_current_objective(Handle *h, double *f, double *g2);
 int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg);
+int driver_set_sharding(Handle *h, int rank, int world, const int32_t *rank_node_begin, mmpgo_exchange_fn ex,
+                        mmpgo_allreduce_fn ar, void *user);
 void driver_free(Handle *h);
+int plan_halo(int64_t N, int num_nodes, int64_t E, const int32_t *ei, const int32_t *ej, int world,
+              const int32_t *rnb, int rank, int64_t *sc, int64_t *rcn, int64_t *sg, int64_t scap, int64_t *rg,
+              int64_t rcap);
 void set_error(const std::string &s);
 
 }  // namespace mmpgo

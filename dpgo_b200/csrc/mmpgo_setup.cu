@@ -286,6 +286,7 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
         for (int k = 0; k < d * d; ++k) r.R[k] = Re[k];
         h->info[a].inter_he.push_back(s);
         nbrs[a].push_back(own_i ? ej[e] : ei[e]);
+        if (pn >= NO) h->boundary_pairs.emplace_back(po, own_i ? en_j[e] : en_i[e]);
         const double *Md = own_i ? Mii : Mjj;
         for (int rr = 0; rr < Rr; ++rr) for (int c = 0; c <= rr; ++c) dinter[(size_t)po * SYM + symi(rr, c)] += Md[rr * Rr + c];
       }
@@ -408,6 +409,80 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   CK(cudaStreamSynchronize(h->stream));
   h->st.assign(A, NodeState());
   h->graph_set = true;
+  return 0;
+}
+
+int plan_halo(int64_t N, int num_nodes, int64_t E, const int32_t *ei, const int32_t *ej, int world,
+              const int32_t *rnb, int rank, int64_t *sc, int64_t *rcn, int64_t *sg, int64_t scap, int64_t *rg,
+              int64_t rcap) {
+  if (N <= 0 || num_nodes <= 0 || world < 1 || rank < 0 || rank >= world || !rnb || !ei || !ej || !sc || !rcn ||
+      rnb[0] != 0 || rnb[world] != num_nodes) {
+    set_error("inconsistent sharding");
+    return MMPGO_ERR_ARG;
+  }
+  const Partition part(N, num_nodes);
+  auto owner = [&](int64_t g) {
+    int nd; int64_t pp;
+    part(g, nd, pp);
+    int r = (int)(std::upper_bound(rnb, rnb + world + 1, nd) - rnb) - 1;
+    return std::min(std::max(r, 0), world - 1);
+  };
+  std::vector<std::vector<int64_t>> snd(world), rcv(world);
+  for (int64_t e = 0; e < E; ++e) {
+    const int ri = owner(ei[e]), rj = owner(ej[e]);
+    if (ri == rj) continue;
+    if (ri == rank) { snd[rj].push_back(ei[e]); rcv[rj].push_back(ej[e]); }
+    if (rj == rank) { snd[ri].push_back(ej[e]); rcv[ri].push_back(ei[e]); }
+  }
+  int64_t so = 0, ro = 0;
+  for (int q = 0; q < world; ++q) {
+    for (auto *v : {&snd[q], &rcv[q]}) { std::sort(v->begin(), v->end()); v->erase(std::unique(v->begin(), v->end()), v->end()); }
+    sc[q] = (int64_t)snd[q].size(); rcn[q] = (int64_t)rcv[q].size();
+    if (sg) { if (so + sc[q] > scap) { set_error("send_gids too small"); return MMPGO_ERR_ARG; } std::copy(snd[q].begin(), snd[q].end(), sg + so); }
+    if (rg) { if (ro + rcn[q] > rcap) { set_error("recv_gids too small"); return MMPGO_ERR_ARG; } std::copy(rcv[q].begin(), rcv[q].end(), rg + ro); }
+    so += sc[q]; ro += rcn[q];
+  }
+  return 0;
+}
+
+int driver_set_sharding(Handle *h, int rank, int world, const int32_t *rnb, mmpgo_exchange_fn ex,
+                        mmpgo_allreduce_fn ar, void *user) {
+  if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
+  if (world < 1 || rank < 0 || rank >= world || !rnb || rnb[rank] != h->node_begin || rnb[rank + 1] != h->node_end ||
+      rnb[0] != 0 || rnb[world] != h->num_nodes) {
+    set_error("inconsistent sharding");
+    return MMPGO_ERR_ARG;
+  }
+  if (world > 1 && (!ex || !ar)) { set_error("collective callbacks required for world_size > 1"); return MMPGO_ERR_ARG; }
+  h->rank = rank; h->world = world; h->exchange_fn = ex; h->allreduce_fn = ar; h->cb_user = user;
+  auto owner = [&](int node) {
+    int r = (int)(std::upper_bound(rnb, rnb + world + 1, node) - rnb) - 1;
+    return std::min(std::max(r, 0), world - 1);
+  };
+  const int PB = (h->d + 1) * h->d;
+  // receive side: the halo is sorted by global id, hence already grouped by owner rank
+  h->recv_poses.assign(world, 0);
+  for (int k = 0; k < h->NH; ++k) h->recv_poses[owner(h->halo_owner[k])]++;
+  // send side: own poses adjacent to a node of rank q, ascending pose id
+  std::vector<std::vector<int>> lists(world);
+  for (const auto &bp : h->boundary_pairs) lists[owner(bp.second)].push_back(bp.first);
+  h->send_poses.assign(world, 0);
+  std::vector<int> idx;
+  for (int q = 0; q < world; ++q) {
+    auto &l = lists[q];
+    std::sort(l.begin(), l.end());
+    l.erase(std::unique(l.begin(), l.end()), l.end());
+    if (q == rank && !l.empty()) { set_error("internal: boundary pose sent to self"); return MMPGO_ERR_ARG; }
+    h->send_poses[q] = (int64_t)l.size();
+    idx.insert(idx.end(), l.begin(), l.end());
+  }
+  h->n_send = (int64_t)idx.size();
+  h->send_dbl.resize(world); h->recv_dbl.resize(world);
+  for (int q = 0; q < world; ++q) { h->send_dbl[q] = h->send_poses[q] * PB; h->recv_dbl[q] = h->recv_poses[q] * PB; }
+  int rc = 0;
+  if ((rc = upload(h, &h->d_send_idx, idx))) return rc;
+  if ((rc = dalloc(h, &h->d_send, (size_t)h->n_send * PB))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

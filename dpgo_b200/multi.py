@@ -1,0 +1,162 @@
+"""Multi-GPU sharding of the robot nodes: one process per GPU, torch.distributed for
+the plumbing (NCCL on GPUs; the same code runs over gloo for CPU-side tests of the
+exchange plan).
+
+Rank r owns the contiguous nodes [r*P/W, (r+1)*P/W) (robot nodes are contiguous pose-id
+ranges, C++/DPGO/src/DPGO_utils.cpp:147-158).  Per iteration only the boundary poses of
+inter-node loop closures cross NVLink (all_to_all_single of packed (d+1) x d blocks,
+the wire format of DPGOHash::receive, C++/DPGO/src/DPGOHash.cpp:45-82), plus one small
+all_reduce per global objective evaluation of AMM-PGO* (C++/DPGO/src/DPGOStar.cpp:147-171).
+AMM-PGO# needs no scalar collective.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+from .pgo import DPGOHash, DPGOStar, Options
+
+
+def rank_node_begin(num_nodes, world):
+    return np.array([r * num_nodes // world for r in range(world + 1)], dtype=np.int32)
+
+
+def plan_halo(graph, num_nodes, world, rank):
+    """Host-only exchange plan (mmpgo_plan_halo): (send_counts, recv_counts, send_gids,
+    recv_gids) for `rank`."""
+    lib = L.load()
+    rnb = rank_node_begin(num_nodes, world)
+    sc = np.zeros(world, dtype=np.int64)
+    rc = np.zeros(world, dtype=np.int64)
+    lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    L.check(lib.mmpgo_plan_halo(graph.num_poses, num_nodes, graph.num_edges, L.iptr(graph.i),
+                                L.iptr(graph.j), world, L.iptr(rnb), rank, lp(sc), lp(rc),
+                                None, 0, None, 0))
+    sg = np.zeros(max(int(sc.sum()), 1), dtype=np.int64)
+    rg = np.zeros(max(int(rc.sum()), 1), dtype=np.int64)
+    L.check(lib.mmpgo_plan_halo(graph.num_poses, num_nodes, graph.num_edges, L.iptr(graph.i),
+                                L.iptr(graph.j), world, L.iptr(rnb), rank, lp(sc), lp(rc),
+                                lp(sg), len(sg), lp(rg), len(rg)))
+    return sc, rc, sg[: int(sc.sum())], rg[: int(rc.sum())]
+
+
+class _DevArray:
+    """Zero-copy view of a raw device pointer for torch.as_tensor."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2}
+
+
+class ShardedDriver:
+    """A DPGOHash / DPGOStar over the nodes of this rank, with the NCCL transport bound."""
+
+    def __init__(self, graph, num_nodes, options, algorithm, rank, world):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = rank, world
+        rnb = rank_node_begin(num_nodes, world)
+        cls = DPGOStar if algorithm == "star" else DPGOHash
+        self.drv = cls(graph, num_nodes, options, int(rnb[rank]), int(rnb[rank + 1]))
+        self.exchanges = 0
+        self.allreduces = 0
+        self.exchange_bytes = 0
+        # keep the callbacks alive for the lifetime of the handle
+        self._ex = L.EXCHANGE_FN(self._exchange)
+        self._ar = L.ALLREDUCE_FN(self._allreduce)
+        L.check(self.drv.lib.mmpgo_set_sharding(self.drv._h, rank, world, L.iptr(rnb), self._ex, self._ar,
+                                                None))
+        self._scratch = torch.zeros(16, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    # ---- transport callbacks (called from inside libmmpgo with its stream idle) ----------
+    def _exchange(self, user, send_ptr, send_counts, recv_ptr, recv_counts):
+        try:
+            torch, dist = self.torch, self.dist
+            W = self.world
+            sc = [int(send_counts[q]) for q in range(W)]
+            rc = [int(recv_counts[q]) for q in range(W)]
+            ns, nr = sum(sc), sum(rc)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            send = torch.as_tensor(_DevArray(send_ptr, ns), device=dev) if ns else \
+                torch.empty(0, dtype=torch.float64, device=dev)
+            recv = torch.as_tensor(_DevArray(recv_ptr, nr), device=dev) if nr else \
+                torch.empty(0, dtype=torch.float64, device=dev)
+            dist.all_to_all_single(recv, send, rc, sc)
+            torch.cuda.current_stream().synchronize()
+            self.exchanges += 1
+            self.exchange_bytes += 8 * ns
+            return 0
+        except Exception as e:          # never let an exception cross the C boundary
+            print("mmpgo exchange callback failed:", repr(e))
+            return 1
+
+    def _allreduce(self, user, vals, n):
+        try:
+            torch, dist = self.torch, self.dist
+            host = np.ctypeslib.as_array(vals, shape=(n,))
+            t = self._scratch[:n]
+            t.copy_(torch.from_numpy(host))
+            dist.all_reduce(t)
+            host[:] = t.cpu().numpy()
+            self.allreduces += 1
+            return 0
+        except Exception as e:
+            print("mmpgo allreduce callback failed:", repr(e))
+            return 1
+
+    # ---- driver interface ------------------------------------------------------------
+    def __getattr__(self, name):
+        return getattr(self.drv, name)
+
+    def global_objective(self):
+        """(F, |grad F|) summed over all ranks."""
+        f, g = self.drv.objective()
+        if self.world == 1:
+            return f, g
+        t = self.torch.tensor([f, g * g], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t)
+        return float(t[0]), float(np.sqrt(t[1].item()))
+
+    def solve_kernels_per_iter(self):
+        return 3.0
+
+    def halo_counts(self):
+        sc = np.zeros(self.world, dtype=np.int64)
+        rc = np.zeros(self.world, dtype=np.int64)
+        lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        L.check(self.drv.lib.mmpgo_halo_counts(self.drv._h, lp(sc), lp(rc)))
+        return sc, rc
+
+
+def make_driver(graph, num_nodes, options, algorithm="star", rank=0, world=1):
+    return ShardedDriver(graph, num_nodes, options or Options(), algorithm, rank, world)
+
+
+def e2e_multi(drv, X0, steps, E, d, N):
+    """End-to-end arm at N > 1: every step uploads the full host iterate (initialize),
+    runs update/iterate/communicate and downloads this rank's rows."""
+    import time
+    torch, dist = drv.torch, drv.dist
+    Xh = np.asfortranarray(X0)
+    assert drv.initialize(Xh) == 0 and drv.update() == 0
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        assert drv.initialize(Xh) == 0
+        L.check(drv.update())
+        L.check(drv.iterate())
+        L.check(drv.communicate())
+        Xh_local = drv.X()
+    drv.synchronize()
+    dist.barrier(); torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nbytes = (d + 1) * N * d * 8
+    return {"value": E * steps / float(t.item()), "unit": "edge-updates/s",
+            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes // drv.world, "steps": steps,
+            "call_sequence": "initialize(X_host); update(); iterate(); communicate(); X()",
+            "note": "each step restarts from the same host iterate on every rank"}

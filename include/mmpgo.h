@@ -148,6 +148,35 @@ int mmpgo_evaluate_f(mmpgo_handle h, const double *X, int64_t ldx, double *fobj)
  * (what dist_pgo logs each iteration, dist_pgo.cpp:523-530). */
 int mmpgo_current_objective(mmpgo_handle h, double *fobj, double *grad_sqnorm);
 
+/* ---- multi-GPU: robot nodes sharded over ranks, one handle per rank ----------
+ * Only the boundary poses of inter-node loop closures move between GPUs
+ * (DPGOHash::receive wire format, DPGOHash.cpp:45-82: one (d+1) x d block per
+ * pose, ascending pose id per peer), plus a scalar all-reduce of the objective /
+ * restart test for AMM-PGO* (DPGOStar.cpp:147-171).  The transport is supplied
+ * by the caller as two callbacks (NCCL through torch.distributed in this repo):
+ *   exchange(user, send_dev, send_counts, recv_dev, recv_counts): all-to-all of
+ *     pose blocks; counts are in doubles per peer rank; the library's stream is
+ *     idle during the call and the data must have landed when it returns;
+ *   allreduce(user, vals, n): in-place sum of n host doubles over all ranks.
+ * rank_node_begin has world+1 entries: rank r owns nodes [begin[r], begin[r+1]).
+ * Call after mmpgo_set_graph and before mmpgo_initialize. */
+typedef int (*mmpgo_exchange_fn)(void *user, const void *send_dev, const int64_t *send_counts,
+                                 void *recv_dev, const int64_t *recv_counts);
+typedef int (*mmpgo_allreduce_fn)(void *user, double *vals, int32_t n);
+int mmpgo_set_sharding(mmpgo_handle h, int32_t rank, int32_t world_size,
+                       const int32_t *rank_node_begin, mmpgo_exchange_fn exchange,
+                       mmpgo_allreduce_fn allreduce, void *user);
+/* per-peer number of boundary poses sent / received each exchange (length world_size) */
+int mmpgo_halo_counts(mmpgo_handle h, int64_t *send_poses, int64_t *recv_poses);
+/* Host-only (no CUDA) restatement of the exchange plan for rank `rank`: the global ids
+ * of the own poses sent to each peer (`sent_`, DPGO_utils.cpp:426-433) and of the remote
+ * poses received from each peer (`recv_`, :435), concatenated in rank order, ascending
+ * id per peer.  gids buffers may be NULL to query the counts only. */
+int mmpgo_plan_halo(int64_t num_poses, int32_t num_nodes, int64_t num_edges, const int32_t *edge_i,
+                    const int32_t *edge_j, int32_t world_size, const int32_t *rank_node_begin,
+                    int32_t rank, int64_t *send_counts, int64_t *recv_counts, int64_t *send_gids,
+                    int64_t send_capacity, int64_t *recv_gids, int64_t recv_capacity);
+
 /* AMM-PGO* master-node scalars: F (the running average, DPGOStar.cpp:210),
  * the last accepted global objective and the number of global restarts. */
 int mmpgo_star_objective(mmpgo_handle h, double *F, double *fobj, int32_t *restarts);
