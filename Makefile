@@ -2,7 +2,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fopenmp,-O3 -Iinclude
-SRC := dpgo_b200/csrc/mmpgo_kernels.cu dpgo_b200/csrc/mmpgo_setup.cu dpgo_b200/csrc/mmpgo_driver.cu dpgo_b200/csrc/mmpgo_capi.cu
+SRC := dpgo_b200/csrc/mmpgo_kernels.cu dpgo_b200/csrc/mmpgo_tsolve.cu dpgo_b200/csrc/mmpgo_setup.cu dpgo_b200/csrc/mmpgo_driver.cu dpgo_b200/csrc/mmpgo_capi.cu
 OBJ := $(SRC:.cu=.o)
 LIB := dpgo_b200/libmmpgo.so
 

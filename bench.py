@@ -226,34 +226,55 @@ def run_ours(args):
     E_intra = sizes["bsr_entries"] // 2
     NO = sizes["own_poses"]
     HE = sizes["inter_half_edges"]
-    k_ms = {k: drv.profile_pass(k, 20) for k in drv.KERNEL_KINDS}
+    kinds = [k for k in drv.KERNEL_KINDS if k != "g00_spmv"]
+    k_ms = {k: drv.profile_pass(k, 20) for k in kinds if k != "g00_solve"}
+    # the persistent translation solve is timed over the solves of the timed steps themselves
+    # (bytes = pose-iterations x bytes per pose-iteration); one extra cold solve gives its duration
+    solve_calls = max(int(ctr.solve_calls), 1)
+    pose_iters = float(ctr.reserved[0])
+    drv.reset_counters()
+    k_ms["g00_solve"] = drv.profile_pass("g00_solve", 5)
+    c2 = drv.counters()
+    solve_pose_iters = float(c2.reserved[0]) / 8.0          # 3 warm-up + 5 timed launches
     per_step = {
         "k2": ctr.intra_passes / args.steps, "k1_inter": ctr.inter_passes / args.steps,
-        "k3_prox": ctr.prox_passes / args.steps, "g00_iter": ctr.solve_iters / args.steps,
+        "k3_prox": ctr.prox_passes / args.steps, "g00_solves": ctr.solve_calls / args.steps,
+        "g00_node_iters": ctr.solve_iters / args.steps,
     }
+    # K2b bytes per pose and CG iteration: sliced-ELLPACK entries (12 B each)
+    # + diagonal twice + 5 vector reads and 2 writes in phase A, 4 reads and 2 writes in phase B
+    sell_bytes_per_pose = 12.0 * 2 * E_intra / max(NO, 1)
+    b_iter = sell_bytes_per_pose + 16 + 8 * d * (5 + 6)
     alg_bytes = {
         "k2_eval": 120 * E_intra + 192 * NO, "k2_grad": 120 * E_intra + 192 * NO,
         "k2_hv": 120 * E_intra + 192 * NO, "k2_g01": 120 * E_intra + 192 * NO,
         "k1_inter": 120 * HE + 192 * NO, "k3_prox": 680 * NO,
-        "g00_spmv": 12 * 2 * E_intra + 4 * 8 * d * NO, "edge_objective": 120 * sizes["owned_edges"] + 96 * NO,
+        "edge_objective": 120 * sizes["owned_edges"] + 96 * NO,
+        "g00_solve": b_iter * solve_pose_iters,
     }
     k2_avg = float(np.mean([k_ms["k2_eval"], k_ms["k2_grad"], k_ms["k2_hv"], k_ms["k2_g01"]]))
     share = {
         "k2 block-CSR pass": per_step["k2"] * k2_avg,
-        "g00 solve iteration": per_step["g00_iter"] * k_ms["g00_spmv"] * drv.solve_kernels_per_iter(),
+        "k2b translation solve": per_step["g00_solves"] * k_ms["g00_solve"] *
+                                 (pose_iters / solve_calls) / max(solve_pose_iters, 1.0),
         "k1 inter-edge pass": per_step["k1_inter"] * k_ms["k1_inter"],
         "k3 fused proximal": per_step["k3_prox"] * k_ms["k3_prox"],
     }
     peak, peak_src = measured_peak()
-    dom = "k2_eval"
+    names = {"k2b translation solve": ("g00_solve", "k_tsolve<3> (K2b persistent Jacobi-PCG translation solve)"),
+             "k2 block-CSR pass": ("k2_eval", "k_gpass<3,G_EVAL> (K2 block-CSR connection-Laplacian pass)"),
+             "k1 inter-edge pass": ("k1_inter", "k_inter<3> (K1 inter-node edge pass)"),
+             "k3 fused proximal": ("k3_prox", "k_prox<3> (K3 fused proximal + SO(3) projection)")}
+    dom, dom_name = names[max(share, key=share.get)]
     achieved = alg_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_gpass<3,G_EVAL> (K2 block-CSR connection-Laplacian pass)",
+        "bound": "hbm", "kernel": dom_name,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": ncu_traffic("k_gpass"), "peak_source": peak_src,
+        "traffic": ncu_traffic(dom), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes[dom], "launch_ms": k_ms[dom],
         "kernel_ms": k_ms, "est_ms_per_step_by_kernel": share, "launches_per_step": per_step,
         "all_kernels_gbs": {k: alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9 for k in k_ms},
+        "all_kernels_frac": {k: alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak for k in k_ms},
     }
 
     # ---- e2e: reference-facing call sequence with host matrices inside the timed region
@@ -297,7 +318,7 @@ def run_ours(args):
             "gpu_launches": int(ctr.launches), "clocks": clk.summary(),
             "counters_per_step": {"launches": ctr.launches / args.steps, "k2_passes": per_step["k2"],
                                   "g00_solves": ctr.solve_calls / args.steps,
-                                  "g00_iterations": per_step["g00_iter"],
+                                  "g00_node_iterations": per_step["g00_node_iters"],
                                   "tcg_iterations": ctr.tcg_iterations / args.steps},
         }
         print(json.dumps(line))

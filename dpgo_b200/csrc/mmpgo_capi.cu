@@ -214,13 +214,15 @@ int mmpgo_profile_pass(mmpgo_handle hh, int32_t kind, int32_t reps, float *ms_av
 int mmpgo_get_counters(mmpgo_handle hh, mmpgo_counters *out) {
   H_OR_FAIL(hh);
   if (!out) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }
+  int rc = mmpgo::driver_sync_counters(h);
+  if (rc) return rc;
   *out = h->ctr;
   return MMPGO_OK;
 }
 int mmpgo_reset_counters(mmpgo_handle hh) {
   H_OR_FAIL(hh);
   std::memset(&h->ctr, 0, sizeof(h->ctr));
-  return MMPGO_OK;
+  return mmpgo::driver_reset_solve_stats(h);
 }
 int mmpgo_synchronize(mmpgo_handle hh) {
   H_OR_FAIL(hh);

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 
 #include "mmpgo_driver.cuh"
@@ -131,46 +132,30 @@ template <int D> struct Drv {
       h->ctr.launches++;
     }
     if (any(mp)) {
-      Tiles tl; RC(make_tiles(h, mp, &tl, h->d_active2));
-      SolveArgs sa;
-      sa.rowptr = h->d_rowptr; sa.col = h->d_col; sa.a00 = h->d_a00; sa.d00 = h->d_d00;
-      sa.node_tile_begin = h->d_node_tb; sa.node_tile_end = h->d_node_te;
-      sa.state = h->d_pcg_state;
-      sa.tol2 = h->opt.translation_solve_tol * h->opt.translation_solve_tol;
-      VecArgs va; std::memset(&va, 0, sizeof(va));
-      if (warm) {
-        va.a = xio; va.o1 = h->tsol;
-        launch_vec<D>(V_GET_T, tl, va, h->stream);
-      } else {
-        va.o1 = h->tsol;
-        launch_vec<D>(V_ZERO_C, tl, va, h->stream);
+      // one persistent launch: per-node Jacobi-PCG to `translation_solve_tol` (mmpgo_tsolve.cu)
+      TSolveArgs ta;
+      std::memset(&ta, 0, sizeof(ta));
+      ta.rowptr = h->d_rowptr; ta.col = h->d_col; ta.a00 = h->d_a00; ta.d00 = h->d_d00;
+      ta.sell_ptr = h->d_sell_ptr; ta.sell_col = h->d_sell_col; ta.sell_val = h->d_sell_val;
+      ta.ct_node = h->d_ct_node; ta.ct_start = h->d_ct_start; ta.ct_cnt = h->d_ct_cnt;
+      ta.n_ct = h->n_ctiles; ta.node_ctb = h->d_node_ctb; ta.node_cte = h->d_node_cte;
+      if (all(mp)) ta.active = nullptr;
+      else {
+        CK(cudaMemcpyAsync(h->d_active2, mp.data(), sizeof(int) * mp.size(), cudaMemcpyHostToDevice, h->stream));
+        ta.active = h->d_active2;
       }
-      launch_pcg_init<D>(tl, sa, h->rhs_t, h->tsol, h->tsol, h->pr, h->pz, h->pp, h->d_partials, h->stream);
-      launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
-      launch_pcg_scalar(h->A, h->d_node_scal, h->d_pcg_state, 0, sa.tol2, h->stream);
-      h->ctr.launches += 4;
-      int it = 0;
-      const int chunk = 8;
-      bool done = false;
-      while (!done && it < h->opt.translation_solve_max_iters) {
-        for (int c = 0; c < chunk; ++c, ++it) {
-          launch_pcg_spmv<D>(tl, sa, h->pp, h->pap, h->d_partials, 0, h->stream);
-          launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
-          launch_pcg_scalar(h->A, h->d_node_scal, h->d_pcg_state, 1, sa.tol2, h->stream);
-          launch_pcg_update<D>(tl, sa, h->tsol, h->pr, h->pz, h->pp, h->pap, h->d_partials, h->stream);
-          launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
-          launch_pcg_scalar(h->A, h->d_node_scal, h->d_pcg_state, 2, sa.tol2, h->stream);
-          launch_pcg_dir<D>(tl, sa, h->pz, h->pp, h->d_partials, h->stream);
-          h->ctr.launches += 7;
-          h->ctr.solve_iters++;
-        }
-        CK(cudaMemcpyAsync(h->h_pinned, h->d_pcg_state, sizeof(double) * h->A * 8, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        done = true;
-        for (int n = 0; n < h->A; ++n) if (mp[n] && h->h_pinned[n * 8 + 6] != 0.0) done = false;
-      }
-      va.a = h->tsol; va.o1 = xio;
-      launch_vec<D>(V_SET_T, tl, va, h->stream);
+      ta.rhs = h->rhs_t; ta.xio = xio; ta.warm = warm ? 1 : 0; ta.mode = h->ts_mode;
+      ta.x = h->ts_x; ta.z = h->ts_z; ta.p = h->ts_p; ta.ap = h->ts_ap;
+      ta.partials = h->ts_partials; ta.nstate = h->ts_nstate;
+      ta.cnt = h->d_ts_sync; ta.n_nodes = h->A; ta.n_active = 0;
+      for (int v : mp) ta.n_active += v ? 1 : 0;
+      ta.stats = h->d_ts_stats; ta.node_off = h->d_node_off;
+      ta.tol2 = h->opt.translation_solve_tol * h->opt.translation_solve_tol;
+      ta.max_iters = h->opt.translation_solve_max_iters;
+      CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (h->A + 8), h->stream));
+      int grid = std::max(1, std::min(h->ts_max_grid, h->n_ctiles));
+      if (h->ts_grid_override > 0) grid = std::min(grid, h->ts_grid_override);
+      CK((cudaError_t)launch_tsolve<D>(ta, grid, h->stream));
       h->ctr.launches++;
     }
     return 0;
@@ -886,6 +871,16 @@ template <int D> static int profile_pass(Handle *h, int kind, int reps, float *m
       int nb = 0;
       launch_edge_objective<D>(h->n_edges_owned, h->d_erec, Xk, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
                                &nb, h->stream);
+    } else if (kind == 8) {
+      // one cold translation solve on scratch (rhs = whatever recover_t left), fixed iteration count
+      const double tol = h->opt.translation_solve_tol; const int mi = h->opt.translation_solve_max_iters;
+      if (getenv("MMPGO_TS_ITERS")) { h->opt.translation_solve_tol = 0.0; h->opt.translation_solve_max_iters = atoi(getenv("MMPGO_TS_ITERS")); }
+      h->ts_mode = getenv("MMPGO_TS_MODE") ? atoi(getenv("MMPGO_TS_MODE")) : 0;
+      h->ts_grid_override = getenv("MMPGO_TS_GRID") ? atoi(getenv("MMPGO_TS_GRID")) : 0;
+      int rc = Dr::solve_t(h, h->xprop, allm, false);
+      h->opt.translation_solve_tol = tol; h->opt.translation_solve_max_iters = mi; h->ts_mode = 0; h->ts_grid_override = 0;
+      if (rc) return rc;
+      h->ctr.launches--;
     } else if (kind == 5) {
       SolveArgs sa;
       sa.rowptr = h->d_rowptr; sa.col = h->d_col; sa.a00 = h->d_a00; sa.d00 = h->d_d00;
@@ -913,6 +908,23 @@ int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg) {
   if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
   if (reps <= 0) { set_error("reps must be positive"); return MMPGO_ERR_ARG; }
   return h->d == 2 ? profile_pass<2>(h, kind, reps, ms_avg) : profile_pass<3>(h, kind, reps, ms_avg);
+}
+
+// device-side solve statistics -> counters (solve_iters = node-iterations of the G00 PCG,
+// reserved[0] = pose-iterations, the unit of its byte accounting)
+int driver_sync_counters(Handle *h) {
+  if (!h->graph_set) return 0;
+  unsigned long long st[2] = {0, 0};
+  CK(cudaMemcpyAsync(st, h->d_ts_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->ctr.solve_iters = (int64_t)st[0];
+  h->ctr.reserved[0] = (int64_t)st[1];
+  return 0;
+}
+int driver_reset_solve_stats(Handle *h) {
+  if (!h->graph_set) return 0;
+  CK(cudaMemsetAsync(h->d_ts_stats, 0, 2 * sizeof(unsigned long long), h->stream));
+  return 0;
 }
 
 int driver_current_objective(Handle *h, double *f, double *g2) {

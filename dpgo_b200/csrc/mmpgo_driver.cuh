@@ -90,6 +90,16 @@ struct Handle {
   // compact (NO x D)
   double *rhs_t = nullptr, *tsol = nullptr, *pr = nullptr, *pz = nullptr, *pp = nullptr, *pap = nullptr;
   double *d_pcg_state = nullptr;
+  // persistent translation solve (mmpgo_tsolve.cu)
+  int *d_sell_ptr = nullptr, *d_sell_col = nullptr, *d_ts_sync = nullptr;
+  int *d_ct_node = nullptr, *d_ct_start = nullptr, *d_ct_cnt = nullptr, *d_node_ctb = nullptr, *d_node_cte = nullptr;
+  int n_ctiles = 0;
+  double *d_sell_val = nullptr;
+  double *ts_x = nullptr, *ts_z = nullptr, *ts_p = nullptr, *ts_ap = nullptr;
+  double *ts_partials = nullptr, *ts_nstate = nullptr;
+  unsigned long long *d_ts_stats = nullptr;
+  int ts_max_grid = 0, ts_mode = 0, ts_grid_override = 0;
+  int64_t sell_entries = 0;
   // per half-edge
   double *w_cur = nullptr, *w_prev = nullptr, *w_tmp = nullptr;
   // scalars
@@ -128,6 +138,8 @@ int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *cou
 int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f);
 int driver_current_objective(Handle *h, double *f, double *g2);
 int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg);
+int driver_sync_counters(Handle *h);
+int driver_reset_solve_stats(Handle *h);
 int driver_set_sharding(Handle *h, int rank, int world, const int32_t *rank_node_begin, mmpgo_exchange_fn ex,
                         mmpgo_allreduce_fn ar, void *user);
 void driver_free(Handle *h);

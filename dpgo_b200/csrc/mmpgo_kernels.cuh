@@ -138,6 +138,37 @@ struct SolveArgs {
   double tol2;
 };
 
+// persistent per-node Jacobi-PCG (mmpgo_tsolve.cu).  A CTA tile is <= CTILE consecutive poses of
+// one node; warp wi of the CTA owns its poses [32 wi, 32 wi + 32).  Solver vectors are laid out
+// [cta tile][warp][D][32]; slice index sl = 8 * cta tile + warp.
+constexpr int CTILE = 256;
+struct TSolveArgs {
+  const int *rowptr, *col;        // G00 CSR over own poses (warm-start residual only)
+  const double *a00, *d00;
+  const int *sell_ptr;            // [8 n_ct + 1] slice offsets (units of 32 entries)
+  const int *sell_col;            // [..][32] slot of the neighbour's column 0
+  const double *sell_val;         // [..][32] -tau (0 = padding)
+  const int *ct_node, *ct_start, *ct_cnt;
+  int n_ct;
+  const int *node_ctb, *node_cte; // CTA-tile range of every node
+  const int *active;              // per-node mask or nullptr
+  const double *rhs;              // [NO][D]
+  double *xio;                    // pose blocks: t rows in (warm start: u0 = -t) and out (t = -u)
+  int warm;
+  int mode;                       // 0 normal; experiments: 1 no arithmetic sweep, 2 no node arrivals
+  double *x, *z, *p, *ap;         // [8 n_ct][D][32]; the residual is kept as z = r / diag
+  double *partials;               // [n_ct][4]
+  double *nstate;                 // [nodes][8]: rz, bb, alpha, beta, iters, rr, finished-in-round + 1
+  int *cnt;                       // [nodes + 3] arrival counters, finished nodes, barrier, exit round (zeroed before launch)
+  int n_nodes, n_active;
+  unsigned long long *stats;      // [2]: sum of node iterations, sum of iterations x poses of the node
+  const int *node_off;            // [nodes+1] own pose offsets
+  double tol2;
+  int max_iters;
+};
+template <int D> int launch_tsolve(const TSolveArgs &a, int grid, cudaStream_t s);
+template <int D> int tsolve_max_grid(int device);
+
 // ---- edge-parallel global objective (AMM-PGO*, DPGOStar.cpp:713-761) ----------
 struct EdgeRec {            // 128 bytes
   int32_t i, j;             // pose indices (own / halo numbering)

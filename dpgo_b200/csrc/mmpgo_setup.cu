@@ -338,6 +338,48 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   h->n_tiles = (int)tnode.size();
   h->h_tile_node = tnode;
 
+  // ---- persistent solve: "CTA tiles" of <= 256 consecutive poses of one node, cut into eight
+  // 32-pose warp slices; sliced ELLPACK of G00 with one slice per warp slice, columns stored as
+  // slots of the [cta tile][warp][d][32] vector layout
+  std::vector<int> ct_node, ct_start, ct_cnt, node_ctb(A, 0), node_cte(A, 0);
+  for (int a = 0; a < A; ++a) {
+    node_ctb[a] = (int)ct_node.size();
+    for (int p = h->node_off[a]; p < h->node_off[a + 1]; p += CTILE) {
+      ct_node.push_back(a); ct_start.push_back(p); ct_cnt.push_back(std::min(CTILE, h->node_off[a + 1] - p));
+    }
+    node_cte[a] = (int)ct_node.size();
+  }
+  h->n_ctiles = (int)ct_node.size();
+  const int n_sl = 8 * h->n_ctiles;
+  std::vector<int> sell_ptr((size_t)n_sl + 1, 0), slot_of(NO, 0);
+  for (int c = 0; c < h->n_ctiles; ++c)
+    for (int k = 0; k < ct_cnt[c]; ++k) slot_of[ct_start[c] + k] = (8 * c + k / 32) * 32 * d + (k % 32);
+  for (int sl = 0; sl < n_sl; ++sl) {
+    const int c = sl / 8, c0 = std::min(32, ct_cnt[c] - 32 * (sl % 8));
+    int width = 0;
+    for (int k = 0; k < c0; ++k) width = std::max(width, rowcnt[ct_start[c] + 32 * (sl % 8) + k]);
+    sell_ptr[sl + 1] = sell_ptr[sl] + (c0 > 0 ? width : 0);
+  }
+  h->sell_entries = sell_ptr.back();
+  std::vector<int> sell_col((size_t)h->sell_entries * 32);
+  std::vector<double> sell_val((size_t)h->sell_entries * 32, 0.0);
+  for (int sl = 0; sl < n_sl; ++sl) {
+    const int c = sl / 8, c0 = std::min(32, ct_cnt[c] - 32 * (sl % 8));
+    if (c0 <= 0) continue;
+    const int p0 = ct_start[c] + 32 * (sl % 8);
+    for (int s = sell_ptr[sl]; s < sell_ptr[sl + 1]; ++s)
+      for (int l = 0; l < 32; ++l) {
+        const int k = s - sell_ptr[sl];
+        const size_t o = (size_t)s * 32 + l;
+        sell_col[o] = slot_of[p0];   // padding: any valid slot, value 0
+        if (l < c0 && k < rowcnt[p0 + l]) {
+          const int e = rowptr[p0 + l] + k;
+          sell_col[o] = slot_of[col[e]];
+          sell_val[o] = a00[e];
+        }
+      }
+  }
+
   // ---- dense G00^{-1} for small nodes
   std::vector<long long> dense_off(A, -1);
   std::vector<double> ginv;
@@ -378,6 +420,14 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   if ((rc = upload(h, &h->d_xrec, xrec))) return rc;
   if ((rc = upload(h, &h->d_erec, erec))) return rc;
   if ((rc = upload(h, &h->d_ginv, ginv))) return rc;
+  if ((rc = upload(h, &h->d_sell_ptr, sell_ptr))) return rc;
+  if ((rc = upload(h, &h->d_sell_col, sell_col))) return rc;
+  if ((rc = upload(h, &h->d_sell_val, sell_val))) return rc;
+  if ((rc = upload(h, &h->d_ct_node, ct_node))) return rc;
+  if ((rc = upload(h, &h->d_ct_start, ct_start))) return rc;
+  if ((rc = upload(h, &h->d_ct_cnt, ct_cnt))) return rc;
+  if ((rc = upload(h, &h->d_node_ctb, node_ctb))) return rc;
+  if ((rc = upload(h, &h->d_node_cte, node_cte))) return rc;
   if ((rc = upload(h, &h->d_dense_off, dense_off))) return rc;
   if ((rc = upload(h, &h->d_tile_node, tnode))) return rc;
   if ((rc = upload(h, &h->d_tile_start, tstart))) return rc;
@@ -397,6 +447,17 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   double **cv[] = {&h->rhs_t, &h->tsol, &h->pr, &h->pz, &h->pp, &h->pap};
   for (auto q : cv) if ((rc = dalloc(h, q, nc))) return rc;
   if ((rc = dalloc(h, &h->d_pcg_state, (size_t)A * 8))) return rc;
+  {
+    const size_t nv = (size_t)8 * h->n_ctiles * 32 * d;
+    double **tv[] = {&h->ts_x, &h->ts_z, &h->ts_p, &h->ts_ap};
+    for (auto q : tv) if ((rc = dalloc(h, q, nv))) return rc;
+    if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4))) return rc;
+    if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
+    if ((rc = dalloc(h, &h->d_ts_sync, (size_t)A + 8))) return rc;
+    if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
+    h->ts_max_grid = d == 2 ? tsolve_max_grid<2>(h->opt.device) : tsolve_max_grid<3>(h->opt.device);
+    if (h->ts_max_grid <= 0) { set_error("occupancy query for the translation solve failed"); return MMPGO_ERR_CUDA; }
+  }
   double **wv[] = {&h->w_cur, &h->w_prev, &h->w_tmp};
   for (auto q : wv) if ((rc = dalloc(h, q, (size_t)nxe))) return rc;
   if ((rc = dalloc(h, &h->d_partials, (size_t)h->n_tiles * NS))) return rc;
