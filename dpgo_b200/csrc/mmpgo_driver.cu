@@ -135,7 +135,7 @@ template <int D> struct Drv {
       // one persistent launch: per-node Jacobi-PCG to `translation_solve_tol` (mmpgo_tsolve.cu)
       TSolveArgs ta;
       std::memset(&ta, 0, sizeof(ta));
-      ta.rowptr = h->d_rowptr; ta.col = h->d_col; ta.a00 = h->d_a00; ta.d00 = h->d_d00;
+      ta.rowptr = h->d_rowptr; ta.col = h->d_col; ta.a00 = h->d_a00; ta.d00 = h->d_d00; ta.diag_s = h->d_diag_s;
       ta.sell_ptr = h->d_sell_ptr; ta.sell_col = h->d_sell_col; ta.sell_val = h->d_sell_val;
       ta.ct_node = h->d_ct_node; ta.ct_start = h->d_ct_start; ta.ct_cnt = h->d_ct_cnt;
       ta.n_ct = h->n_ctiles; ta.node_ctb = h->d_node_ctb; ta.node_cte = h->d_node_cte;
@@ -152,9 +152,13 @@ template <int D> struct Drv {
       ta.stats = h->d_ts_stats; ta.node_off = h->d_node_off;
       ta.tol2 = h->opt.translation_solve_tol * h->opt.translation_solve_tol;
       ta.max_iters = h->opt.translation_solve_max_iters;
-      CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (h->A + 8), h->stream));
+      CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (2 * h->A + 8), h->stream));
       int grid = std::max(1, std::min(h->ts_max_grid, h->n_ctiles));
       if (h->ts_grid_override > 0) grid = std::min(grid, h->ts_grid_override);
+      if ((int64_t)grid * TS_MAXCT < h->n_ctiles) {
+        set_error("translation solve: too many poses per GPU for the persistent kernel (shard over more GPUs)");
+        return MMPGO_ERR_UNSUPPORTED;
+      }
       CK((cudaError_t)launch_tsolve<D>(ta, grid, h->stream));
       h->ctr.launches++;
     }

@@ -94,7 +94,7 @@ struct Handle {
   int *d_sell_ptr = nullptr, *d_sell_col = nullptr, *d_ts_sync = nullptr;
   int *d_ct_node = nullptr, *d_ct_start = nullptr, *d_ct_cnt = nullptr, *d_node_ctb = nullptr, *d_node_cte = nullptr;
   int n_ctiles = 0;
-  double *d_sell_val = nullptr;
+  double *d_sell_val = nullptr, *d_diag_s = nullptr;
   double *ts_x = nullptr, *ts_z = nullptr, *ts_p = nullptr, *ts_ap = nullptr;
   double *ts_partials = nullptr, *ts_nstate = nullptr;
   unsigned long long *d_ts_stats = nullptr;

@@ -142,9 +142,11 @@ struct SolveArgs {
 // one node; warp wi of the CTA owns its poses [32 wi, 32 wi + 32).  Solver vectors are laid out
 // [cta tile][warp][D][32]; slice index sl = 8 * cta tile + warp.
 constexpr int CTILE = 256;
+constexpr int TS_MAXCT = 32;     // CTA tiles one persistent CTA can own
 struct TSolveArgs {
   const int *rowptr, *col;        // G00 CSR over own poses (warm-start residual only)
   const double *a00, *d00;
+  const double *diag_s;           // diag of G00 in the solver layout [cta tile][CTILE], padded with 1
   const int *sell_ptr;            // [8 n_ct + 1] slice offsets (units of 32 entries)
   const int *sell_col;            // [..][32] slot of the neighbour's column 0
   const double *sell_val;         // [..][32] -tau (0 = padding)
@@ -159,7 +161,7 @@ struct TSolveArgs {
   double *x, *z, *p, *ap;         // [8 n_ct][D][32]; the residual is kept as z = r / diag
   double *partials;               // [n_ct][4]
   double *nstate;                 // [nodes][8]: rz, bb, alpha, beta, iters, rr, finished-in-round + 1
-  int *cnt;                       // [nodes + 3] arrival counters, finished nodes, barrier, exit round (zeroed before launch)
+  int *cnt;                       // [2 nodes] arrival counters, then epochs (zeroed before launch)
   int n_nodes, n_active;
   unsigned long long *stats;      // [2]: sum of node iterations, sum of iterations x poses of the node
   const int *node_off;            // [nodes+1] own pose offsets

@@ -361,6 +361,9 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     sell_ptr[sl + 1] = sell_ptr[sl] + (c0 > 0 ? width : 0);
   }
   h->sell_entries = sell_ptr.back();
+  std::vector<double> diag_s((size_t)h->n_ctiles * CTILE, 1.0);
+  for (int c = 0; c < h->n_ctiles; ++c)
+    for (int k = 0; k < ct_cnt[c]; ++k) diag_s[(size_t)c * CTILE + k] = d00[ct_start[c] + k];
   std::vector<int> sell_col((size_t)h->sell_entries * 32);
   std::vector<double> sell_val((size_t)h->sell_entries * 32, 0.0);
   for (int sl = 0; sl < n_sl; ++sl) {
@@ -423,6 +426,7 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   if ((rc = upload(h, &h->d_sell_ptr, sell_ptr))) return rc;
   if ((rc = upload(h, &h->d_sell_col, sell_col))) return rc;
   if ((rc = upload(h, &h->d_sell_val, sell_val))) return rc;
+  if ((rc = upload(h, &h->d_diag_s, diag_s))) return rc;
   if ((rc = upload(h, &h->d_ct_node, ct_node))) return rc;
   if ((rc = upload(h, &h->d_ct_start, ct_start))) return rc;
   if ((rc = upload(h, &h->d_ct_cnt, ct_cnt))) return rc;
@@ -453,7 +457,7 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     for (auto q : tv) if ((rc = dalloc(h, q, nv))) return rc;
     if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4))) return rc;
     if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
-    if ((rc = dalloc(h, &h->d_ts_sync, (size_t)A + 8))) return rc;
+    if ((rc = dalloc(h, &h->d_ts_sync, (size_t)2 * A + 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
     h->ts_max_grid = d == 2 ? tsolve_max_grid<2>(h->opt.device) : tsolve_max_grid<3>(h->opt.device);
     if (h->ts_max_grid <= 0) { set_error("occupancy query for the translation solve failed"); return MMPGO_ERR_CUDA; }
