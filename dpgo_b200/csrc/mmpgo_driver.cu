@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <limits>
 
 #include "mmpgo_driver.cuh"
@@ -135,17 +136,17 @@ template <int D> struct Drv {
       // one persistent launch: per-node Jacobi-PCG to `translation_solve_tol` (mmpgo_tsolve.cu)
       TSolveArgs ta;
       std::memset(&ta, 0, sizeof(ta));
-      ta.rowptr = h->d_rowptr; ta.col = h->d_col; ta.a00 = h->d_a00; ta.d00 = h->d_d00; ta.diag_s = h->d_diag_s;
-      ta.sell_ptr = h->d_sell_ptr; ta.sell_col = h->d_sell_col; ta.sell_val = h->d_sell_val;
+      ta.rowptr = h->d_rowptr; ta.col = h->d_col; ta.a00 = h->d_a00; ta.d00 = h->d_d00;
+      ta.sell_ptr = h->d_sell_ptr; ta.sell_pack = h->d_sell_pack;
       ta.ct_node = h->d_ct_node; ta.ct_start = h->d_ct_start; ta.ct_cnt = h->d_ct_cnt;
-      ta.n_ct = h->n_ctiles; ta.node_ctb = h->d_node_ctb; ta.node_cte = h->d_node_cte;
+      ta.n_ct = h->n_ctiles; ta.chunk = getenv("MMPGO_TS_CHUNK") ? std::max(1, atoi(getenv("MMPGO_TS_CHUNK"))) : 8; ta.node_ctb = h->d_node_ctb; ta.node_cte = h->d_node_cte;
       if (all(mp)) ta.active = nullptr;
       else {
         CK(cudaMemcpyAsync(h->d_active2, mp.data(), sizeof(int) * mp.size(), cudaMemcpyHostToDevice, h->stream));
         ta.active = h->d_active2;
       }
       ta.rhs = h->rhs_t; ta.xio = xio; ta.warm = warm ? 1 : 0; ta.mode = h->ts_mode;
-      ta.x = h->ts_x; ta.z = h->ts_z; ta.p = h->ts_p; ta.ap = h->ts_ap;
+      ta.rec = h->ts_rec; ta.z = h->ts_z;
       ta.partials = h->ts_partials; ta.nstate = h->ts_nstate;
       ta.cnt = h->d_ts_sync; ta.n_nodes = h->A; ta.n_active = 0;
       for (int v : mp) ta.n_active += v ? 1 : 0;
@@ -155,7 +156,7 @@ template <int D> struct Drv {
       CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (2 * h->A + 8), h->stream));
       int grid = std::max(1, std::min(h->ts_max_grid, h->n_ctiles));
       if (h->ts_grid_override > 0) grid = std::min(grid, h->ts_grid_override);
-      if ((int64_t)grid * TS_MAXCT < h->n_ctiles) {
+      if (((int64_t)h->n_ctiles / ((int64_t)grid * ta.chunk) + 1) * ta.chunk > TS_MAXCT) {
         set_error("translation solve: too many poses per GPU for the persistent kernel (shard over more GPUs)");
         return MMPGO_ERR_UNSUPPORTED;
       }
@@ -918,16 +919,30 @@ int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg) {
 // reserved[0] = pose-iterations, the unit of its byte accounting)
 int driver_sync_counters(Handle *h) {
   if (!h->graph_set) return 0;
-  unsigned long long st[2] = {0, 0};
+  unsigned long long st[16] = {0};
   CK(cudaMemcpyAsync(st, h->d_ts_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->ctr.solve_iters = (int64_t)st[0];
   h->ctr.reserved[0] = (int64_t)st[1];
+  for (int q = 2; q < 7; ++q) h->ctr.reserved[q - 1] = (int64_t)st[q];
+  if (getenv("MMPGO_TS_TRACE")) {
+    std::vector<double> ns((size_t)h->A * 8);
+    CK(cudaMemcpy(ns.data(), h->ts_nstate, ns.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int n = 0; n < std::min(h->A, 6); ++n)
+      fprintf(stderr, "node %d: rz %.3e bb %.3e alpha %.3e beta %.3e iters %.0f rr %.3e\n", n, ns[n*8], ns[n*8+1], ns[n*8+2], ns[n*8+3], ns[n*8+4], ns[n*8+5]);
+  }
+  if (getenv("MMPGO_TS_TRACE")) fprintf(stderr, "scheduler cycles: flag scan %llu, segments %llu, dispatch %llu (selection %llu, issue %llu)\n", st[7], st[8], st[9], st[10], st[11]);
+  if (getenv("MMPGO_TS_TRACE")) {
+    std::vector<unsigned long long> tr(800, 0);
+    CK(cudaMemcpy(tr.data(), h->d_ts_stats + 16, 784 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 0; ++q)
+      fprintf(stderr, "dispatch %d t=%llu k=%d round=%d\n", q, tr[2 * q], (int)(tr[2 * q + 1] >> 32), (int)(tr[2 * q + 1] & 0x3fffffff));
+  }
   return 0;
 }
 int driver_reset_solve_stats(Handle *h) {
   if (!h->graph_set) return 0;
-  CK(cudaMemsetAsync(h->d_ts_stats, 0, 2 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->d_ts_stats, 0, 808 * sizeof(unsigned long long), h->stream));
   return 0;
 }
 

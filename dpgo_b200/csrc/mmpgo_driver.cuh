@@ -91,11 +91,11 @@ struct Handle {
   double *rhs_t = nullptr, *tsol = nullptr, *pr = nullptr, *pz = nullptr, *pp = nullptr, *pap = nullptr;
   double *d_pcg_state = nullptr;
   // persistent translation solve (mmpgo_tsolve.cu)
-  int *d_sell_ptr = nullptr, *d_sell_col = nullptr, *d_ts_sync = nullptr;
+  int *d_sell_ptr = nullptr, *d_ts_sync = nullptr;
+  unsigned char *d_sell_pack = nullptr;
   int *d_ct_node = nullptr, *d_ct_start = nullptr, *d_ct_cnt = nullptr, *d_node_ctb = nullptr, *d_node_cte = nullptr;
   int n_ctiles = 0;
-  double *d_sell_val = nullptr, *d_diag_s = nullptr;
-  double *ts_x = nullptr, *ts_z = nullptr, *ts_p = nullptr, *ts_ap = nullptr;
+  double *ts_rec = nullptr, *ts_z = nullptr, *ts_z_base = nullptr;
   double *ts_partials = nullptr, *ts_nstate = nullptr;
   unsigned long long *d_ts_stats = nullptr;
   int ts_max_grid = 0, ts_mode = 0, ts_grid_override = 0;

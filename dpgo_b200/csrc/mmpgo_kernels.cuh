@@ -141,24 +141,27 @@ struct SolveArgs {
 // persistent per-node Jacobi-PCG (mmpgo_tsolve.cu).  A CTA tile is <= CTILE consecutive poses of
 // one node; warp wi of the CTA owns its poses [32 wi, 32 wi + 32).  Solver vectors are laid out
 // [cta tile][warp][D][32]; slice index sl = 8 * cta tile + warp.
-constexpr int CTILE = 256;
-constexpr int TS_MAXCT = 32;     // CTA tiles one persistent CTA can own
+constexpr int CTILE = 128;        // poses per CTA tile of the translation solve
+constexpr int TS_WPT = CTILE / 32;  // 32-pose warp slices per CTA tile
+constexpr int TS_HALO = 2;        // neighbour tiles staged on each side for the z gathers
+constexpr int TS_MAXCT = 128;     // CTA tiles one persistent CTA can own
 struct TSolveArgs {
   const int *rowptr, *col;        // G00 CSR over own poses (warm-start residual only)
   const double *a00, *d00;
-  const double *diag_s;           // diag of G00 in the solver layout [cta tile][CTILE], padded with 1
-  const int *sell_ptr;            // [8 n_ct + 1] slice offsets (units of 32 entries)
-  const int *sell_col;            // [..][32] slot of the neighbour's column 0
-  const double *sell_val;         // [..][32] -tau (0 = padding)
+  const int *sell_ptr;            // [TS_WPT n_ct + 1] slice offsets (units of 32 entries)
+  const unsigned char *sell_pack; // per CTA tile (rows = its ELLPACK rows): {-tau}[rows][32] doubles, then
+                                  // {slot of the neighbour's column 0}[rows][32] ints; tile at byte 384 sell_ptr[TS_WPT ct]
   const int *ct_node, *ct_start, *ct_cnt;
   int n_ct;
+  int chunk;                      // consecutive CTA tiles dealt to one CTA at a time
   const int *node_ctb, *node_cte; // CTA-tile range of every node
   const int *active;              // per-node mask or nullptr
   const double *rhs;              // [NO][D]
   double *xio;                    // pose blocks: t rows in (warm start: u0 = -t) and out (t = -u)
   int warm;
   int mode;                       // 0 normal; experiments: 1 no arithmetic sweep, 2 no node arrivals
-  double *x, *z, *p, *ap;         // [8 n_ct][D][32]; the residual is kept as z = r / diag
+  double *rec;                    // per CTA tile one record {x, p, Ap}[TS_WPT][D][32] + diag[CTILE] (padded with 1)
+  double *z;                      // [TS_WPT n_ct][D][32], padded by TS_HALO tiles at both ends; r is kept as z = r / diag
   double *partials;               // [n_ct][4]
   double *nstate;                 // [nodes][8]: rz, bb, alpha, beta, iters, rr, finished-in-round + 1
   int *cnt;                       // [2 nodes] arrival counters, then epochs (zeroed before launch)

@@ -350,37 +350,43 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     node_cte[a] = (int)ct_node.size();
   }
   h->n_ctiles = (int)ct_node.size();
-  const int n_sl = 8 * h->n_ctiles;
+  const int n_sl = TS_WPT * h->n_ctiles;
   std::vector<int> sell_ptr((size_t)n_sl + 1, 0), slot_of(NO, 0);
   for (int c = 0; c < h->n_ctiles; ++c)
-    for (int k = 0; k < ct_cnt[c]; ++k) slot_of[ct_start[c] + k] = (8 * c + k / 32) * 32 * d + (k % 32);
+    for (int k = 0; k < ct_cnt[c]; ++k) slot_of[ct_start[c] + k] = (TS_WPT * c + k / 32) * 32 * d + (k % 32);
   for (int sl = 0; sl < n_sl; ++sl) {
-    const int c = sl / 8, c0 = std::min(32, ct_cnt[c] - 32 * (sl % 8));
+    const int c = sl / TS_WPT, c0 = std::min(32, ct_cnt[c] - 32 * (sl % TS_WPT));
     int width = 0;
-    for (int k = 0; k < c0; ++k) width = std::max(width, rowcnt[ct_start[c] + 32 * (sl % 8) + k]);
+    for (int k = 0; k < c0; ++k) width = std::max(width, rowcnt[ct_start[c] + 32 * (sl % TS_WPT) + k]);
     sell_ptr[sl + 1] = sell_ptr[sl] + (c0 > 0 ? width : 0);
   }
   h->sell_entries = sell_ptr.back();
-  std::vector<double> diag_s((size_t)h->n_ctiles * CTILE, 1.0);
+  // per-tile records {x, p, Ap, diag} (one bulk copy per phase) and the packed ELLPACK rows
+  const size_t RL = (size_t)3 * CTILE * d + CTILE;
+  std::vector<double> rec((size_t)h->n_ctiles * RL, 0.0);
   for (int c = 0; c < h->n_ctiles; ++c)
-    for (int k = 0; k < ct_cnt[c]; ++k) diag_s[(size_t)c * CTILE + k] = d00[ct_start[c] + k];
-  std::vector<int> sell_col((size_t)h->sell_entries * 32);
-  std::vector<double> sell_val((size_t)h->sell_entries * 32, 0.0);
-  for (int sl = 0; sl < n_sl; ++sl) {
-    const int c = sl / 8, c0 = std::min(32, ct_cnt[c] - 32 * (sl % 8));
-    if (c0 <= 0) continue;
-    const int p0 = ct_start[c] + 32 * (sl % 8);
-    for (int s = sell_ptr[sl]; s < sell_ptr[sl + 1]; ++s)
-      for (int l = 0; l < 32; ++l) {
-        const int k = s - sell_ptr[sl];
-        const size_t o = (size_t)s * 32 + l;
-        sell_col[o] = slot_of[p0];   // padding: any valid slot, value 0
-        if (l < c0 && k < rowcnt[p0 + l]) {
-          const int e = rowptr[p0 + l] + k;
-          sell_col[o] = slot_of[col[e]];
-          sell_val[o] = a00[e];
+    for (int k = 0; k < CTILE; ++k) rec[(size_t)c * RL + 3 * CTILE * d + k] = k < ct_cnt[c] ? d00[ct_start[c] + k] : 1.0;
+  std::vector<unsigned char> sell_pack((size_t)h->sell_entries * 384 + 16, 0);
+  for (int c = 0; c < h->n_ctiles; ++c) {
+    const int r0 = sell_ptr[TS_WPT * c], rows = sell_ptr[TS_WPT * (c + 1)] - r0;
+    double *pv = reinterpret_cast<double *>(&sell_pack[(size_t)r0 * 384]);
+    int *pc = reinterpret_cast<int *>(&sell_pack[(size_t)r0 * 384 + (size_t)rows * 256]);
+    for (int w = 0; w < TS_WPT; ++w) {
+      const int sl = TS_WPT * c + w, c0 = std::min(32, ct_cnt[c] - 32 * w);
+      const int p0 = ct_start[c] + 32 * w;
+      for (int s_ = sell_ptr[sl]; s_ < sell_ptr[sl + 1]; ++s_)
+        for (int l = 0; l < 32; ++l) {
+          const int k = s_ - sell_ptr[sl];
+          const size_t o = (size_t)(s_ - r0) * 32 + l;
+          pc[o] = slot_of[ct_start[c]];   // padding: any valid slot, value 0
+          pv[o] = 0.0;
+          if (c0 > 0 && l < c0 && k < rowcnt[p0 + l]) {
+            const int e = rowptr[p0 + l] + k;
+            pc[o] = slot_of[col[e]];
+            pv[o] = a00[e];
+          }
         }
-      }
+    }
   }
 
   // ---- dense G00^{-1} for small nodes
@@ -424,9 +430,8 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   if ((rc = upload(h, &h->d_erec, erec))) return rc;
   if ((rc = upload(h, &h->d_ginv, ginv))) return rc;
   if ((rc = upload(h, &h->d_sell_ptr, sell_ptr))) return rc;
-  if ((rc = upload(h, &h->d_sell_col, sell_col))) return rc;
-  if ((rc = upload(h, &h->d_sell_val, sell_val))) return rc;
-  if ((rc = upload(h, &h->d_diag_s, diag_s))) return rc;
+  if ((rc = upload(h, &h->d_sell_pack, sell_pack))) return rc;
+  if ((rc = upload(h, &h->ts_rec, rec))) return rc;
   if ((rc = upload(h, &h->d_ct_node, ct_node))) return rc;
   if ((rc = upload(h, &h->d_ct_start, ct_start))) return rc;
   if ((rc = upload(h, &h->d_ct_cnt, ct_cnt))) return rc;
@@ -452,13 +457,14 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   for (auto q : cv) if ((rc = dalloc(h, q, nc))) return rc;
   if ((rc = dalloc(h, &h->d_pcg_state, (size_t)A * 8))) return rc;
   {
-    const size_t nv = (size_t)8 * h->n_ctiles * 32 * d;
-    double **tv[] = {&h->ts_x, &h->ts_z, &h->ts_p, &h->ts_ap};
-    for (auto q : tv) if ((rc = dalloc(h, q, nv))) return rc;
+    const size_t nv = (size_t)h->n_ctiles * CTILE * d;
+    // z is staged with a TS_HALO-tile halo on both sides: pad the array accordingly at each end
+    if ((rc = dalloc(h, &h->ts_z_base, nv + (size_t)2 * TS_HALO * CTILE * d))) return rc;
+    h->ts_z = h->ts_z_base + (size_t)TS_HALO * CTILE * d;
     if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4))) return rc;
     if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_sync, (size_t)2 * A + 8))) return rc;
-    if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
+    if ((rc = dalloc(h, &h->d_ts_stats, (size_t)8 + 800))) return rc;
     h->ts_max_grid = d == 2 ? tsolve_max_grid<2>(h->opt.device) : tsolve_max_grid<3>(h->opt.device);
     if (h->ts_max_grid <= 0) { set_error("occupancy query for the translation solve failed"); return MMPGO_ERR_CUDA; }
   }

@@ -97,332 +97,482 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 template <int D> struct TSCfg {
   static constexpr int VEC = CTILE * D;          // doubles of one solver vector per CTA tile
-  static constexpr int SELL_CAP = 80;            // 32-entry ELLPACK rows of one CTA tile that fit a stage
-  static constexpr int NSTAGE = 2;
-  // stage layout (bytes): v0 v1 v2 | diag | X, X = {sell values, sell columns} (phase A) or v3 (phase B)
-  static constexpr int OFF_DIAG = 3 * VEC * 8;
-  static constexpr int OFF_X = OFF_DIAG + CTILE * 8;
-  static constexpr int OFF_COL = OFF_X + SELL_CAP * 32 * 8;
-  static constexpr int STAGE_BYTES = OFF_COL + SELL_CAP * 32 * 4;
-  static_assert(SELL_CAP * 32 * 12 >= VEC * 8, "phase-B vector must fit the overlay region");
+  static constexpr int RL = 3 * VEC + CTILE;     // doubles of one tile record {x, p, Ap, diag}
+  static constexpr int WPT = TS_WPT;             // consumer warps per tile (one pose per thread)
+  static constexpr int NGRP = 2;                 // consumer groups (tiles in arithmetic at the same time)
+  static constexpr int HV = 2 * TS_HALO + 1;     // tiles of z staged for phase A (own tile in the middle)
+  static constexpr int SELL_CAP = 40;            // 32-entry ELLPACK rows of one CTA tile that fit a stage
+  static constexpr int NSTAGE = 5;
+  static constexpr int THREADS = NGRP * CTILE + 64;   // consumer groups + boundary warp + dispatch warp
+  // stage layout (bytes):  Z (HV VEC) | R (record or its {p, Ap, diag} tail) | S (packed ELLPACK rows)
+  //   phase A: Z = z of the tiles ct-HALO .. ct+HALO, R = {p, Ap, diag}, S = the tile's rows   (3 bulk copies)
+  //   phase B: Z = z of the tile, R = {x, p, Ap, diag}                                        (2 bulk copies)
+  static constexpr int OFF_R = HV * VEC * 8;
+  static constexpr int OFF_S = OFF_R + RL * 8;
+  static constexpr int STAGE_BYTES = OFF_S + SELL_CAP * 384;
   static constexpr int DYN_BYTES = NSTAGE * STAGE_BYTES;
 };
 
+namespace {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta_shared(const int *p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(int *p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(CTILE) : "memory");
+}
+}  // namespace
+
+// tile flags (shared memory): scheduler 0 -> 1 (dispatched), consumers 1 -> 2 (phase executed),
+// scheduler 2 -> 0 (arrived on the node)
 template <int D>
-__global__ void __launch_bounds__(256, 2) k_tsolve(TSolveArgs a) {
+__global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
   typedef TSCfg<D> C;
   constexpr int PB = (D + 1) * D;
   constexpr int NST = C::NSTAGE;
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  constexpr int WPT = C::WPT;
+  const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;   // the last warp schedules, the others consume
+  const int wi = wg % WPT, grp = wg / WPT;                    // consumer: warp inside its group, group
   int *epoch = a.cnt + a.n_nodes;            // [nodes] next phase the node's tiles may run (| DONE_BIT)
   extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ uint64_t full[NST];
-  // this CTA's tiles: static description, own phase counter, per-pass scratch
-  __shared__ int m_node[TS_MAXCT], m_start[TS_MAXCT], m_cnt[TS_MAXCT], m_sell[TS_MAXCT][9];
-  __shared__ int t_round[TS_MAXCT];          // next phase of the tile; -1 = retired
-  __shared__ int r_k[TS_MAXCT], r_ep[TS_MAXCT], n_ready_s, n_live_s;
-  __shared__ double r_coef[TS_MAXCT];
-  __shared__ double red[8][3];
-  uint32_t ph0 = 0, ph1 = 0;                 // mbarrier parities of the two stages
+  // full barriers: one per use modulo 2 NST, so that a barrier is always waited on by the same
+  // consumer group (NST is odd: with one barrier per stage the groups would alternate on it, and a
+  // group running ahead could mistake the other group's unfinished phase for its own)
+  __shared__ uint64_t full[2 * NST], empty[NST];
+  __shared__ int m_node[TS_MAXCT], m_start[TS_MAXCT], m_cnt[TS_MAXCT], m_sell[TS_MAXCT][TS_WPT + 1];
+  __shared__ int t_round[TS_MAXCT];          // next phase of the tile; -1 = retired           (scheduler)
+  __shared__ int t_flag[TS_MAXCT];
+  __shared__ int d_k[NST], d_kind[NST], d_seg[NST];   // work descriptor of a stage
+  __shared__ int returned_s;                  // tiles the consumers have handed back (monotone)
+  __shared__ int sg_done[TS_MAXCT];           // per segment: tiles of the current phase handed back
+  __shared__ double d_coef[NST];
+  __shared__ double red[2][2][TS_WPT][3];
+  __shared__ int n_live_s;
 
-  const int nb = (a.n_ct - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // <= TS_MAXCT (host-checked)
+  // CTA tiles are dealt to the CTAs in chunks of `chunk` consecutive tiles, round-robin: a node's
+  // rendezvous involves only the CTAs that hold one of its chunks, yet a node that needs many more
+  // iterations than the others still keeps ~tiles/chunk CTAs busy in the tail
+  const int CH = a.chunk;
+  const int n_chunks = (a.n_ct + CH - 1) / CH;
+  auto tile_of = [&](int k) { return (int)(blockIdx.x + (k / CH) * gridDim.x) * CH + k % CH; };
+  int nb = 0;                                                                        // <= TS_MAXCT (host-checked)
+  for (int j = blockIdx.x; j < n_chunks; j += gridDim.x) nb += min(CH, a.n_ct - j * CH);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < NST; ++q) mbar_init(&full[q], 1);
+    for (int q = 0; q < NST; ++q) mbar_init(&empty[q], 1);
+#pragma unroll
+    for (int q = 0; q < 2 * NST; ++q) mbar_init(&full[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     n_live_s = 0;
+    returned_s = 0;
   }
   __syncthreads();
   if (threadIdx.x < nb) {
-    const int k = threadIdx.x, ct = blockIdx.x + k * gridDim.x;
+    const int k = threadIdx.x, ct = tile_of(k);
     const int node = __ldg(a.ct_node + ct);
     m_node[k] = node; m_start[k] = __ldg(a.ct_start + ct); m_cnt[k] = __ldg(a.ct_cnt + ct);
     const bool on = !(a.active && !__ldg(a.active + node));
     t_round[k] = on ? 0 : -1;
+    t_flag[k] = 0;
     if (on) atomicAdd(&n_live_s, 1);
   }
-  for (int q = threadIdx.x; q < nb * 9; q += blockDim.x) {
-    const int k = q / 9, r = q % 9;
-    m_sell[k][r] = __ldg(a.sell_ptr + 8 * (blockIdx.x + k * gridDim.x) + r);
+  for (int q = threadIdx.x; q < nb * (WPT + 1); q += blockDim.x) {
+    const int k = q / (WPT + 1), r = q % (WPT + 1);
+    m_sell[k][r] = __ldg(a.sell_ptr + WPT * tile_of(k) + r);
   }
   __syncthreads();
-  int n_live = n_live_s;
 
-  while (n_live > 0) {
-    // ---- poll: which of my tiles may run their next phase?
-    if (wi == 0) {
-      if (lane == 0) n_ready_s = 0;
+  // A segment = this CTA's tiles of one node (contiguous).  Two service warps:
+  //   boundary warp : per segment and phase one arrival on the node, the node reduction when it is
+  //                   the last arriver, and the poll for the node's next epoch -> opens the phase
+  //   dispatch warp : moves tiles of open phases into the copy ring (shared-memory state only)
+  __shared__ int sg_k0[TS_MAXCT], sg_n[TS_MAXCT], sg_node[TS_MAXCT], sg_target[TS_MAXCT];
+  __shared__ int sg_kind[TS_MAXCT];            // kind of the open phase: 0 init, 1 phase A, 2 phase B, 3 publish
+  __shared__ double sg_coef[TS_MAXCT];         // beta (phase A) / alpha (phase B) of the open phase
+  __shared__ int sg_open[TS_MAXCT];            // last phase opened for dispatch   (boundary -> dispatch, release)
+  __shared__ int n_seg_s, all_done_s;
+  if (wg >= C::NGRP * WPT) {
+    if (wg == C::NGRP * WPT && lane == 0) {
+      int ns = 0;
+      for (int k = 0; k < nb; ++k) {
+        if (t_round[k] < 0) continue;                    // masked node
+        if (ns > 0 && sg_node[ns - 1] == m_node[k] && sg_k0[ns - 1] + sg_n[ns - 1] == k) { sg_n[ns - 1]++; continue; }
+        sg_k0[ns] = k; sg_n[ns] = 1; sg_node[ns] = m_node[k];
+        // CTAs that share the node = arrivals the node expects per phase
+        const int nd = m_node[k];
+        const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
+        sg_target[ns] = min((ce - 1) / CH - cb / CH + 1, (int)gridDim.x);
+        sg_kind[ns] = 0; sg_coef[ns] = 0.0; sg_open[ns] = 0; sg_done[ns] = 0;   // phase 0 (init) is open
+        ++ns;
+      }
+      n_seg_s = ns;
+      all_done_s = 0;
+    }
+    asm volatile("bar.sync 15, 64;" ::: "memory");     // the two service warps
+    const int n_seg = n_seg_s;
+
+    if (wg == C::NGRP * WPT) {
+      // =========================== boundary warp ===========================
+      // sg_state (private): 1 phase running, 0 waiting for the node's epoch, -1 retired
+      __shared__ int sg_state[TS_MAXCT], sg_round[TS_MAXCT];
+      for (int q = lane; q < n_seg; q += 32) { sg_state[q] = 1; sg_round[q] = 0; }
       __syncwarp();
-      for (int k0 = 0; k0 < nb; k0 += 32) {
-        const int k = k0 + lane;
-        bool ready = false;
-        int ep = 0;
-        if (k < nb && t_round[k] >= 0) {
-          ep = t_round[k] == 0 ? 0 : ld_relaxed(epoch + m_node[k]);
-          ready = (ep & DONE_BIT) || ep >= t_round[k];
+      int n_live = n_seg;
+      int ep_polled = 0;
+      while (n_live > 0) {
+        bool progress = false;
+        for (int s0 = 0; s0 < n_seg; s0 += 32) {
+          const int sidx = s0 + lane;
+          const bool have = sidx < n_seg;
+          const int state = have ? sg_state[sidx] : -1;
+          int old = -1, node = 0, rnd = 0;
+          bool arrived = false, retired = false;
+          if (state == 1 && ld_acquire_cta_shared(&sg_done[sidx]) == sg_n[sidx]) {
+            // every tile of the segment has executed the phase
+            node = sg_node[sidx]; rnd = sg_round[sidx];
+            sg_done[sidx] = 0;
+            if (sg_kind[sidx] == 3) { sg_state[sidx] = -1; retired = true; }
+            else {
+              old = atom_add_acq_rel(a.cnt + node, 1);   // release: the consumers' stores of the phase
+              sg_round[sidx] = rnd + 1; sg_state[sidx] = 0;
+              arrived = true;
+            }
+          }
+          n_live -= __popc(__ballot_sync(0xffffffffu, retired));
+          if (__ballot_sync(0xffffffffu, arrived || retired)) progress = true;
+          unsigned last = __ballot_sync(0xffffffffu, arrived && old == sg_target[sidx] - 1);
+          while (last) {
+            // this CTA was the last of the node's CTAs in this phase: reduce the node, set its scalars
+            const int src = __ffs(last) - 1;
+            last &= last - 1;
+            const int nd = __shfl_sync(0xffffffffu, node, src);
+            const int round = __shfl_sync(0xffffffffu, rnd, src);
+            double *nst = a.nstate + (size_t)nd * 8;
+            const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
+            bool done = false;
+            if (round == 0) {
+              double sm[3];
+              node_sum<3>(a.partials, cb, ce, lane, sm);
+              if (lane == 0) { nst[0] = sm[0]; nst[1] = sm[1]; nst[5] = sm[2]; nst[2] = 0.0; nst[3] = 0.0; nst[4] = 0.0; }
+              done = !(sm[0] > 0.0) || !(sm[2] > a.tol2 * sm[1]);
+            } else if (round & 1) {
+              double sm[1];
+              node_sum<1>(a.partials, cb, ce, lane, sm);
+              if (sm[0] > 0.0) { if (lane == 0) nst[2] = __ldcg(nst + 0) / sm[0]; }
+              else done = true;
+            } else {
+              double sm[3];
+              node_sum<3>(a.partials, cb, ce, lane, sm);
+              const double rz = __ldcg(nst + 0), bb = __ldcg(nst + 1), it = __ldcg(nst + 4) + 1.0;
+              __syncwarp();
+              if (lane == 0) { nst[3] = sm[0] / rz; nst[0] = sm[0]; nst[5] = sm[2]; nst[4] = it; }
+              done = !(sm[2] > a.tol2 * bb) || !(sm[0] > 0.0) || it >= (double)a.max_iters;
+            }
+            if (lane == 0) {
+              a.cnt[nd] = 0;
+              if (done && a.stats) {
+                const unsigned long long it = (unsigned long long)(round / 2);
+                atomicAdd(a.stats, it);
+                atomicAdd(a.stats + 1, it * (unsigned long long)(__ldg(a.node_off + nd + 1) - __ldg(a.node_off + nd)));
+              }
+              st_release(epoch + nd, (round + 1) | (done ? DONE_BIT : 0));
+            }
+          }
+          __syncwarp();
+          // segments waiting for their node: has the next phase been published?  (the epoch was
+          // polled at the end of the previous pass)
+          bool fresh = false;
+          const int ep = s0 == 0 ? ep_polled : ld_relaxed(epoch + sg_node[min(sidx, n_seg - 1)]);
+          if (have && sg_state[sidx] == 0 && !arrived) fresh = (ep & DONE_BIT) || ep >= sg_round[sidx];
+          if (__ballot_sync(0xffffffffu, fresh)) {
+            fence_acq_rel();                              // what the publishers stored is visible from here on
+            if (fresh) {
+              const int r = sg_round[sidx];
+              const int kind = (ep & DONE_BIT) ? 3 : ((r & 1) ? 1 : 2);
+              if (kind != 3) sg_coef[sidx] = __ldcg(a.nstate + (size_t)sg_node[sidx] * 8 + (kind == 1 ? 3 : 2));
+              sg_kind[sidx] = kind;
+              sg_state[sidx] = 1;
+              st_release_cta_shared(&sg_open[sidx], r);   // the dispatch warp may hand out the phase
+            }
+            progress = true;
+          }
+          __syncwarp();
         }
-        const unsigned m = __ballot_sync(0xffffffffu, ready);
-        if (ready) {
-          const int pos = n_ready_s + __popc(m & ((1u << lane) - 1));
-          r_k[pos] = k; r_ep[pos] = ep;
+        ep_polled = (lane < n_seg && sg_state[lane] == 0) ? ld_relaxed(epoch + sg_node[lane]) : 0;
+        if (!progress) __nanosleep(20);
+      }
+      if (lane == 0) st_release_cta_shared(&all_done_s, 1);
+      return;
+    }
+
+    // =========================== dispatch warp ===========================
+    __shared__ int dp_round[TS_MAXCT];                 // next phase to hand out, per segment (private)
+    for (int q = lane; q < n_seg; q += 32) dp_round[q] = 0;
+    __syncwarp();
+    int stage = 0;
+    uint32_t pe = 0;                                   // parity bits of the empty barriers
+    int uses = 0;                                      // stages handed out so far
+    unsigned long long dbg_loops = 0, dbg_wait_empty = 0, dbg_t0 = clock64(), dbg_c5 = 0;
+    int cur = -1, cur_next = 0, cur_n = 0, cur_k0 = 0, cur_kind = 0;   // segment being handed out (warp-uniform)
+    double cur_coef = 0.0;
+    while (true) {
+      ++dbg_loops;
+      int in_flight = uses - ld_acquire_cta_shared(&returned_s);
+      if (in_flight == 0 && ld_acquire_cta_shared(&all_done_s)) break;
+      bool progress = false;
+      while (in_flight < NST) {
+        if (cur < 0 || cur_next >= cur_n) {
+          // pick the open segment with the oldest phase
+          int best = -1, best_round = 0x7fffffff;
+          for (int s0 = 0; s0 < n_seg; s0 += 32) {
+            const int sidx = s0 + lane;
+            int key = 0x7fffffff;
+            if (sidx < n_seg && ld_acquire_cta_shared(&sg_open[sidx]) >= dp_round[sidx]) key = dp_round[sidx];
+            int idx = sidx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const int k2 = __shfl_xor_sync(0xffffffffu, key, o), i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+              if (k2 < key || (k2 == key && i2 < idx)) { key = k2; idx = i2; }
+            }
+            if (key < best_round) { best_round = key; best = idx; }
+          }
+          cur = best;
+          if (best < 0) break;
+          cur_next = 0; cur_n = sg_n[best]; cur_k0 = sg_k0[best]; cur_kind = sg_kind[best]; cur_coef = sg_coef[best];
+          if (lane == 0) {
+            dp_round[best] = best_round + 1;             // the whole phase is handed out below
+            asm volatile("fence.proxy.async;" ::: "memory");   // bulk copies read what other CTAs stored
+          }
+          __syncwarp();
+        }
+        progress = true;
+        const long long tS = clock64();
+        const int kk = cur_k0 + cur_next, kd = cur_kind;
+        ++cur_next;
+        if (lane == 0) {
+          if (uses >= NST) { const long long w0 = clock64(); mbar_wait(&empty[stage], (pe >> stage) & 1u); dbg_wait_empty += clock64() - w0; }
+          d_k[stage] = kk; d_kind[stage] = kd; d_coef[stage] = cur_coef; d_seg[stage] = cur;
+          if (kd == 1 || kd == 2) {
+            const int ct = tile_of(kk);
+            unsigned char *sb = dyn + (size_t)stage * C::STAGE_BYTES;
+            const double *rc = a.rec + (size_t)ct * C::RL;
+            const size_t v0 = (size_t)ct * C::VEC;
+            if (kd == 1) {
+              const int r0 = m_sell[kk][0], rows = m_sell[kk][WPT] - r0;
+              const bool sell_staged = rows <= C::SELL_CAP && rows > 0;
+              mbar_expect_tx(&full[uses % (2 * NST)], (C::HV * C::VEC + 2 * C::VEC + CTILE) * 8 + (sell_staged ? rows * 384 : 0));
+              bulk_g2s(sb, a.z + v0 - TS_HALO * C::VEC, C::HV * C::VEC * 8, &full[uses % (2 * NST)]);   // z is padded by the halo
+              bulk_g2s(sb + C::OFF_R, rc + C::VEC, (2 * C::VEC + CTILE) * 8, &full[uses % (2 * NST)]);
+              if (sell_staged) bulk_g2s(sb + C::OFF_S, a.sell_pack + (size_t)r0 * 384, rows * 384, &full[uses % (2 * NST)]);
+            } else {
+              mbar_expect_tx(&full[uses % (2 * NST)], (C::VEC + C::RL) * 8);
+              bulk_g2s(sb, a.z + v0, C::VEC * 8, &full[uses % (2 * NST)]);
+              bulk_g2s(sb + C::OFF_R, rc, C::RL * 8, &full[uses % (2 * NST)]);
+            }
+          } else {
+            mbar_arrive(&full[uses % (2 * NST)]);                  // no staged data: init / publish use direct loads
+          }
         }
         __syncwarp();
-        if (lane == 0) n_ready_s += __popc(m);
-        __syncwarp();
+        dbg_c5 += clock64() - tS;
+        if (uses >= NST) pe ^= 1u << stage;
+        ++uses;
+        ++in_flight;
+        stage = stage + 1 == NST ? 0 : stage + 1;
+      }
+      if (!progress) __nanosleep(20);
+    }
+    // ---- every segment retired and every tile handed back: tell the consumers to stop
+    if (lane == 0) {
+      for (int q = 0; q < C::NGRP; ++q) {                // one stop descriptor per consumer group
+        if (uses >= NST) mbar_wait(&empty[stage], (pe >> stage) & 1u);
+        d_kind[stage] = -1;
+        mbar_arrive(&full[uses % (2 * NST)]);
+        if (uses >= NST) pe ^= 1u << stage;
+        ++uses;
+        stage = stage + 1 == NST ? 0 : stage + 1;
+      }
+      if (a.stats && blockIdx.x == 7) {
+        a.stats[2] = dbg_loops; a.stats[3] = dbg_wait_empty; a.stats[4] = clock64() - dbg_t0; a.stats[5] = uses;
+        a.stats[11] = dbg_c5;
       }
     }
-    __syncthreads();
-    const int n_ready = n_ready_s;
-    if (n_ready == 0) { __nanosleep(200); __syncthreads(); continue; }
-    fence_acq_rel();                                     // what the publishers stored is visible from here on
-    if (threadIdx.x < n_ready) {
-      // scalars of the phase: beta for phase A (odd), alpha for phase B (even)
-      const int j = threadIdx.x, k = r_k[j], r = t_round[k];
-      double coef = 0.0;
-      if (!(r_ep[j] & DONE_BIT) && r > 0) coef = __ldcg(a.nstate + (size_t)m_node[k] * 8 + ((r & 1) ? 3 : 2));
-      r_coef[j] = coef;
+    return;
+  }
+
+  // =============================== consumer warps ===================================
+  // the two groups take the ring's uses alternately, so that one group's waits (far gathers,
+  // barriers) overlap the other group's arithmetic
+  int tick = 0;
+  unsigned long long dbg_wait_full = 0;
+  for (int use = grp;; use += 2) {
+    const int stage = use % NST;
+    const long long w0 = clock64();
+    mbar_wait(&full[use % (2 * NST)], (unsigned)(use / (2 * NST)) & 1u);
+    dbg_wait_full += clock64() - w0;
+    const int kd = d_kind[stage];
+    if (kd < 0) { if (a.stats && blockIdx.x == 7 && threadIdx.x == 0) a.stats[6] = dbg_wait_full; break; }
+    const int k = d_k[stage], ct = tile_of(k);
+    const double coef = d_coef[stage];
+    const bool valid = 32 * wi + lane < m_cnt[k];
+    const int p = m_start[k] + 32 * wi + lane;                     // own pose index
+    const size_t vb = (size_t)(WPT * ct + wi) * (32 * D) + lane;     // slot of (pose, column 0)
+    const unsigned char *sb = dyn + (size_t)stage * C::STAGE_BYTES;
+    double part[3] = {0.0, 0.0, 0.0};
+    double *rc = a.rec + (size_t)ct * C::RL;             // this tile's record {x, p, Ap, diag}
+    const int lo = wi * (32 * D) + lane;                 // this pose inside a tile-sized vector
+    if (kd == 3) {
+      // node finished: publish u into the pose array, t = -u
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) a.xio[(size_t)p * PB + c] = -__ldcg(rc + lo + 32 * c);
+      }
+    } else if (kd == 0) {
+      // r = b - A x0 ; z = r / diag ; p = Ap = 0 ; partials rz, bb, rr   (direct loads, once per solve)
+      if (valid) {
+        double x0[D], acc[D], b[D];
+        const double dg = __ldg(a.d00 + p);
+#pragma unroll
+        for (int c = 0; c < D; ++c) { x0[c] = 0.0; acc[c] = 0.0; b[c] = a.rhs[(size_t)p * D + c]; }
+        if (a.warm) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) { x0[c] = -a.xio[(size_t)p * PB + c]; acc[c] = dg * x0[c]; }
+          const int e0 = __ldg(a.rowptr + p), e1 = __ldg(a.rowptr + p + 1);
+          for (int e = e0; e < e1; ++e) {
+            const double av = __ldg(a.a00 + e);
+            const double *xq = a.xio + (size_t)__ldg(a.col + e) * PB;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] = fma(av, -xq[c], acc[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const double rv = b[c] - acc[c], zv = rv / dg;
+          rc[lo + 32 * c] = x0[c];
+          a.z[vb + 32 * c] = zv;
+          rc[C::VEC + lo + 32 * c] = 0.0;
+          rc[2 * C::VEC + lo + 32 * c] = 0.0;
+          part[0] += rv * zv; part[1] += b[c] * b[c]; part[2] += rv * rv;
+        }
+      }
+    } else if (kd == 1) {
+      // phase A: w = A z ; Ap = w + beta Ap ; p = z + beta p ; partial p.Ap
+      const double beta = coef;
+      const double *zh = reinterpret_cast<const double *>(sb);              // z of the tiles ct-HALO .. ct+HALO
+      const double *sp = reinterpret_cast<const double *>(sb + C::OFF_R) + lo;
+      const double *sap = sp + C::VEC;
+      const double dg = reinterpret_cast<const double *>(sb + C::OFF_R)[2 * C::VEC + 32 * wi + lane];
+      const int r0 = m_sell[k][0], rows = m_sell[k][WPT] - r0;
+      const int s0 = m_sell[k][wi] - r0, s1 = m_sell[k][wi + 1] - r0;
+      const bool sell_staged = rows <= C::SELL_CAP;
+      const unsigned char *pack = sell_staged ? sb + C::OFF_S : a.sell_pack + (size_t)r0 * 384;
+      const double *sval = reinterpret_cast<const double *>(pack);
+      const int *scol = reinterpret_cast<const int *>(pack + (size_t)rows * 256);
+      const int halo_lo = (ct - TS_HALO) * C::VEC;
+      double zo[D], acc[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) { zo[c] = zh[TS_HALO * C::VEC + lo + 32 * c]; acc[c] = dg * zo[c]; }
+      // the slice loop is warp-uniform (padded entries have value 0); entries are taken eight at
+      // a time so that the gathers of far neighbours (outside the staged tiles) overlap
+      constexpr int EB = 8;
+      for (int s = s0; s < s1; s += EB) {
+        int slot[EB];
+        double av[EB], zq[EB][D];
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+          const bool in = s + q < s1;
+          slot[q] = in ? scol[(s + q) * 32 + lane] : (int)vb;
+          av[q] = in ? sval[(s + q) * 32 + lane] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+          const unsigned rel = (unsigned)(slot[q] - halo_lo);
+          if (rel >= (unsigned)(C::HV * C::VEC)) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) zq[q][c] = __ldcg(a.z + (size_t)slot[q] + 32 * c);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+          const unsigned rel = (unsigned)(slot[q] - halo_lo);
+          if (rel < (unsigned)(C::HV * C::VEC)) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) zq[q][c] = zh[rel + 32 * c];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < EB; ++q)
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc[c] = fma(av[q], zq[q][c], acc[c]);
+      }
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const double apv = acc[c] + beta * sap[32 * c];
+          const double pv = zo[c] + beta * sp[32 * c];
+          rc[2 * C::VEC + lo + 32 * c] = apv;
+          rc[C::VEC + lo + 32 * c] = pv;
+          part[0] += pv * apv;
+        }
+      }
+    } else {
+      // phase B: x += alpha p ; z -= alpha Ap / diag (r = diag z) ; partials rz, rr
+      const double alpha = coef;
+      const double *sz = reinterpret_cast<const double *>(sb) + lo;
+      const double *sx = reinterpret_cast<const double *>(sb + C::OFF_R) + lo;
+      const double *sp = sx + C::VEC, *sap = sx + 2 * C::VEC;
+      const double dg = reinterpret_cast<const double *>(sb + C::OFF_R)[3 * C::VEC + 32 * wi + lane];
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const double xv = sx[32 * c] + alpha * sp[32 * c];
+          const double rv = dg * sz[32 * c] - alpha * sap[32 * c];
+          const double zv = rv / dg;
+          rc[lo + 32 * c] = xv;
+          a.z[vb + 32 * c] = zv;
+          part[0] += rv * zv; part[2] += rv * rv;
+        }
+      }
     }
-    if (threadIdx.x == 0) asm volatile("fence.proxy.async;" ::: "memory");   // bulk copies read others' stores
-    __syncthreads();
-
-    // ---- the tile's vectors (and its ELLPACK rows) arrive by bulk copy, two stages deep;
-    // thread 0 is the producer.  kind: 0 init, 1 phase A, 2 phase B, 3 publish the result
-    auto kind_of = [&](int j) {
-      if (r_ep[j] & DONE_BIT) return 3;
-      const int r = t_round[r_k[j]];
-      return r == 0 ? 0 : ((r & 1) ? 1 : 2);
-    };
-    auto issue = [&](int j) {
-      const int kd = kind_of(j);
-      if (kd == 0 || kd == 3) return;                    // direct loads, once per solve
-      const int k = r_k[j], ct = blockIdx.x + k * gridDim.x, stg = j % NST;
-      unsigned char *sb = dyn + (size_t)stg * C::STAGE_BYTES;
-      const size_t v0 = (size_t)ct * C::VEC;
-      const int r0 = m_sell[k][0], rows = m_sell[k][8] - r0;
-      const bool phA = kd == 1, sell_staged = phA && rows <= C::SELL_CAP;
-      uint32_t bytes = 3 * C::VEC * 8 + CTILE * 8;
-      if (phA) { if (sell_staged) bytes += rows * 32 * 12; }
-      else bytes += C::VEC * 8;
-      mbar_expect_tx(&full[stg], bytes);
-      const double *s0 = phA ? a.z : a.p, *s1 = a.ap, *s2 = phA ? a.p : a.x;
-      bulk_g2s(sb, s0 + v0, C::VEC * 8, &full[stg]);
-      bulk_g2s(sb + C::VEC * 8, s1 + v0, C::VEC * 8, &full[stg]);
-      bulk_g2s(sb + 2 * C::VEC * 8, s2 + v0, C::VEC * 8, &full[stg]);
-      bulk_g2s(sb + C::OFF_DIAG, a.diag_s + (size_t)ct * CTILE, CTILE * 8, &full[stg]);
-      if (phA) {
-        if (sell_staged && rows > 0) {
-          bulk_g2s(sb + C::OFF_X, a.sell_val + (size_t)r0 * 32, rows * 32 * 8, &full[stg]);
-          bulk_g2s(sb + C::OFF_COL, a.sell_col + (size_t)r0 * 32, rows * 32 * 4, &full[stg]);
-        }
-      } else {
-        bulk_g2s(sb + C::OFF_X, a.z + v0, C::VEC * 8, &full[stg]);
-      }
-    };
-    if (threadIdx.x == 0)
-      for (int j = 0; j < min(NST, n_ready); ++j) issue(j);
-
-    for (int j = 0; j < n_ready; ++j) {
-      const int k = r_k[j], ct = blockIdx.x + k * gridDim.x, stg = j % NST, kd = kind_of(j);
-      const bool valid = 32 * wi + lane < m_cnt[k];
-      const int p = m_start[k] + 32 * wi + lane;                     // own pose index
-      const size_t vb = (size_t)(8 * ct + wi) * (32 * D) + lane;     // slot of (pose, column 0)
-      double part[3] = {0.0, 0.0, 0.0};
-      if (kd == 3) {
-        // node finished: publish u into the pose array, t = -u
-        if (valid) {
-#pragma unroll
-          for (int c = 0; c < D; ++c) a.xio[(size_t)p * PB + c] = -__ldcg(a.x + vb + 32 * c);
-        }
-      } else if (kd == 0) {
-        // r = b - A x0 ; z = r / diag ; p = Ap = 0 ; partials rz, bb, rr
-        if (valid) {
-          double x0[D], acc[D], b[D];
-          const double dg = __ldg(a.d00 + p);
-#pragma unroll
-          for (int c = 0; c < D; ++c) { x0[c] = 0.0; acc[c] = 0.0; b[c] = a.rhs[(size_t)p * D + c]; }
-          if (a.warm) {
-#pragma unroll
-            for (int c = 0; c < D; ++c) { x0[c] = -a.xio[(size_t)p * PB + c]; acc[c] = dg * x0[c]; }
-            const int e0 = __ldg(a.rowptr + p), e1 = __ldg(a.rowptr + p + 1);
-            for (int e = e0; e < e1; ++e) {
-              const double av = __ldg(a.a00 + e);
-              const double *xq = a.xio + (size_t)__ldg(a.col + e) * PB;
-#pragma unroll
-              for (int c = 0; c < D; ++c) acc[c] = fma(av, -xq[c], acc[c]);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < D; ++c) {
-            const double rv = b[c] - acc[c], zv = rv / dg;
-            a.x[vb + 32 * c] = x0[c];
-            a.z[vb + 32 * c] = zv;
-            a.p[vb + 32 * c] = 0.0;
-            a.ap[vb + 32 * c] = 0.0;
-            part[0] += rv * zv; part[1] += b[c] * b[c]; part[2] += rv * rv;
-          }
-        }
-      } else {
-        const unsigned char *sb = dyn + (size_t)stg * C::STAGE_BYTES;
-        const double *sv0 = reinterpret_cast<const double *>(sb) + wi * (32 * D) + lane;
-        const double *sv1 = sv0 + C::VEC, *sv2 = sv0 + 2 * C::VEC;
-        if (stg == 0) { mbar_wait(&full[0], ph0); ph0 ^= 1; }
-        else { mbar_wait(&full[1], ph1); ph1 ^= 1; }
-        const double dg = reinterpret_cast<const double *>(sb + C::OFF_DIAG)[32 * wi + lane];
-        if (kd == 1) {
-          // phase A: w = A z ; Ap = w + beta Ap ; p = z + beta p ; partial p.Ap
-          const double beta = r_coef[j];
-          const int r0 = m_sell[k][0];
-          const int s0 = m_sell[k][wi] - r0, s1 = m_sell[k][wi + 1] - r0;
-          const bool sell_staged = m_sell[k][8] - r0 <= C::SELL_CAP;
-          const double *sval = reinterpret_cast<const double *>(sb + C::OFF_X);
-          const int *scol = reinterpret_cast<const int *>(sb + C::OFF_COL);
-          const double *zt = reinterpret_cast<const double *>(sb);   // this tile's z, slots relative to tile_lo
-          const int tile_lo = ct * C::VEC;
-          double zo[D], acc[D];
-#pragma unroll
-          for (int c = 0; c < D; ++c) { zo[c] = sv0[32 * c]; acc[c] = dg * zo[c]; }
-          // the slice loop is warp-uniform (padded entries have value 0); entries are taken four
-          // at a time so that the gathers of out-of-tile neighbours overlap
-          for (int s = s0; s < s1; s += 4) {
-            int slot[4];
-            double av[4], zq[4][D];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const bool in = s + q < s1;
-              if (sell_staged) {
-                slot[q] = in ? scol[(s + q) * 32 + lane] : (int)vb;
-                av[q] = in ? sval[(s + q) * 32 + lane] : 0.0;
-              } else {
-                slot[q] = in ? __ldg(a.sell_col + (size_t)(r0 + s + q) * 32 + lane) : (int)vb;
-                av[q] = in ? __ldg(a.sell_val + (size_t)(r0 + s + q) * 32 + lane) : 0.0;
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const unsigned rel = (unsigned)(slot[q] - tile_lo);
-              if (rel < (unsigned)C::VEC) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) zq[q][c] = zt[rel + 32 * c];
-              } else {
-#pragma unroll
-                for (int c = 0; c < D; ++c) zq[q][c] = __ldcg(a.z + (size_t)slot[q] + 32 * c);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-              for (int c = 0; c < D; ++c) acc[c] = fma(av[q], zq[q][c], acc[c]);
-          }
-          if (valid) {
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              const double apv = acc[c] + beta * sv1[32 * c];
-              const double pv = zo[c] + beta * sv2[32 * c];
-              a.ap[vb + 32 * c] = apv;
-              a.p[vb + 32 * c] = pv;
-              part[0] += pv * apv;
-            }
-          }
-        } else {
-          // phase B: x += alpha p ; z -= alpha Ap / diag (r = diag z) ; partials rz, rr
-          const double alpha = r_coef[j];
-          const double *sv3 = reinterpret_cast<const double *>(sb + C::OFF_X) + wi * (32 * D) + lane;
-          if (valid) {
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              const double xv = sv2[32 * c] + alpha * sv0[32 * c];
-              const double rv = dg * sv3[32 * c] - alpha * sv1[32 * c];
-              const double zv = rv / dg;
-              a.x[vb + 32 * c] = xv;
-              a.z[vb + 32 * c] = zv;
-              part[0] += rv * zv; part[2] += rv * rv;
-            }
-          }
-        }
-      }
-      if (kd != 3) {
-        const double p0 = warp_sum(part[0]), p1 = warp_sum(part[1]), p2 = warp_sum(part[2]);
-        if (lane == 0) { red[wi][0] = p0; red[wi][1] = p1; red[wi][2] = p2; }
-      }
-      __syncthreads();                                   // stage buffer free again, red[] complete
-      if (threadIdx.x == 0 && j + NST < n_ready) issue(j + NST);
-      if (kd != 3 && threadIdx.x < 3) {
+    const int rb = tick & 1;
+    if (kd != 3) {
+      const double p0 = warp_sum(part[0]), p1 = warp_sum(part[1]), p2 = warp_sum(part[2]);
+      if (lane == 0) { red[grp][rb][wi][0] = p0; red[grp][rb][wi][1] = p1; red[grp][rb][wi][2] = p2; }
+    }
+    consumer_barrier(grp);                               // the group is done with the stage; red[grp][rb] complete
+    if (wi == 0) {
+      if (kd != 3 && lane < 3) {
         // the tile's partial, summed over the warps in a fixed order
         double sacc = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sacc += red[q][threadIdx.x];
-        a.partials[(size_t)ct * 4 + threadIdx.x] = sacc;
+        for (int q = 0; q < WPT; ++q) sacc += red[grp][rb][q][lane];
+        a.partials[(size_t)ct * 4 + lane] = sacc;
       }
-      __syncthreads();                                   // red[] free again
-    }
-
-    // ---- warp 0: arrive on the nodes of the tiles just executed
-    if (wi == 0) {
-      for (int j0 = 0; j0 < n_ready; j0 += 32) {
-        const int j = j0 + lane;
-        const bool mine = j < n_ready;
-        int old = -1, node = 0, rnd = 0;
-        bool fin = false;
-        if (mine) {
-          const int k = r_k[j];
-          node = m_node[k]; rnd = t_round[k];
-          fin = (r_ep[j] & DONE_BIT) != 0;
-          if (fin) { t_round[k] = -1; atomicSub(&n_live_s, 1); }
-          else {
-            t_round[k] = rnd + 1;
-            old = atom_add_acq_rel(a.cnt + node, 1);     // release: this CTA's stores of the phase (ordered by bar.sync)
-          }
-        }
-        unsigned last = __ballot_sync(0xffffffffu, mine && !fin &&
-                                      old == __ldg(a.node_cte + node) - __ldg(a.node_ctb + node) - 1);
-        while (last) {
-          // a tile of this CTA was the last of its node in this phase: reduce the node, set its scalars
-          const int src = __ffs(last) - 1;
-          last &= last - 1;
-          const int nd = __shfl_sync(0xffffffffu, node, src);
-          const int round = __shfl_sync(0xffffffffu, rnd, src);
-          double *nst = a.nstate + (size_t)nd * 8;
-          const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
-          bool done = false;
-          if (round == 0) {
-            double s[3];
-            node_sum<3>(a.partials, cb, ce, lane, s);
-            if (lane == 0) { nst[0] = s[0]; nst[1] = s[1]; nst[5] = s[2]; nst[2] = 0.0; nst[3] = 0.0; nst[4] = 0.0; }
-            done = !(s[0] > 0.0) || !(s[2] > a.tol2 * s[1]);
-          } else if (round & 1) {
-            double s[1];
-            node_sum<1>(a.partials, cb, ce, lane, s);
-            if (s[0] > 0.0) { if (lane == 0) nst[2] = __ldcg(nst + 0) / s[0]; }
-            else done = true;
-          } else {
-            double s[3];
-            node_sum<3>(a.partials, cb, ce, lane, s);
-            const double rz = __ldcg(nst + 0), bb = __ldcg(nst + 1), it = __ldcg(nst + 4) + 1.0;
-            __syncwarp();
-            if (lane == 0) { nst[3] = s[0] / rz; nst[0] = s[0]; nst[5] = s[2]; nst[4] = it; }
-            done = !(s[2] > a.tol2 * bb) || !(s[0] > 0.0) || it >= (double)a.max_iters;
-          }
-          if (lane == 0) {
-            a.cnt[nd] = 0;
-            if (done && a.stats) {
-              const unsigned long long it = (unsigned long long)(round / 2);
-              atomicAdd(a.stats, it);
-              atomicAdd(a.stats + 1, it * (unsigned long long)(__ldg(a.node_off + nd + 1) - __ldg(a.node_off + nd)));
-            }
-            st_release(epoch + nd, (round + 1) | (done ? DONE_BIT : 0));
-          }
-        }
+      __syncwarp();
+      if (lane == 0) {
+        const int seg = d_seg[stage];
+        mbar_arrive(&empty[stage]);                      // stage buffer free again
+        // hand the tile back: the scheduler arrives on the node once the whole segment is back
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
+        atomicAdd(&sg_done[seg], 1);
+        atomicAdd(&returned_s, 1);
       }
     }
-    __syncthreads();
-    n_live = n_live_s;
+    ++tick;
   }
 }
 
 template <int D> int launch_tsolve(const TSolveArgs &a, int grid, cudaStream_t s) {
   TSolveArgs args = a;
   void *params[] = {&args};
-  return (int)cudaLaunchCooperativeKernel((const void *)k_tsolve<D>, dim3(grid), dim3(256), params,
+  return (int)cudaLaunchCooperativeKernel((const void *)k_tsolve<D>, dim3(grid), dim3(TSCfg<D>::THREADS), params,
                                           TSCfg<D>::DYN_BYTES, s);
 }
 template int launch_tsolve<2>(const TSolveArgs &, int, cudaStream_t);
@@ -432,7 +582,7 @@ template <int D> int tsolve_max_grid(int device) {
   int per_sm = 0, sms = 0;
   if (cudaFuncSetAttribute(k_tsolve<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSCfg<D>::DYN_BYTES) != cudaSuccess)
     return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tsolve<D>, 256, TSCfg<D>::DYN_BYTES) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tsolve<D>, TSCfg<D>::THREADS, TSCfg<D>::DYN_BYTES) != cudaSuccess)
     return -1;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
   return per_sm * sms;
