@@ -750,34 +750,38 @@ template <int D> struct Drv {
 };
 
 // ---- layout conversion between the reference's global X and device pose blocks ------
-static void pack_pose(int d, const double *X, int64_t ldx, int64_t N, int64_t gid, double *blk) {
-  for (int c = 0; c < d; ++c) blk[c] = X[gid + c * ldx];
-  for (int r = 0; r < d; ++r)
-    for (int c = 0; c < d; ++c) blk[(1 + r) * d + c] = X[N + d * gid + r + c * ldx];
+// The host matrix goes to the device as it is (one strided copy, d columns of (d+1)N doubles)
+// and is re-laid out there; nothing is converted on the host.
+static int stage_alloc(Handle *h) {
+  if (h->d_xstage) return 0;
+  const size_t n = (size_t)(h->d + 1) * h->N * h->d;
+  void *q = nullptr;
+  CK(cudaMalloc(&q, n * sizeof(double)));
+  CK(cudaMemsetAsync(q, 0, n * sizeof(double), h->stream));
+  h->allocs.push_back(q);
+  h->d_xstage = static_cast<double *>(q);
+  return 0;
 }
-static void unpack_pose(int d, double *X, int64_t ldx, int64_t N, int64_t gid, const double *blk) {
-  for (int c = 0; c < d; ++c) X[gid + c * ldx] = blk[c];
-  for (int r = 0; r < d; ++r)
-    for (int c = 0; c < d; ++c) X[N + d * gid + r + c * ldx] = blk[(1 + r) * d + c];
+static int stage_upload(Handle *h, const double *X, int64_t ldx) {
+  RC(stage_alloc(h));
+  const size_t rows = (size_t)(h->d + 1) * h->N;
+  CK(cudaMemcpy2DAsync(h->d_xstage, rows * sizeof(double), X, (size_t)ldx * sizeof(double), rows * sizeof(double),
+                       h->d, cudaMemcpyHostToDevice, h->stream));
+  return 0;
 }
-static void pack_all(Handle *h, const double *X, int64_t ldx, std::vector<double> &buf) {
-  const int PB = PBof(h);
-  buf.resize((size_t)h->NP * PB);
-  for (int p = 0; p < h->NO; ++p) pack_pose(h->d, X, ldx, h->N, h->own_gid[p], &buf[(size_t)p * PB]);
-  for (int k = 0; k < h->NH; ++k) pack_pose(h->d, X, ldx, h->N, h->halo_gid[k], &buf[(size_t)(h->NO + k) * PB]);
+static void pack_dev(Handle *h, double *d0, double *d1, double *d2, double *d3, double *d4) {
+  const int64_t ld = (int64_t)(h->d + 1) * h->N;
+  if (h->d == 2) launch_pack_poses<2>(h->NP, h->d_pose_gid, h->d_xstage, ld, h->N, d0, d1, d2, d3, d4, h->stream);
+  else launch_pack_poses<3>(h->NP, h->d_pose_gid, h->d_xstage, ld, h->N, d0, d1, d2, d3, d4, h->stream);
+  h->ctr.launches++;
 }
 
 int driver_initialize(Handle *h, const double *X, int64_t ldx) {
   if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
   if (ldx < (int64_t)(h->d + 1) * h->N) { set_error("ldx too small"); return MMPGO_ERR_ARG; }
-  std::vector<double> buf;
-  pack_all(h, X, ldx, buf);
+  RC(stage_upload(h, X, ldx));
   h->ik = 0; h->ikm1 = 1; h->iak = 2; h->icur = 0;
-  for (int k = 0; k < 3; ++k)
-    CK(cudaMemcpyAsync(h->X[k], buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->Xakh, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->xprop, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  pack_dev(h, h->X[0], h->X[1], h->X[2], h->Xakh, h->xprop);
   for (auto &s : h->st) { s = NodeState(); s.updated = false; }
   h->star_restarts = 0;
   if (h->opt.algorithm == MMPGO_ALG_STAR) {
@@ -786,6 +790,8 @@ int driver_initialize(Handle *h, const double *X, int64_t ldx) {
                        : Drv<3>::edge_objective(h, h->X[h->ik], &f, false);
     if (rc) return rc;
     h->star_fobj = f; h->starF = f;                                   // DPGOStar.cpp:120-122
+  } else {
+    CK(cudaStreamSynchronize(h->stream));                             // X is borrowed for the call only
   }
   h->initialized = true;
   return 0;
@@ -806,11 +812,20 @@ int driver_communicate(Handle *h) {
 
 int driver_get_poses(Handle *h, double *X, int64_t ldx) {
   if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
-  const int PB = PBof(h);
-  std::vector<double> buf((size_t)h->NO * PB);
-  CK(cudaMemcpyAsync(buf.data(), h->X[h->ik], buf.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  RC(stage_alloc(h));
+  const int d = h->d;
+  const int64_t ld = (int64_t)(d + 1) * h->N;
+  if (d == 2) launch_unpack_poses<2>(h->NO, h->d_pose_gid, h->X[h->ik], h->d_xstage, ld, h->N, h->stream);
+  else launch_unpack_poses<3>(h->NO, h->d_pose_gid, h->X[h->ik], h->d_xstage, ld, h->N, h->stream);
+  h->ctr.launches++;
+  // only the rows of the local nodes travel back: own poses are the id range [g_lo, g_hi)
+  const int64_t g_lo = h->own_gid.front(), g_hi = h->own_gid.back() + 1;
+  CK(cudaMemcpy2DAsync(X + g_lo, (size_t)ldx * sizeof(double), h->d_xstage + g_lo, (size_t)ld * sizeof(double),
+                       (size_t)(g_hi - g_lo) * sizeof(double), d, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpy2DAsync(X + h->N + d * g_lo, (size_t)ldx * sizeof(double), h->d_xstage + h->N + d * g_lo,
+                       (size_t)ld * sizeof(double), (size_t)(g_hi - g_lo) * d * sizeof(double), d,
+                       cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  for (int p = 0; p < h->NO; ++p) unpack_pose(h->d, X, ldx, h->N, h->own_gid[p], &buf[(size_t)p * PB]);
   return 0;
 }
 
@@ -833,9 +848,8 @@ int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *cou
 
 int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f) {
   if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
-  std::vector<double> buf;
-  pack_all(h, X, ldx, buf);
-  CK(cudaMemcpyAsync(h->xeval, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  RC(stage_upload(h, X, ldx));
+  pack_dev(h, h->xeval, nullptr, nullptr, nullptr, nullptr);
   // evaluate_f reports the LOCAL partial sum (see mmpgo.h); halo rows come from X itself
   const int world = h->world;
   h->world = 1;

@@ -78,6 +78,8 @@ struct Handle {
   int max_dense_n0 = 0;
   bool any_dense = false, any_pcg = false;
   std::vector<int> dense_mask, pcg_mask;
+  double *d_xstage = nullptr;         // global iterate in the reference layout (lazy)
+  int64_t *d_pose_gid = nullptr;      // [NP] global id of own + halo poses
   // pose vectors (NP x PB)
   double *X[3] = {nullptr, nullptr, nullptr};   // rotating: Xk, Xkm1, Xak
   int ik = 0, ikm1 = 1, iak = 2;

@@ -1150,4 +1150,55 @@ template void launch_gather_poses<3>(int64_t, const int *, const double *, doubl
 template void launch_scatter_poses<2>(int64_t, const int *, const double *, double *, cudaStream_t);
 template void launch_scatter_poses<3>(int64_t, const int *, const double *, double *, cudaStream_t);
 
+// =============================================================================
+// layout conversion between the reference's global iterate (column-major ((d+1)N) x d,
+// rows [t; R blocks], C++/examples/dist_pgo.cpp:502-511) and the device pose blocks
+// =============================================================================
+template <int D>
+__global__ void k_pack_poses(int64_t n, const int64_t *gid, const double *X, int64_t ld, int64_t N, double *d0,
+                             double *d1, double *d2, double *d3, double *d4) {
+  constexpr int PB = Dim<D>::PB;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * PB) return;
+  const int64_t p = i / PB;
+  const int k = (int)(i % PB), r = k / D, c = k % D;
+  const int64_t g = gid[p];
+  const double v = r == 0 ? X[g + c * ld] : X[N + D * g + (r - 1) + c * ld];
+  d0[i] = v;
+  if (d1) d1[i] = v;
+  if (d2) d2[i] = v;
+  if (d3) d3[i] = v;
+  if (d4) d4[i] = v;
+}
+template <int D>
+__global__ void k_unpack_poses(int64_t n, const int64_t *gid, const double *src, double *X, int64_t ld, int64_t N) {
+  constexpr int PB = Dim<D>::PB;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * PB) return;
+  const int64_t p = i / PB;
+  const int k = (int)(i % PB), r = k / D, c = k % D;
+  const int64_t g = gid[p];
+  const double v = src[i];
+  if (r == 0) X[g + c * ld] = v;
+  else X[N + D * g + (r - 1) + c * ld] = v;
+}
+template <int D>
+void launch_pack_poses(int64_t n, const int64_t *gid, const double *X, int64_t ld, int64_t N, double *d0, double *d1,
+                       double *d2, double *d3, double *d4, cudaStream_t s) {
+  if (n <= 0) return;
+  const int64_t tot = n * Dim<D>::PB;
+  k_pack_poses<D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(n, gid, X, ld, N, d0, d1, d2, d3, d4);
+}
+template <int D>
+void launch_unpack_poses(int64_t n, const int64_t *gid, const double *src, double *X, int64_t ld, int64_t N,
+                         cudaStream_t s) {
+  if (n <= 0) return;
+  const int64_t tot = n * Dim<D>::PB;
+  k_unpack_poses<D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(n, gid, src, X, ld, N);
+}
+template void launch_pack_poses<2>(int64_t, const int64_t *, const double *, int64_t, int64_t, double *, double *, double *, double *, double *, cudaStream_t);
+template void launch_pack_poses<3>(int64_t, const int64_t *, const double *, int64_t, int64_t, double *, double *, double *, double *, double *, cudaStream_t);
+template void launch_unpack_poses<2>(int64_t, const int64_t *, const double *, double *, int64_t, int64_t, cudaStream_t);
+template void launch_unpack_poses<3>(int64_t, const int64_t *, const double *, double *, int64_t, int64_t, cudaStream_t);
+
 }  // namespace mmpgo

@@ -216,4 +216,10 @@ template <int D> void launch_pcg_dir(const Tiles &tl, const SolveArgs &sa, const
 template <int D> void launch_gather_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);
 template <int D> void launch_scatter_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);
 
+// global iterate (column-major, rows [t; R blocks]) <-> pose blocks, on the device
+template <int D> void launch_pack_poses(int64_t n, const int64_t *gid, const double *X, int64_t ld, int64_t N,
+                                        double *d0, double *d1, double *d2, double *d3, double *d4, cudaStream_t s);
+template <int D> void launch_unpack_poses(int64_t n, const int64_t *gid, const double *src, double *X, int64_t ld,
+                                          int64_t N, cudaStream_t s);
+
 }  // namespace mmpgo

@@ -35,9 +35,14 @@ template <typename T> static int dalloc(Handle *h, T **p, size_t n) {
   return 0;
 }
 template <typename T> static int upload(Handle *h, T **p, const std::vector<T> &v) {
+  // the copy goes through the handle's stream like dalloc's memset: the stream is non-blocking,
+  // so a copy on the legacy default stream would not be ordered after that memset
   int rc = dalloc(h, p, v.size());
   if (rc) return rc;
-  if (!v.empty()) CK(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (!v.empty()) {
+    CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // v may be a temporary
+  }
   return 0;
 }
 
@@ -415,6 +420,11 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
 
   // ---- upload
   int rc = 0;
+  {
+    std::vector<int64_t> pg(h->own_gid);
+    pg.insert(pg.end(), h->halo_gid.begin(), h->halo_gid.end());
+    if ((rc = upload(h, &h->d_pose_gid, pg))) return rc;
+  }
   if ((rc = upload(h, &h->d_rowptr, rowptr))) return rc;
   if ((rc = upload(h, &h->d_col, col))) return rc;
   if ((rc = upload(h, &h->d_blk, blk))) return rc;

@@ -110,9 +110,11 @@ class _Driver:
         return out.value
 
     # -- results() ----------------------------------------------------------
-    def X(self):
-        """Global-layout copy of the current iterate (rows of local nodes)."""
-        X = np.zeros(((self.d + 1) * self.N, self.d), order="F")
+    def X(self, out=None):
+        """Global-layout copy of the current iterate (rows of local nodes).  `out`: an
+        F-ordered ((d+1)N x d) float64 array to write into (e.g. pinned memory)."""
+        X = np.zeros(((self.d + 1) * self.N, self.d), order="F") if out is None else out
+        assert X.flags.f_contiguous and X.shape == ((self.d + 1) * self.N, self.d)
         L.check(self.lib.mmpgo_get_poses(self._h, L.dptr(X), X.shape[0]))
         return X
 
