@@ -6,4 +6,4 @@ reference's driver interface plus graph I/O.  There is no CPU fallback.
 """
 from .graph import PoseGraph, read_g2o, grid3d, sphere_rings, city2d  # noqa: F401
 from .lib import MmpgoError, load  # noqa: F401
-from .pgo import DPGOHash, DPGOStar, Options, run_dist_pgo  # noqa: F401
+from .pgo import DPGOHash, DPGOStar, Options, project_to_SOdn, run_dist_pgo  # noqa: F401

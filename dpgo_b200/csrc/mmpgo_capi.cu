@@ -239,4 +239,27 @@ int mmpgo_graph_sizes(mmpgo_handle hh, int64_t *sizes /* [8] */) {
   return MMPGO_OK;
 }
 
+int mmpgo_project_to_sodn(int32_t d, int64_t n, const double *A, double *U, int32_t device) {
+  if ((d != 2 && d != 3) || n < 0 || !A || !U) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
+  if (n == 0) return MMPGO_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) {
+    mmpgo::set_error("no CUDA device: libmmpgo has no CPU fallback");
+    return MMPGO_ERR_CUDA;
+  }
+  double *dA = nullptr, *dU = nullptr;
+  const size_t bytes = (size_t)n * d * d * sizeof(double);
+  int rc = MMPGO_OK;
+  if (cudaMalloc(&dA, bytes) != cudaSuccess || cudaMalloc(&dU, bytes) != cudaSuccess ||
+      cudaMemcpy(dA, A, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = MMPGO_ERR_CUDA;
+  if (!rc) {
+    if (d == 2) mmpgo::launch_project_blocks<2>(n, dA, dU, nullptr);
+    else mmpgo::launch_project_blocks<3>(n, dA, dU, nullptr);
+    if (cudaMemcpy(U, dU, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MMPGO_ERR_CUDA;
+  }
+  if (rc) mmpgo::set_error(std::string("project_to_SOdn: ") + cudaGetErrorString(cudaGetLastError()));
+  cudaFree(dA); cudaFree(dU);
+  return rc;
+}
+
 }  // extern "C"

@@ -1201,4 +1201,23 @@ template void launch_pack_poses<3>(int64_t, const int64_t *, const double *, int
 template void launch_unpack_poses<2>(int64_t, const int64_t *, const double *, double *, int64_t, int64_t, cudaStream_t);
 template void launch_unpack_poses<3>(int64_t, const int64_t *, const double *, double *, int64_t, int64_t, cudaStream_t);
 
+// batched polar projection of n row-major d x d blocks (project_to_SO3n / project_to_SO2n,
+// C++/DPGO/include/DPGO/DPGO_utils.h:515-565), one block per thread
+template <int D> __global__ void k_project_blocks(int64_t n, const double *A, double *U) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double M[D * D], R[D * D];
+#pragma unroll
+  for (int k = 0; k < D * D; ++k) M[k] = A[i * D * D + k];
+  project_to_SOd<D>(M, R);
+#pragma unroll
+  for (int k = 0; k < D * D; ++k) U[i * D * D + k] = R[k];
+}
+template <int D> void launch_project_blocks(int64_t n, const double *A, double *U, cudaStream_t s) {
+  if (n <= 0) return;
+  k_project_blocks<D><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, A, U);
+}
+template void launch_project_blocks<2>(int64_t, const double *, double *, cudaStream_t);
+template void launch_project_blocks<3>(int64_t, const double *, double *, cudaStream_t);
+
 }  // namespace mmpgo

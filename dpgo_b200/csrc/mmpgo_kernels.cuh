@@ -222,4 +222,6 @@ template <int D> void launch_pack_poses(int64_t n, const int64_t *gid, const dou
 template <int D> void launch_unpack_poses(int64_t n, const int64_t *gid, const double *src, double *X, int64_t ld,
                                           int64_t N, cudaStream_t s);
 
+template <int D> void launch_project_blocks(int64_t n, const double *A, double *U, cudaStream_t s);
+
 }  // namespace mmpgo

@@ -109,6 +109,7 @@ SIGNATURES = {
     "mmpgo_reset_counters": (C.c_int, [_P]),
     "mmpgo_synchronize": (C.c_int, [_P]),
     "mmpgo_stream": (C.c_void_p, [_P]),
+    "mmpgo_project_to_sodn": (C.c_int, [C.c_int32, C.c_int64, _dp, _dp, C.c_int32]),
 }
 
 _lib = None

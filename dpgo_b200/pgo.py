@@ -184,6 +184,15 @@ class DPGOStar(_Driver):
         return F.value, f.value, r.value
 
 
+def project_to_SOdn(A, device=0):
+    """project_to_SO3n / project_to_SO2n (C++/DPGO/include/DPGO/DPGO_utils.h:515-565) on the
+    device: the polar projection of every row-major d x d block of A (n, d, d)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    U = np.empty_like(A)
+    L.check(L.load().mmpgo_project_to_sodn(A.shape[1], A.shape[0], L.dptr(A), L.dptr(U), device))
+    return U
+
+
 def run_dist_pgo(graph, num_nodes, X0, iters, options=None, algorithm="hash", log=True):
     """The outer loop of `dist_pgo` (dist_pgo.cpp:446-531) on one GPU.
     Returns (driver, trace) with trace[k] = (2F, 2|grad F|) before iteration k."""

@@ -184,6 +184,12 @@ int mmpgo_star_objective(mmpgo_handle h, double *F, double *fobj, int32_t *resta
  * owned edges, tiles, local nodes, d} */
 int mmpgo_graph_sizes(mmpgo_handle h, int64_t *sizes);
 
+/* project_to_SO3n / project_to_SO2n (C++/DPGO/include/DPGO/DPGO_utils.h:515-565; kernels
+ * C++/DPGO/src/internal/project_to_SOd.cpp:27-33,121-196): the polar projection of n row-major
+ * d x d host blocks onto SO(d), on `device`; the operation the fused proximal kernel applies to
+ * every pose.  Needs no handle. */
+int mmpgo_project_to_sodn(int32_t d, int64_t n, const double *A, double *U, int32_t device);
+
 /* Measurement hook: average device time (CUDA events on the handle's stream) of
  * `reps` back-to-back launches of one hot kernel on the current iterate.
  * kind: 0 K2 evaluate, 1 K2 gradient, 2 K1 inter-edge pass, 3 K3 fused proximal,

@@ -176,3 +176,20 @@ def test_full_size_properties():
     Y = X[N:].reshape(N, 3, 3)
     assert np.abs(Y @ np.swapaxes(Y, 1, 2) - np.eye(3)).max() < 1e-12
     assert np.abs(np.linalg.det(Y) - 1).max() < 1e-12
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_projection_bitwise_vs_reference_avx2(d):
+    """The device polar projection against the outputs of the REAL reference kernels
+    (project_to_SOd.cpp compiled from /root/reference with -ffp-contract=off; fixture made by
+    tests/golden/make_projection_golden.py): bit-identical, since the device code spells the same
+    mul / add / fma sequence.  The stock (FMA-contracted) reference build differs by ulps."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref", "sod_projection.npz"))
+    A, want = z["A%d" % d], z["U%d" % d]
+    got = D.project_to_SOdn(A)
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    assert np.abs(got - z["U%d_fma" % d]).max() < 2e-14
+    from oracle import ref
+    if ref.available():                       # the compiled reference travels with the repo
+        assert np.array_equal(ref.project(A, nofma=True), want)
