@@ -6,7 +6,13 @@ SRC := dpgo_b200/csrc/mmpgo_kernels.cu dpgo_b200/csrc/mmpgo_tsolve.cu dpgo_b200/
 OBJ := $(SRC:.cu=.o)
 LIB := dpgo_b200/libmmpgo.so
 
-all: $(LIB)
+HOSTBIN := host/dist_pgo
+
+all: $(LIB) $(HOSTBIN)
+
+# the reference-language host: dist_pgo CLI + DPGOHash/DPGOStar classes over the C ABI
+$(HOSTBIN): host/src/dist_pgo.cpp host/include/mmpgo_host/DPGO.h include/mmpgo.h $(LIB)
+	g++ -O2 -std=c++17 -fopenmp -Ihost/include host/src/dist_pgo.cpp -o $@ -Ldpgo_b200 -lmmpgo -Wl,-rpath,'$$ORIGIN/../dpgo_b200'
 
 %.o: %.cu dpgo_b200/csrc/mmpgo_kernels.cuh dpgo_b200/csrc/mmpgo_driver.cuh dpgo_b200/csrc/so3_project.cuh include/mmpgo.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -15,5 +21,5 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -Xcompiler -fopenmp -lgomp -cudart shared
 
 clean:
-	rm -f $(OBJ) $(LIB)
+	rm -f $(OBJ) $(LIB) $(HOSTBIN)
 .PHONY: all clean

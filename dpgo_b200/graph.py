@@ -85,6 +85,48 @@ def read_g2o(path):
     return PoseGraph(d, n, i, j, R, t, kappa, tau)
 
 
+def _rot_to_quat(R):
+    # (qx, qy, qz, qw) of a rotation matrix, branch on the largest diagonal term
+    q = np.empty((len(R), 4))
+    for k, M in enumerate(R):
+        tr = M[0, 0] + M[1, 1] + M[2, 2]
+        if tr > 0:
+            s = 2.0 * np.sqrt(tr + 1.0)
+            q[k] = ((M[2, 1] - M[1, 2]) / s, (M[0, 2] - M[2, 0]) / s, (M[1, 0] - M[0, 1]) / s, 0.25 * s)
+        else:
+            i = int(np.argmax(np.diag(M)))
+            j, l = (i + 1) % 3, (i + 2) % 3
+            s = 2.0 * np.sqrt(1.0 + M[i, i] - M[j, j] - M[l, l])
+            v = np.empty(4)
+            v[i] = 0.25 * s
+            v[j] = (M[j, i] + M[i, j]) / s
+            v[l] = (M[l, i] + M[i, l]) / s
+            v[3] = (M[l, j] - M[j, l]) / s
+            q[k] = v
+    return q
+
+
+def write_g2o(path, g):
+    """Writes a PoseGraph as EDGE_SE2 / EDGE_SE3:QUAT lines with isotropic information matrices
+    chosen so that the reader's formulas (DPGO_utils.cpp:63-67, 107-116) give back tau and kappa."""
+    with open(path, "w") as fh:
+        if g.d == 3:
+            q = _rot_to_quat(g.R)
+            for k in range(g.num_edges):
+                it, ir = g.tau[k], 2.0 * g.kappa[k]
+                info = [it, 0, 0, 0, 0, 0, it, 0, 0, 0, 0, it, 0, 0, 0, ir, 0, 0, ir, 0, ir]
+                fh.write("EDGE_SE3:QUAT %d %d %s %s %s\n" % (
+                    g.i[k], g.j[k], " ".join(repr(float(v)) for v in g.t[k]),
+                    " ".join(repr(float(v)) for v in q[k]), " ".join(repr(float(v)) for v in info)))
+        else:
+            for k in range(g.num_edges):
+                th = np.arctan2(g.R[k, 1, 0], g.R[k, 0, 0])
+                it = g.tau[k]
+                fh.write("EDGE_SE2 %d %d %r %r %r %r 0.0 0.0 %r 0.0 %r\n" % (
+                    g.i[k], g.j[k], float(g.t[k, 0]), float(g.t[k, 1]), float(th), float(it), float(it),
+                    float(g.kappa[k])))
+
+
 # ---------------------------------------------------------------------------
 # synthetic graphs
 # ---------------------------------------------------------------------------

@@ -1,0 +1,79 @@
+"""The reference-language host (host/dist_pgo, host/include/mmpgo_host/DPGO.h): flag handling and
+the g2o reader without a GPU; the optimisation loop against the Python mirror on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import dpgo_b200 as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "host", "dist_pgo")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(BIN), reason="host/dist_pgo not built (make)")
+
+
+def _run(args, cwd=None):
+    return subprocess.run([BIN] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
+
+
+def test_flags_like_the_reference():
+    r = _run(["--help"])
+    assert r.returncode == 0
+    for flag in ("--dataset", "--num_nodes", "--iters", "--dist_init", "--loss", "--accelerated", "--save"):
+        assert flag in r.stdout                                  # dist_pgo.cpp:23-47
+    assert _run(["--num_nodes", "4"]).returncode != 0            # no dataset  (:59-62)
+    assert _run(["--dataset", "x.g2o"]).returncode != 0          # no node count (:64-67)
+    assert _run(["--dataset", "x.g2o", "--num_nodes", "2", "--loss", "cauchy"]).returncode != 0   # (:77-90)
+
+
+@pytest.mark.parametrize("kind", ["se3", "se2"])
+def test_cpp_reader_matches_python_reader(tmp_path, kind):
+    g = D.grid3d(4, 4, 3, seed=2)[0] if kind == "se3" else D.city2d(6, 5, seed=1)[0]
+    path = str(tmp_path / "g.g2o")
+    D.write_g2o(path, g)
+    h = D.read_g2o(path)
+    r = _run(["--dataset", path, "--num_nodes", "2", "--parse_only", "1"])
+    assert r.returncode == 0, r.stderr
+    tok = [l for l in r.stdout.splitlines() if l.startswith("parse_only")][0].split()[1:]
+    d = h.d
+    w = np.arange(1, d * d + 1)
+    want = [d, h.num_poses, h.num_edges, int(h.i.sum()), int(h.j.sum()), h.tau.sum(), h.kappa.sum(),
+            (h.R.reshape(-1, d * d) * w).sum(), (h.t * np.arange(1, d + 1)).sum()]
+    assert [int(v) for v in tok[:5]] == want[:5]
+    assert np.allclose([float(v) for v in tok[5:]], want[5:], rtol=1e-13, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg,loss", [("hash", "trivial"), ("star", "huber")])
+def test_cli_trace_equals_python_driver(tmp_path, alg, loss):
+    g, _, X0 = D.grid3d(6, 6, 6, seed=1)
+    path = str(tmp_path / "g.g2o")
+    D.write_g2o(path, g)
+    g = D.read_g2o(path)                    # both sides see the file's (rounded) numbers
+    np.savetxt(str(tmp_path / "x0.txt"), X0, fmt="%.17g")
+    iters = 6
+    r = _run(["--dataset", path, "--num_nodes", "4", "--iters", str(iters), "--loss", loss, "--algorithm", alg,
+              "--init", str(tmp_path / "x0.txt")], cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr + r.stdout
+    res = np.loadtxt(str(tmp_path / "results_chordal_4_amm.txt"))
+    assert res.shape == (iters + 1, 4)
+    _, trace = D.run_dist_pgo(g, 4, X0, iters, D.Options(loss=loss), alg)
+    assert np.allclose(res[:, 2], [t[0] for t in trace], rtol=1e-13)
+    assert np.allclose(res[:, 3], [t[1] for t in trace], rtol=1e-10)
+    assert os.path.exists(str(tmp_path / ("estimates_%s.txt" % loss)))
+
+
+@pytest.mark.gpu
+def test_cli_chordal_initialisation_is_a_sane_start(tmp_path):
+    g, Xgt, _ = D.grid3d(5, 5, 4, seed=4)
+    path = str(tmp_path / "g.g2o")
+    D.write_g2o(path, g)
+    r = _run(["--dataset", path, "--num_nodes", "4", "--iters", "3", "--dist_init", "false", "--save", "false"],
+             cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr + r.stdout
+    f0 = float([l for l in r.stdout.splitlines() if l.startswith("0: ")][0].split()[1])
+    drv = D.DPGOStar(D.read_g2o(path), 4)
+    f_gt = 2 * drv.evaluate_f(Xgt)
+    assert f0 < 3 * f_gt                    # the chordal relaxation starts near the ground-truth cost
