@@ -40,7 +40,7 @@ __device__ __forceinline__ void jacobi_conj(double &S11, double &S21, double &S3
                                             double &S33, double &qs, double &QX, double &QY, double &QZ) {
   const double kTiny = 1.0e-32;
   const double kFourGammaSq = 5.828427124746190;   // sqrt(8) + 3
-  const double kSinPi8 = 0.3826834323650898;       // 0.5 sqrt(2 - sqrt 2)
+  const double kSinPi8 = 0.3826834323650897;       // 0.5 sqrt(2 - sqrt 2) as the reference computes it at run time (traits.cpp:16-17)
   const double kCosPi8 = 0.9238795325112867;       // 0.5 sqrt(2 + sqrt 2)
   double sh = MUL(S21, 0.5);
   double t5 = SUB(S11, S22);
