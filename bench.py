@@ -241,10 +241,11 @@ def run_ours(args):
         "k3_prox": ctr.prox_passes / args.steps, "g00_solves": ctr.solve_calls / args.steps,
         "g00_node_iters": ctr.solve_iters / args.steps,
     }
-    # K2b bytes per pose and CG iteration: sliced-ELLPACK entries (12 B each)
-    # + diagonal twice + 5 vector reads and 2 writes in phase A, 4 reads and 2 writes in phase B
+    # K2b algorithmic bytes per pose and CG iteration: ELLPACK entries (12 B
+    # each, one per intra-node half-edge) + the diagonal in both phases + phase A: read z, p, Ap,
+    # write p, Ap; phase B: read x, p, Ap, z, write x, z  (11 vector streams of 8 d bytes)
     sell_bytes_per_pose = 12.0 * 2 * E_intra / max(NO, 1)
-    b_iter = sell_bytes_per_pose + 16 + 8 * d * (5 + 6)
+    b_iter = sell_bytes_per_pose + 16 + 8 * d * 11
     alg_bytes = {
         "k2_eval": 120 * E_intra + 192 * NO, "k2_grad": 120 * E_intra + 192 * NO,
         "k2_hv": 120 * E_intra + 192 * NO, "k2_g01": 120 * E_intra + 192 * NO,

@@ -35,7 +35,6 @@ namespace mmpgo {
 
 typedef std::vector<int> Mask;
 
-static inline int PBof(const Handle *h) { return (h->d + 1) * h->d; }
 
 static bool any(const Mask &m) {
   for (int v : m) if (v) return true;
@@ -145,7 +144,7 @@ template <int D> struct Drv {
         CK(cudaMemcpyAsync(h->d_active2, mp.data(), sizeof(int) * mp.size(), cudaMemcpyHostToDevice, h->stream));
         ta.active = h->d_active2;
       }
-      ta.rhs = h->rhs_t; ta.xio = xio; ta.warm = warm ? 1 : 0; ta.mode = h->ts_mode;
+      ta.rhs = h->rhs_t; ta.xio = xio; ta.warm = warm ? 1 : 0;
       ta.rec = h->ts_rec; ta.z = h->ts_z;
       ta.partials = h->ts_partials; ta.nstate = h->ts_nstate;
       ta.cnt = h->d_ts_sync; ta.n_nodes = h->A; ta.n_active = 0;
@@ -894,17 +893,11 @@ template <int D> static int profile_pass(Handle *h, int kind, int reps, float *m
       // one cold translation solve on scratch (rhs = whatever recover_t left), fixed iteration count
       const double tol = h->opt.translation_solve_tol; const int mi = h->opt.translation_solve_max_iters;
       if (getenv("MMPGO_TS_ITERS")) { h->opt.translation_solve_tol = 0.0; h->opt.translation_solve_max_iters = atoi(getenv("MMPGO_TS_ITERS")); }
-      h->ts_mode = getenv("MMPGO_TS_MODE") ? atoi(getenv("MMPGO_TS_MODE")) : 0;
       h->ts_grid_override = getenv("MMPGO_TS_GRID") ? atoi(getenv("MMPGO_TS_GRID")) : 0;
       int rc = Dr::solve_t(h, h->xprop, allm, false);
-      h->opt.translation_solve_tol = tol; h->opt.translation_solve_max_iters = mi; h->ts_mode = 0; h->ts_grid_override = 0;
+      h->opt.translation_solve_tol = tol; h->opt.translation_solve_max_iters = mi; h->ts_grid_override = 0;
       if (rc) return rc;
       h->ctr.launches--;
-    } else if (kind == 5) {
-      SolveArgs sa;
-      sa.rowptr = h->d_rowptr; sa.col = h->d_col; sa.a00 = h->d_a00; sa.d00 = h->d_d00;
-      sa.node_tile_begin = h->d_node_tb; sa.node_tile_end = h->d_node_te; sa.state = h->d_pcg_state; sa.tol2 = 0;
-      launch_pcg_spmv<D>(tl, sa, h->pp, h->pap, h->d_partials, 0, h->stream);
     } else {
       set_error("unknown kernel kind");
       return MMPGO_ERR_ARG;
@@ -933,30 +926,16 @@ int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg) {
 // reserved[0] = pose-iterations, the unit of its byte accounting)
 int driver_sync_counters(Handle *h) {
   if (!h->graph_set) return 0;
-  unsigned long long st[16] = {0};
+  unsigned long long st[2] = {0, 0};
   CK(cudaMemcpyAsync(st, h->d_ts_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->ctr.solve_iters = (int64_t)st[0];
   h->ctr.reserved[0] = (int64_t)st[1];
-  for (int q = 2; q < 7; ++q) h->ctr.reserved[q - 1] = (int64_t)st[q];
-  if (getenv("MMPGO_TS_TRACE")) {
-    std::vector<double> ns((size_t)h->A * 8);
-    CK(cudaMemcpy(ns.data(), h->ts_nstate, ns.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int n = 0; n < std::min(h->A, 6); ++n)
-      fprintf(stderr, "node %d: rz %.3e bb %.3e alpha %.3e beta %.3e iters %.0f rr %.3e\n", n, ns[n*8], ns[n*8+1], ns[n*8+2], ns[n*8+3], ns[n*8+4], ns[n*8+5]);
-  }
-  if (getenv("MMPGO_TS_TRACE")) fprintf(stderr, "scheduler cycles: flag scan %llu, segments %llu, dispatch %llu (selection %llu, issue %llu)\n", st[7], st[8], st[9], st[10], st[11]);
-  if (getenv("MMPGO_TS_TRACE")) {
-    std::vector<unsigned long long> tr(800, 0);
-    CK(cudaMemcpy(tr.data(), h->d_ts_stats + 16, 784 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (int q = 0; q < 0; ++q)
-      fprintf(stderr, "dispatch %d t=%llu k=%d round=%d\n", q, tr[2 * q], (int)(tr[2 * q + 1] >> 32), (int)(tr[2 * q + 1] & 0x3fffffff));
-  }
   return 0;
 }
 int driver_reset_solve_stats(Handle *h) {
   if (!h->graph_set) return 0;
-  CK(cudaMemsetAsync(h->d_ts_stats, 0, 808 * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->d_ts_stats, 0, 2 * sizeof(unsigned long long), h->stream));
   return 0;
 }
 

@@ -90,8 +90,7 @@ struct Handle {
   double *gex = nullptr, *Dfex = nullptr, *nab = nullptr, *grad = nullptr;
   double *cg_s = nullptr, *cg_r = nullptr, *cg_v = nullptr, *cg_p = nullptr, *cg_Hp = nullptr;
   // compact (NO x D)
-  double *rhs_t = nullptr, *tsol = nullptr, *pr = nullptr, *pz = nullptr, *pp = nullptr, *pap = nullptr;
-  double *d_pcg_state = nullptr;
+  double *rhs_t = nullptr;
   // persistent translation solve (mmpgo_tsolve.cu)
   int *d_sell_ptr = nullptr, *d_ts_sync = nullptr;
   unsigned char *d_sell_pack = nullptr;
@@ -100,7 +99,7 @@ struct Handle {
   double *ts_rec = nullptr, *ts_z = nullptr, *ts_z_base = nullptr;
   double *ts_partials = nullptr, *ts_nstate = nullptr;
   unsigned long long *d_ts_stats = nullptr;
-  int ts_max_grid = 0, ts_mode = 0, ts_grid_override = 0;
+  int ts_max_grid = 0, ts_grid_override = 0;
   int64_t sell_entries = 0;
   // per half-edge
   double *w_cur = nullptr, *w_prev = nullptr, *w_tmp = nullptr;

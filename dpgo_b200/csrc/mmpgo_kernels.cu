@@ -963,146 +963,6 @@ __global__ void __launch_bounds__(256) k_dense_solve(const int *node_off, const 
   }
 }
 
-// PCG path (Jacobi-preconditioned CG on the scalar Laplacian, d right-hand sides
-// treated as one system with the Frobenius inner product).
-template <int D>
-__global__ void __launch_bounds__(TILE *D) k_pcg_spmv(Tiles tl, SolveArgs sa, const double *v, double *av,
-                                                      const double *rhs, double *r, double *z, double *pdir,
-                                                      double *partials, int init) {
-  // init: r = rhs - A v ; z = r / d ; p = z ; s0 = r.z ; s1 = rhs.rhs ; s2 = r.r
-  // else: av = A v ; s0 = v.av
-  const int tile = blockIdx.x;
-  const int node = tl.node[tile];
-  if (tl.active && !tl.active[node]) return;
-  const int pl = threadIdx.x / D, c = threadIdx.x % D;
-  const int p = tl.start[tile] + pl;
-  const bool valid = pl < tl.cnt[tile];
-  double sc[3] = {0, 0, 0};
-  if (valid) {
-    double acc = sa.d00[p] * v[(size_t)p * D + c];
-    const int e0 = sa.rowptr[p], e1 = sa.rowptr[p + 1];
-    for (int e = e0; e < e1; ++e) acc = fma(__ldg(sa.a00 + e), v[(size_t)__ldg(sa.col + e) * D + c], acc);
-    if (init) {
-      const double b = rhs[(size_t)p * D + c];
-      const double rv = b - acc;
-      const double zv = rv / sa.d00[p];
-      r[(size_t)p * D + c] = rv;
-      z[(size_t)p * D + c] = zv;
-      pdir[(size_t)p * D + c] = zv;
-      sc[0] = rv * zv;
-      sc[1] = b * b;
-      sc[2] = rv * rv;
-    } else {
-      av[(size_t)p * D + c] = acc;
-      sc[0] = v[(size_t)p * D + c] * acc;
-    }
-  }
-  block_reduce_store<3, TILE * D>(sc, partials + (size_t)tile * NS);
-}
-
-// state slots: 0 rz, 1 pAp, 2 alpha, 3 beta, 4 rr, 5 bb, 6 active, 7 iters
-__global__ void k_pcg_scalar(int num_nodes, const double *node_scal, double *state, int stage, double tol2) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= num_nodes) return;
-  double *st = state + (size_t)a * 8;
-  const double *ns = node_scal + (size_t)a * NS;
-  if (stage == 0) {  // after init
-    st[0] = ns[0]; st[5] = ns[1]; st[4] = ns[2]; st[2] = 0.0; st[3] = 0.0; st[7] = 0.0;
-    st[6] = (ns[0] > 0.0 && ns[2] > tol2 * ns[1]) ? 1.0 : 0.0;
-  } else if (stage == 1) {  // after spmv: alpha
-    st[1] = ns[0];
-    st[2] = (st[6] != 0.0 && ns[0] > 0.0) ? st[0] / ns[0] : 0.0;
-  } else {  // after update: beta, convergence
-    if (st[6] != 0.0) {
-      const double rz_new = ns[0];
-      st[3] = rz_new / st[0];
-      st[0] = rz_new;
-      st[4] = ns[1];
-      st[7] += 1.0;
-      if (ns[1] <= tol2 * st[5] || !(rz_new > 0.0)) { st[6] = 0.0; }
-    } else {
-      st[3] = 0.0;
-      st[2] = 0.0;
-    }
-  }
-}
-
-template <int D>
-__global__ void __launch_bounds__(TILE *D) k_pcg_update(Tiles tl, SolveArgs sa, double *x, double *r, double *z,
-                                                        const double *pdir, const double *ap, double *partials) {
-  const int tile = blockIdx.x;
-  const int node = tl.node[tile];
-  if (tl.active && !tl.active[node]) return;
-  const int pl = threadIdx.x / D, c = threadIdx.x % D;
-  const int p = tl.start[tile] + pl;
-  const bool valid = pl < tl.cnt[tile];
-  const double al = sa.state[(size_t)node * 8 + 2];
-  double sc[2] = {0, 0};
-  if (valid) {
-    const size_t i = (size_t)p * D + c;
-    x[i] = x[i] + al * pdir[i];
-    const double rv = r[i] - al * ap[i];
-    const double zv = rv / sa.d00[p];
-    r[i] = rv;
-    z[i] = zv;
-    sc[0] = rv * zv;
-    sc[1] = rv * rv;
-  }
-  block_reduce_store<2, TILE * D>(sc, partials + (size_t)tile * NS);
-}
-template <int D>
-__global__ void __launch_bounds__(TILE *D) k_pcg_dir(Tiles tl, SolveArgs sa, const double *z, double *pdir) {
-  const int tile = blockIdx.x;
-  const int node = tl.node[tile];
-  if (tl.active && !tl.active[node]) return;
-  const int pl = threadIdx.x / D, c = threadIdx.x % D;
-  const int p = tl.start[tile] + pl;
-  if (pl >= tl.cnt[tile]) return;
-  const double be = sa.state[(size_t)node * 8 + 3];
-  const double on = sa.state[(size_t)node * 8 + 6];
-  const size_t i = (size_t)p * D + c;
-  if (on != 0.0) pdir[i] = z[i] + be * pdir[i];
-}
-
-template <int D>
-void launch_pcg_init(const Tiles &tl, const SolveArgs &sa, const double *rhs, const double *x0, double *x,
-                     double *r, double *z, double *p, double *partials, cudaStream_t s) {
-  (void)x;
-  k_pcg_spmv<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, x0, nullptr, rhs, r, z, p, partials, 1);
-}
-template <int D>
-void launch_pcg_spmv(const Tiles &tl, const SolveArgs &sa, const double *p, double *ap, double *partials,
-                     int first, cudaStream_t s) {
-  (void)first;
-  k_pcg_spmv<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, p, ap, nullptr, nullptr, nullptr, nullptr, partials, 0);
-}
-template <int D>
-void launch_pcg_update(const Tiles &tl, const SolveArgs &sa, double *x, double *r, double *z, const double *p,
-                       const double *ap, double *partials, cudaStream_t s) {
-  k_pcg_update<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, x, r, z, p, ap, partials);
-}
-template <int D>
-void launch_pcg_dir(const Tiles &tl, const SolveArgs &sa, const double *z, double *p, double *partials,
-                    cudaStream_t s) {
-  (void)partials;
-  k_pcg_dir<D><<<tl.n_tiles, TILE * D, 0, s>>>(tl, sa, z, p);
-}
-void launch_pcg_scalar(int num_nodes, const double *node_scal, double *state, int stage, double tol2,
-                       cudaStream_t s) {
-  k_pcg_scalar<<<(num_nodes + 127) / 128, 128, 0, s>>>(num_nodes, node_scal, state, stage, tol2);
-}
-#define MMPGO_INST_PCG(D)                                                                                        \
-  template void launch_pcg_init<D>(const Tiles &, const SolveArgs &, const double *, const double *, double *,  \
-                                   double *, double *, double *, double *, cudaStream_t);                       \
-  template void launch_pcg_spmv<D>(const Tiles &, const SolveArgs &, const double *, double *, double *, int,   \
-                                   cudaStream_t);                                                               \
-  template void launch_pcg_update<D>(const Tiles &, const SolveArgs &, double *, double *, double *,            \
-                                     const double *, const double *, double *, cudaStream_t);                   \
-  template void launch_pcg_dir<D>(const Tiles &, const SolveArgs &, const double *, double *, double *,         \
-                                  cudaStream_t);
-MMPGO_INST_PCG(2)
-MMPGO_INST_PCG(3)
-
 template <int D>
 void launch_dense_solve(int num_nodes, const int *node_off, const long long *dense_off, const int *node_active,
                         const double *ginv, const double *rhs, double *xout, int max_n0, cudaStream_t s) {

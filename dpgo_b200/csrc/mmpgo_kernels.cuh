@@ -129,20 +129,12 @@ struct VecArgs {
 };
 
 // ---- K2b: translation solve --------------------------------------------------
-struct SolveArgs {
-  const int *rowptr, *col;  // G00 pattern (= intra pattern)
-  const double *a00;        // off-diagonal values (-tau)
-  const double *d00;        // diagonal of G00
-  const int *node_tile_begin, *node_tile_end;
-  double *state;            // [num_nodes][8]: rz, pAp, alpha, beta, rr, bb, active, iters
-  double tol2;
-};
-
 // persistent per-node Jacobi-PCG (mmpgo_tsolve.cu).  A CTA tile is <= CTILE consecutive poses of
 // one node; warp wi of the CTA owns its poses [32 wi, 32 wi + 32).  Solver vectors are laid out
 // [cta tile][warp][D][32]; slice index sl = 8 * cta tile + warp.
 constexpr int CTILE = 128;        // poses per CTA tile of the translation solve
 constexpr int TS_WPT = CTILE / 32;  // 32-pose warp slices per CTA tile
+constexpr int TS_NGRP = 3;        // consumer groups of the persistent solve kernel
 constexpr int TS_HALO = 2;        // neighbour tiles staged on each side for the z gathers
 constexpr int TS_MAXCT = 128;     // CTA tiles one persistent CTA can own
 struct TSolveArgs {
@@ -159,7 +151,6 @@ struct TSolveArgs {
   const double *rhs;              // [NO][D]
   double *xio;                    // pose blocks: t rows in (warm start: u0 = -t) and out (t = -u)
   int warm;
-  int mode;                       // 0 normal; experiments: 1 no arithmetic sweep, 2 no node arrivals
   double *rec;                    // per CTA tile one record {x, p, Ap}[TS_WPT][D][32] + diag[CTILE] (padded with 1)
   double *z;                      // [TS_WPT n_ct][D][32], padded by TS_HALO tiles at both ends; r is kept as z = r / diag
   double *partials;               // [n_ct][4]
@@ -196,22 +187,11 @@ template <int D> void launch_edge_objective(int64_t n_edges, const EdgeRec *rec,
                                             int *n_blocks_out, cudaStream_t s);
 void launch_sum_blocks(int n_blocks, const double *block_partials, double *out, cudaStream_t s);
 
-// translation solve building blocks
+// translation solve, dense path (small nodes): t = -G00^{-1} rhs
 template <int D> void launch_dense_solve(int num_nodes, const int *node_off, const long long *node_dense_off,
                                          const int *node_active, const double *ginv, const double *rhs,
                                          double *xout /*pose blocks, row 0 = -Ginv rhs*/, int max_n0,
                                          cudaStream_t s);
-void launch_pcg_scalar(int num_nodes, const double *node_scal, double *state, int stage, double tol2,
-                       cudaStream_t s);
-template <int D> void launch_pcg_init(const Tiles &tl, const SolveArgs &sa, const double *rhs, const double *x0,
-                                      double *x, double *r, double *z, double *p, double *partials, cudaStream_t s);
-template <int D> void launch_pcg_spmv(const Tiles &tl, const SolveArgs &sa, const double *p, double *ap,
-                                      double *partials, int first, cudaStream_t s);
-template <int D> void launch_pcg_update(const Tiles &tl, const SolveArgs &sa, double *x, double *r, double *z,
-                                        const double *p, const double *ap, double *partials, cudaStream_t s);
-template <int D> void launch_pcg_dir(const Tiles &tl, const SolveArgs &sa, const double *z, double *p,
-                                     double *partials, cudaStream_t s);
-
 // halo pack / unpack (DPGOHash::receive wire format, DPGOHash.cpp:45-82)
 template <int D> void launch_gather_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);
 template <int D> void launch_scatter_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);

@@ -463,9 +463,8 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   double **ov[] = {&h->g[0], &h->g[1], &h->Df[0], &h->Df[1], &h->gex, &h->Dfex, &h->nab, &h->grad,
                    &h->cg_s, &h->cg_r, &h->cg_v, &h->cg_p, &h->cg_Hp};
   for (auto q : ov) if ((rc = dalloc(h, q, no))) return rc;
-  double **cv[] = {&h->rhs_t, &h->tsol, &h->pr, &h->pz, &h->pp, &h->pap};
+  double **cv[] = {&h->rhs_t};
   for (auto q : cv) if ((rc = dalloc(h, q, nc))) return rc;
-  if ((rc = dalloc(h, &h->d_pcg_state, (size_t)A * 8))) return rc;
   {
     const size_t nv = (size_t)h->n_ctiles * CTILE * d;
     // z is staged with a TS_HALO-tile halo on both sides: pad the array accordingly at each end
@@ -474,7 +473,7 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4))) return rc;
     if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_sync, (size_t)2 * A + 8))) return rc;
-    if ((rc = dalloc(h, &h->d_ts_stats, (size_t)8 + 800))) return rc;
+    if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
     h->ts_max_grid = d == 2 ? tsolve_max_grid<2>(h->opt.device) : tsolve_max_grid<3>(h->opt.device);
     if (h->ts_max_grid <= 0) { set_error("occupancy query for the translation solve failed"); return MMPGO_ERR_CUDA; }
   }

@@ -99,7 +99,7 @@ template <int D> struct TSCfg {
   static constexpr int VEC = CTILE * D;          // doubles of one solver vector per CTA tile
   static constexpr int RL = 3 * VEC + CTILE;     // doubles of one tile record {x, p, Ap, diag}
   static constexpr int WPT = TS_WPT;             // consumer warps per tile (one pose per thread)
-  static constexpr int NGRP = 2;                 // consumer groups (tiles in arithmetic at the same time)
+  static constexpr int NGRP = TS_NGRP;           // consumer groups (tiles in arithmetic at the same time)
   static constexpr int HV = 2 * TS_HALO + 1;     // tiles of z staged for phase A (own tile in the middle)
   static constexpr int SELL_CAP = 40;            // 32-entry ELLPACK rows of one CTA tile that fit a stage
   static constexpr int NSTAGE = 5;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void consumer_barrier(int group) {
 // tile flags (shared memory): scheduler 0 -> 1 (dispatched), consumers 1 -> 2 (phase executed),
 // scheduler 2 -> 0 (arrived on the node)
 template <int D>
-__global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
+__global__ void __launch_bounds__(TS_NGRP * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
   typedef TSCfg<D> C;
   constexpr int PB = (D + 1) * D;
   constexpr int NST = C::NSTAGE;
@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
   const int wi = wg % WPT, grp = wg / WPT;                    // consumer: warp inside its group, group
   int *epoch = a.cnt + a.n_nodes;            // [nodes] next phase the node's tiles may run (| DONE_BIT)
   extern __shared__ __align__(128) unsigned char dyn[];
-  // full barriers: one per use modulo 2 NST, so that a barrier is always waited on by the same
-  // consumer group (NST is odd: with one barrier per stage the groups would alternate on it, and a
-  // group running ahead could mistake the other group's unfinished phase for its own)
-  __shared__ uint64_t full[2 * NST], empty[NST];
+  // full barriers: one per use modulo NGRP * NST, so that a barrier is always waited on by the same
+  // consumer group (with one barrier per stage the groups would alternate on it, and a group
+  // running ahead could mistake another group's unfinished phase for its own)
+  __shared__ uint64_t full[C::NGRP * NST], empty[NST];
   __shared__ int m_node[TS_MAXCT], m_start[TS_MAXCT], m_cnt[TS_MAXCT], m_sell[TS_MAXCT][TS_WPT + 1];
   __shared__ int t_round[TS_MAXCT];          // next phase of the tile; -1 = retired           (scheduler)
   __shared__ int t_flag[TS_MAXCT];
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
   __shared__ int returned_s;                  // tiles the consumers have handed back (monotone)
   __shared__ int sg_done[TS_MAXCT];           // per segment: tiles of the current phase handed back
   __shared__ double d_coef[NST];
-  __shared__ double red[2][2][TS_WPT][3];
+  __shared__ double red[TS_NGRP][2][TS_WPT][3];
   __shared__ int n_live_s;
 
   // CTA tiles are dealt to the CTAs in chunks of `chunk` consecutive tiles, round-robin: a node's
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
 #pragma unroll
     for (int q = 0; q < NST; ++q) mbar_init(&empty[q], 1);
 #pragma unroll
-    for (int q = 0; q < 2 * NST; ++q) mbar_init(&full[q], 1);
+    for (int q = 0; q < C::NGRP * NST; ++q) mbar_init(&full[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     n_live_s = 0;
     returned_s = 0;
@@ -319,11 +319,9 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
     int stage = 0;
     uint32_t pe = 0;                                   // parity bits of the empty barriers
     int uses = 0;                                      // stages handed out so far
-    unsigned long long dbg_loops = 0, dbg_wait_empty = 0, dbg_t0 = clock64(), dbg_c5 = 0;
     int cur = -1, cur_next = 0, cur_n = 0, cur_k0 = 0, cur_kind = 0;   // segment being handed out (warp-uniform)
     double cur_coef = 0.0;
     while (true) {
-      ++dbg_loops;
       int in_flight = uses - ld_acquire_cta_shared(&returned_s);
       if (in_flight == 0 && ld_acquire_cta_shared(&all_done_s)) break;
       bool progress = false;
@@ -353,11 +351,10 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
           __syncwarp();
         }
         progress = true;
-        const long long tS = clock64();
         const int kk = cur_k0 + cur_next, kd = cur_kind;
         ++cur_next;
         if (lane == 0) {
-          if (uses >= NST) { const long long w0 = clock64(); mbar_wait(&empty[stage], (pe >> stage) & 1u); dbg_wait_empty += clock64() - w0; }
+          if (uses >= NST) mbar_wait(&empty[stage], (pe >> stage) & 1u);
           d_k[stage] = kk; d_kind[stage] = kd; d_coef[stage] = cur_coef; d_seg[stage] = cur;
           if (kd == 1 || kd == 2) {
             const int ct = tile_of(kk);
@@ -367,21 +364,20 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
             if (kd == 1) {
               const int r0 = m_sell[kk][0], rows = m_sell[kk][WPT] - r0;
               const bool sell_staged = rows <= C::SELL_CAP && rows > 0;
-              mbar_expect_tx(&full[uses % (2 * NST)], (C::HV * C::VEC + 2 * C::VEC + CTILE) * 8 + (sell_staged ? rows * 384 : 0));
-              bulk_g2s(sb, a.z + v0 - TS_HALO * C::VEC, C::HV * C::VEC * 8, &full[uses % (2 * NST)]);   // z is padded by the halo
-              bulk_g2s(sb + C::OFF_R, rc + C::VEC, (2 * C::VEC + CTILE) * 8, &full[uses % (2 * NST)]);
-              if (sell_staged) bulk_g2s(sb + C::OFF_S, a.sell_pack + (size_t)r0 * 384, rows * 384, &full[uses % (2 * NST)]);
+              mbar_expect_tx(&full[uses % (C::NGRP * NST)], (C::HV * C::VEC + 2 * C::VEC + CTILE) * 8 + (sell_staged ? rows * 384 : 0));
+              bulk_g2s(sb, a.z + v0 - TS_HALO * C::VEC, C::HV * C::VEC * 8, &full[uses % (C::NGRP * NST)]);   // z is padded by the halo
+              bulk_g2s(sb + C::OFF_R, rc + C::VEC, (2 * C::VEC + CTILE) * 8, &full[uses % (C::NGRP * NST)]);
+              if (sell_staged) bulk_g2s(sb + C::OFF_S, a.sell_pack + (size_t)r0 * 384, rows * 384, &full[uses % (C::NGRP * NST)]);
             } else {
-              mbar_expect_tx(&full[uses % (2 * NST)], (C::VEC + C::RL) * 8);
-              bulk_g2s(sb, a.z + v0, C::VEC * 8, &full[uses % (2 * NST)]);
-              bulk_g2s(sb + C::OFF_R, rc, C::RL * 8, &full[uses % (2 * NST)]);
+              mbar_expect_tx(&full[uses % (C::NGRP * NST)], (C::VEC + C::RL) * 8);
+              bulk_g2s(sb, a.z + v0, C::VEC * 8, &full[uses % (C::NGRP * NST)]);
+              bulk_g2s(sb + C::OFF_R, rc, C::RL * 8, &full[uses % (C::NGRP * NST)]);
             }
           } else {
-            mbar_arrive(&full[uses % (2 * NST)]);                  // no staged data: init / publish use direct loads
+            mbar_arrive(&full[uses % (C::NGRP * NST)]);                  // no staged data: init / publish use direct loads
           }
         }
         __syncwarp();
-        dbg_c5 += clock64() - tS;
         if (uses >= NST) pe ^= 1u << stage;
         ++uses;
         ++in_flight;
@@ -394,14 +390,10 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
       for (int q = 0; q < C::NGRP; ++q) {                // one stop descriptor per consumer group
         if (uses >= NST) mbar_wait(&empty[stage], (pe >> stage) & 1u);
         d_kind[stage] = -1;
-        mbar_arrive(&full[uses % (2 * NST)]);
+        mbar_arrive(&full[uses % (C::NGRP * NST)]);
         if (uses >= NST) pe ^= 1u << stage;
         ++uses;
         stage = stage + 1 == NST ? 0 : stage + 1;
-      }
-      if (a.stats && blockIdx.x == 7) {
-        a.stats[2] = dbg_loops; a.stats[3] = dbg_wait_empty; a.stats[4] = clock64() - dbg_t0; a.stats[5] = uses;
-        a.stats[11] = dbg_c5;
       }
     }
     return;
@@ -411,14 +403,11 @@ __global__ void __launch_bounds__(2 * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
   // the two groups take the ring's uses alternately, so that one group's waits (far gathers,
   // barriers) overlap the other group's arithmetic
   int tick = 0;
-  unsigned long long dbg_wait_full = 0;
-  for (int use = grp;; use += 2) {
+  for (int use = grp;; use += C::NGRP) {
     const int stage = use % NST;
-    const long long w0 = clock64();
-    mbar_wait(&full[use % (2 * NST)], (unsigned)(use / (2 * NST)) & 1u);
-    dbg_wait_full += clock64() - w0;
+    mbar_wait(&full[use % (C::NGRP * NST)], (unsigned)(use / (C::NGRP * NST)) & 1u);
     const int kd = d_kind[stage];
-    if (kd < 0) { if (a.stats && blockIdx.x == 7 && threadIdx.x == 0) a.stats[6] = dbg_wait_full; break; }
+    if (kd < 0) break;
     const int k = d_k[stage], ct = tile_of(k);
     const double coef = d_coef[stage];
     const bool valid = 32 * wi + lane < m_cnt[k];

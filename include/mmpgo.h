@@ -193,7 +193,8 @@ int mmpgo_project_to_sodn(int32_t d, int64_t n, const double *A, double *U, int3
 /* Measurement hook: average device time (CUDA events on the handle's stream) of
  * `reps` back-to-back launches of one hot kernel on the current iterate.
  * kind: 0 K2 evaluate, 1 K2 gradient, 2 K1 inter-edge pass, 3 K3 fused proximal,
- * 4 edge-parallel objective, 5 G00 SpMV, 6 K2 Hessian-vector, 7 K2 G01 pass. */
+ * 4 edge-parallel objective, 6 K2 Hessian-vector, 7 K2 G01 pass, 8 one cold K2b translation
+ * solve (one persistent launch). */
 int mmpgo_profile_pass(mmpgo_handle h, int32_t kind, int32_t reps, float *ms_avg);
 int mmpgo_get_counters(mmpgo_handle h, mmpgo_counters *out);
 int mmpgo_reset_counters(mmpgo_handle h);

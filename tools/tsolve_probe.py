@@ -17,5 +17,3 @@ for iters in (20,):
         os.environ["MMPGO_TS_ITERS"] = str(iters); os.environ["MMPGO_TS_MODE"] = str(mode); os.environ["MMPGO_TS_GRID"] = str(grid)
         ms = drv.profile_pass("g00_solve", reps)
         print("iters %d grid %d mode %d: %.3f ms/solve  %.1f us/iter" % (iters, grid, mode, ms, 1e3 * ms / iters), flush=True)
-        c = drv.counters()
-        print("  last solve, CTA 7: scheduler loops %d, cycles waiting for a free stage %d, scheduler cycles %d, dispatches %d, consumer cycles waiting for data %d" % tuple(c.reserved[1:6]))
