@@ -194,10 +194,10 @@ template <int D> struct Drv {
   }
 
   static int vec(Handle *h, int op, const Mask &m, const double *a_, const double *b_, double *o1, double *o2,
-                 double *o3, double *o4, const double *y) {
+                 double *o3, double *o4, const double *y, double *o5 = nullptr) {
     Tiles tl; RC(make_tiles(h, m, &tl));
     VecArgs a; std::memset(&a, 0, sizeof(a));
-    a.a = a_; a.b = b_; a.o1 = o1; a.o2 = o2; a.o3 = o3; a.o4 = o4; a.y = y;
+    a.a = a_; a.b = b_; a.o1 = o1; a.o2 = o2; a.o3 = o3; a.o4 = o4; a.o5 = o5; a.y = y;
     a.pinv = h->d_pinv; a.precon = h->opt.preconditioner; a.coef = h->d_coef; a.partials = h->d_partials;
     launch_vec<D>(op, tl, a, h->stream);
     h->ctr.launches++; h->ctr.vector_passes++;
@@ -234,7 +234,7 @@ template <int D> struct Drv {
     std::vector<double> rv(A, 0), sk_M_pk(A, 0), sk_M_2(A, 0), pk_M_2(A, 0), target(A, 0), coef((size_t)A * MAXC, 0.0);
     Mask act = m;
     hMnorm.assign(A, 0.0); inner.assign(A, 0);
-    RC(vec(h, V_CG_INIT, m, h->grad, nullptr, h->cg_s, h->cg_r, h->cg_v, h->cg_p, x));
+    RC(vec(h, V_CG_INIT, m, h->grad, nullptr, h->cg_s, h->cg_r, h->cg_v, h->cg_p, x, h->cg_Hs));
     const double *s; RC(reduce_to_host(h, &s));
     for (int n = 0; n < A; ++n) if (m[n]) {
       rv[n] = s[n * NS];
@@ -280,11 +280,11 @@ template <int D> struct Drv {
       }
       RC(upload_coef(h, coef));
       if (any(fin)) {
-        RC(vec(h, V_CG_FINAL, fin, h->cg_p, nullptr, h->cg_s, nullptr, nullptr, nullptr, nullptr));
+        RC(vec(h, V_CG_FINAL, fin, h->cg_p, h->cg_Hp, h->cg_s, nullptr, nullptr, nullptr, nullptr, h->cg_Hs));
         for (int n = 0; n < A; ++n) if (fin[n]) { act[n] = 0; hMnorm[n] = Delta[n]; }
       }
       if (any(cont)) {
-        RC(vec(h, V_CG_STEP, cont, h->cg_p, h->cg_Hp, h->cg_s, h->cg_r, h->cg_v, nullptr, x));
+        RC(vec(h, V_CG_STEP, cont, h->cg_p, h->cg_Hp, h->cg_s, h->cg_r, h->cg_v, nullptr, x, h->cg_Hs));
         RC(reduce_to_host(h, &s));
         for (int n = 0; n < A; ++n) if (cont[n]) {
           const double alpha = coef[(size_t)n * MAXC + 0];
@@ -347,12 +347,17 @@ template <int D> struct Drv {
       RC(vec(h, V_RETRACT, run, x, h->cg_s, h->xprop, nullptr, nullptr, nullptr, nullptr));
       RC(recover_t(h, h->xprop, g, run));
       RC(eval_G(h, h->xprop, g, run, fprop));
-      // predicted decrease needs grad.h and h.Hess h
+      // predicted decrease needs grad.h and h.Hess h.  H is linear and the step is s = sum alpha_k p_k,
+      // so H s was accumulated from the H p_k of the tCG iterations (cg_Hs): no further
+      // Hessian-vector product (the reference recomputes it, TNT.h:514-515; same value up to rounding)
       RC(vec(h, V_DOTS, run, h->grad, h->cg_s, nullptr, nullptr, nullptr, nullptr, nullptr));
       const double *s; RC(reduce_to_host(h, &s));
       std::vector<double> gh(A, 0);
-      for (int n = 0; n < A; ++n) gh[n] = s[n * NS];
-      RC(hess_vec(h, x, h->cg_s, h->cg_Hp, run, sHs, HsHs, ss));
+      ss.assign(A, 0.0); sHs.assign(A, 0.0);
+      for (int n = 0; n < A; ++n) { gh[n] = s[n * NS]; ss[n] = s[n * NS + 2]; }
+      RC(vec(h, V_DOTS, run, h->cg_s, h->cg_Hs, nullptr, nullptr, nullptr, nullptr, nullptr));
+      RC(reduce_to_host(h, &s));
+      for (int n = 0; n < A; ++n) sHs[n] = s[n * NS];
       Mask accm(A, 0), requad(A, 0);
       for (int n = 0; n < A; ++n) if (run[n]) {
         h->st[n].tcg_iterations += inner[n];

@@ -725,6 +725,7 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
 #pragma unroll
       for (int k = 0; k < DD; ++k) {
         a.o1[o + k] = 0.0; a.o2[o + k] = r[k]; a.o3[o + k] = v[k]; a.o4[o + k] = -v[k];
+        a.o5[o + k] = 0.0;
         sc[0] += r[k] * v[k];
       }
 #pragma unroll
@@ -736,6 +737,7 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
 #pragma unroll
       for (int k = 0; k < DD; ++k) {
         a.o1[o + k] = a.o1[o + k] + al * a.a[o + k];
+        a.o5[o + k] = a.o5[o + k] + al * a.b[o + k];
         r[k] = a.o2[o + k] + al * a.b[o + k];
         Y[k] = a.y[o + k];
       }
@@ -751,7 +753,10 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
       // o1 = s, a = p; coef[2] = sigma (sign folded in by the host)
       const double sg = cf[2];
 #pragma unroll
-      for (int k = 0; k < DD; ++k) a.o1[o + k] = a.o1[o + k] + sg * a.a[o + k];
+      for (int k = 0; k < DD; ++k) {
+        a.o1[o + k] = a.o1[o + k] + sg * a.a[o + k];
+        a.o5[o + k] = a.o5[o + k] + sg * a.b[o + k];
+      }
     } else if (OP == V_RETRACT) {
       // a = x, b = s; o1 = xprop (rotation rows)
       double M[DD], Yn[DD];

@@ -103,10 +103,10 @@ struct ProxArgs {
 
 // ---- generic per-pose vector ops (tCG / TNT bookkeeping) --------------------
 enum VecOp {
-  V_CG_INIT = 0,   // s=0; r=grad; v=P(r); p=-v;           s0 = r.v, s1 = p.p... (IterativeSolvers.h:204-262)
-  V_CG_STEP = 1,   // s+=a p; r+=a Hp; v=P(r);             s0 = r.v
+  V_CG_INIT = 0,   // s=0; Hs=0; r=grad; v=P(r); p=-v;     s0 = r.v, s1 = p.p... (IterativeSolvers.h:204-262)
+  V_CG_STEP = 1,   // s+=a p; Hs+=a Hp; r+=a Hp; v=P(r);   s0 = r.v
   V_CG_DIR = 2,    // p = -v + b p
-  V_CG_FINAL = 3,  // s += sigma p  (p optionally negated first)
+  V_CG_FINAL = 3,  // s += sigma p; Hs += sigma Hp  (p optionally negated first)
   V_RETRACT = 4,   // xprop.Y = proj(x.Y + s.Y)                 (DPGOProblem.cpp:127-143)
   V_DOTS = 5,      // s0 = a.b  s1 = a.a  s2 = b.b (rotation rows)
   V_COPY_ROT = 6,  // out.Y = a.Y
@@ -121,6 +121,7 @@ enum VecOp {
 struct VecArgs {
   const double *a, *b, *c;
   double *o1, *o2, *o3, *o4;
+  double *o5;               // tCG: H s, accumulated alongside s (H s = sum alpha_k H p_k)
   const double *y;          // point for tangent projection (pose blocks)
   const double *pinv;       // [NO][d*d] block-Jacobi inverse or [NO][d] Jacobi
   int precon;               // 0 none, 1 jacobi, 2 block jacobi
