@@ -313,7 +313,9 @@ template <int D> struct Drv {
     std::vector<double> gnorm(A, 0), pgnorm(A, 0), Delta(A, 1.0);   // Delta0 = 1, TNT.h:81
     std::vector<int> it(A, 0), acc(A, 0);
     Mask run = m;
-    RC(eval_G(h, x, g, m, fx));
+    // the quadratic model pass (reduced gradient) also yields the surrogate value G(x): one pass
+    // instead of evaluate_G + gradient (TNT.h:369-382)
+    fx.assign(A, 0.0);
     auto quad_model = [&](const Mask &mm) -> int {
       Tiles tl; RC(make_tiles(h, mm, &tl));
       GPassArgs a = gargs(h);
@@ -321,7 +323,7 @@ template <int D> struct Drv {
       launch_gpass<D>(G_REDGRAD, tl, a, h->stream);
       h->ctr.launches++; h->ctr.intra_passes++;
       const double *s; RC(reduce_to_host(h, &s));
-      for (int n = 0; n < A; ++n) if (mm[n]) gnorm[n] = std::sqrt(s[n * NS]);
+      for (int n = 0; n < A; ++n) if (mm[n]) { gnorm[n] = std::sqrt(s[n * NS]); fx[n] = s[n * NS + 1]; }
       if (o.preconditioner != MMPGO_PRECON_NONE) {
         RC(vec(h, V_PRECOND, mm, h->grad, nullptr, nullptr, nullptr, nullptr, nullptr, x));
         RC(reduce_to_host(h, &s));
@@ -657,7 +659,7 @@ template <int D> struct Drv {
   static int edge_objective(Handle *h, double *x, double *f, bool exchange = true) {
     if (exchange) RC(halo_exchange(h, x));
     int nb = 0;
-    launch_edge_objective<D>(h->n_edges_owned, h->d_erec, x, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
+    launch_edge_objective<D>(h->n_edges_owned, h->d_eidx, h->d_eval, x, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
                              &nb, h->stream);
     launch_sum_blocks(nb, h->d_block_partials, h->d_scalar, h->stream);
     h->ctr.launches += 2; h->ctr.inter_passes++;
@@ -892,7 +894,7 @@ template <int D> static int profile_pass(Handle *h, int kind, int reps, float *m
       launch_prox<D>(tl, a, h->stream);
     } else if (kind == 4) {
       int nb = 0;
-      launch_edge_objective<D>(h->n_edges_owned, h->d_erec, Xk, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
+      launch_edge_objective<D>(h->n_edges_owned, h->d_eidx, h->d_eval, Xk, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
                                &nb, h->stream);
     } else if (kind == 8) {
       // one cold translation solve on scratch (rhs = whatever recover_t left), fixed iteration count

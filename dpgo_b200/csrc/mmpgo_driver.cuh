@@ -72,7 +72,8 @@ struct Handle {
   double *d_a00 = nullptr, *d_d00 = nullptr;
   int *d_xrowptr = nullptr;
   InterRec *d_xrec = nullptr;
-  EdgeRec *d_erec = nullptr;
+  int *d_eidx = nullptr;              // owned edges, struct-of-arrays: i, j, inter flag
+  double *d_eval = nullptr;           // tau, kappa, t[3], R[9] per owned edge, field-major
   double *d_ginv = nullptr;
   long long *d_dense_off = nullptr;
   int max_dense_n0 = 0;

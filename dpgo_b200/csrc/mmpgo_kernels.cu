@@ -82,7 +82,7 @@ k_gpass(Tiles tl, GPassArgs a) {
   // which input rows participate: G_RHS_T uses rotation rows only (G01)
   constexpr int K0 = (MODE == G_RHS_T) ? 1 : 0;
   const bool row_on = (MODE == G_RHS_T) ? (row == 0)
-                    : (MODE == G_REDGRAD || MODE == G_HV) ? (row >= 1) : true;
+                    : (MODE == G_HV) ? (row >= 1) : true;
 
   double acc[D];
 #pragma unroll
@@ -171,12 +171,17 @@ k_gpass(Tiles tl, GPassArgs a) {
     return;
   }
   if (MODE == G_REDGRAD) {
-    if (valid && row >= 1) {
+    // all rows of G x are formed, so the surrogate value s1 = sum x.(g + 1/2 G x) comes for free
+    if (valid) {
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        const double v = a.g[(size_t)p * PB + row * D + c] + acc[c];
-        a.out[(size_t)p * PB + row * D + c] = v;
-        sV[pl][row * D + c] = v;
+        const double gv = a.g[(size_t)p * PB + row * D + c];
+        sc[1] += xp[row * D + c] * (gv + 0.5 * acc[c]);
+        if (row >= 1) {
+          const double v = gv + acc[c];
+          a.out[(size_t)p * PB + row * D + c] = v;
+          sV[pl][row * D + c] = v;
+        }
       }
     }
     __syncthreads();
@@ -189,7 +194,7 @@ k_gpass(Tiles tl, GPassArgs a) {
         sc[0] += pr[c] * pr[c];
       }
     }
-    block_reduce_store<1, NT>(reinterpret_cast<double(&)[1]>(sc), a.partials + (size_t)tile * NS);
+    block_reduce_store<2, NT>(reinterpret_cast<double(&)[2]>(sc), a.partials + (size_t)tile * NS);
     return;
   }
   if (MODE == G_HV) {
@@ -847,21 +852,29 @@ void launch_reduce(int num_nodes, const int *tb, const int *te, const double *pa
 // =============================================================================
 // edge-parallel global objective  (DPGOStar::evaluate_f, DPGOStar.cpp:713-761)
 // =============================================================================
+// Edge data are struct-of-arrays: field f of edge e at val[f * n + e], f = tau, kappa, t[0..2],
+// R[0..8] (row-major); idx[0..2][n] = i, j, inter flag.  Every load is coalesced.
 template <int D>
-__global__ void __launch_bounds__(256) k_edge_objective(int64_t n, const EdgeRec *rec, const double *x, int loss,
-                                                        double loss_reg, double *block_partials) {
+__global__ void __launch_bounds__(256) k_edge_objective(int64_t n, const int *idx, const double *val, const double *x,
+                                                        int loss, double loss_reg, double *block_partials) {
   constexpr int PB = Dim<D>::PB;
   double sc[1] = {0.0};
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const EdgeRec *r = rec + e;
-    const double *xi = x + (size_t)r->i * PB, *xj = x + (size_t)r->j * PB;
-    const double tau = r->tau, kap = r->kappa;
+    const int pi = __ldg(idx + e), pj = __ldg(idx + n + e), inter = __ldg(idx + 2 * n + e);
+    const double tau = __ldg(val + e), kap = __ldg(val + n + e);
+    double t[D], R[D * D], xi[PB], xj[PB];
+#pragma unroll
+    for (int k = 0; k < D; ++k) t[k] = __ldg(val + (2 + k) * n + e);
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) R[k] = __ldg(val + (5 + k) * n + e);
+#pragma unroll
+    for (int k = 0; k < PB; ++k) { xi[k] = x[(size_t)pi * PB + k]; xj[k] = x[(size_t)pj * PB + k]; }
     double et = 0.0, er = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       double s = xi[k] - xj[k];
 #pragma unroll
-      for (int cc = 0; cc < D; ++cc) s += r->t[cc] * xi[(1 + cc) * D + k];
+      for (int cc = 0; cc < D; ++cc) s += t[cc] * xi[(1 + cc) * D + k];
       et += s * s;
     }
     if (loss == 0) {
@@ -873,7 +886,7 @@ __global__ void __launch_bounds__(256) k_edge_objective(int64_t n, const EdgeRec
         for (int k = 0; k < D; ++k) {
           double s = 0.0;
 #pragma unroll
-          for (int cc = 0; cc < D; ++cc) s += r->R[cc * D + rr] * xi[(1 + cc) * D + k];
+          for (int cc = 0; cc < D; ++cc) s += R[cc * D + rr] * xi[(1 + cc) * D + k];
           cr += s * xj[(1 + rr) * D + k];
           ni += xi[(1 + rr) * D + k] * xi[(1 + rr) * D + k];
           nj += xj[(1 + rr) * D + k] * xj[(1 + rr) * D + k];
@@ -887,11 +900,11 @@ __global__ void __launch_bounds__(256) k_edge_objective(int64_t n, const EdgeRec
         for (int k = 0; k < D; ++k) {
           double s = -xj[(1 + rr) * D + k];
 #pragma unroll
-          for (int cc = 0; cc < D; ++cc) s += r->R[cc * D + rr] * xi[(1 + cc) * D + k];
+          for (int cc = 0; cc < D; ++cc) s += R[cc * D + rr] * xi[(1 + cc) * D + k];
           er += s * s;
         }
       const double e2 = tau * et + kap * er;
-      if (r->inter) {
+      if (inter) {
         double rho;
         irls_weight(loss, e2, loss_reg, rho);
         sc[0] += rho;
@@ -915,17 +928,17 @@ __global__ void k_sum_blocks(int n, const double *bp, double *out) {
   if (threadIdx.x == 0) out[0] = sm[0];
 }
 template <int D>
-void launch_edge_objective(int64_t n_edges, const EdgeRec *rec, const double *x, int loss, double loss_reg,
+void launch_edge_objective(int64_t n_edges, const int *idx, const double *val, const double *x, int loss, double loss_reg,
                            double *block_partials, int *n_blocks_out, cudaStream_t s) {
   int nb = (int)((n_edges + 255) / 256);
   if (nb > 148 * 8) nb = 148 * 8;
   if (nb < 1) nb = 1;
   *n_blocks_out = nb;
-  k_edge_objective<D><<<nb, 256, 0, s>>>(n_edges, rec, x, loss, loss_reg, block_partials);
+  k_edge_objective<D><<<nb, 256, 0, s>>>(n_edges, idx, val, x, loss, loss_reg, block_partials);
 }
-template void launch_edge_objective<2>(int64_t, const EdgeRec *, const double *, int, double, double *, int *,
+template void launch_edge_objective<2>(int64_t, const int *, const double *, const double *, int, double, double *, int *,
                                        cudaStream_t);
-template void launch_edge_objective<3>(int64_t, const EdgeRec *, const double *, int, double, double *, int *,
+template void launch_edge_objective<3>(int64_t, const int *, const double *, const double *, int, double, double *, int *,
                                        cudaStream_t);
 void launch_sum_blocks(int n_blocks, const double *bp, double *out, cudaStream_t s) {
   k_sum_blocks<<<1, 256, 0, s>>>(n_blocks, bp, out);

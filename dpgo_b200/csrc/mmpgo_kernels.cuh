@@ -36,7 +36,7 @@ enum GMode {
   G_EVAL = 0,     // s0 = sum x.(g + 1/2 G x)                     (evaluate_G, DPGOProblem.cpp:180-203)
   G_GRAD = 1,     // out = g + G x; s0 as above; s1 = |gradF|^2; s2 = x.Gx; s3 = x.g
   G_RHS_T = 2,    // rhs_t = g_t + G01 Y  (t rows out, Y rows in)   (DPGOProblem.h:289-290)
-  G_REDGRAD = 3,  // nab = g_Y + (G x)_Y; grad = Proj(Y, nab); s0 = |grad|^2 (DPGOProblem.h:370-393)
+  G_REDGRAD = 3,  // nab = g_Y + (G x)_Y; grad = Proj(Y, nab); s0 = |grad|^2 (DPGOProblem.h:370-393); s1 = evaluate_G
   G_HV = 4        // Hp = Proj(Y, (G p)_Y - sym(nab Y^T) p_Y); s0=p.Hp s1=Hp.Hp s2=p.p (DPGOProblem.cpp:552-577)
 };
 
@@ -167,7 +167,7 @@ template <int D> int launch_tsolve(const TSolveArgs &a, int grid, cudaStream_t s
 template <int D> int tsolve_max_grid(int device);
 
 // ---- edge-parallel global objective (AMM-PGO*, DPGOStar.cpp:713-761) ----------
-struct EdgeRec {            // 128 bytes
+struct EdgeRec {            // host-side staging record; the device keeps the fields as struct-of-arrays
   int32_t i, j;             // pose indices (own / halo numbering)
   double tau, kappa;
   double t[3];
@@ -183,7 +183,7 @@ template <int D> void launch_prox(const Tiles &tl, const ProxArgs &a, cudaStream
 template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cudaStream_t s);
 void launch_reduce(int num_nodes, const int *node_tile_begin, const int *node_tile_end,
                    const double *partials, double *node_scal, cudaStream_t s);
-template <int D> void launch_edge_objective(int64_t n_edges, const EdgeRec *rec, const double *x,
+template <int D> void launch_edge_objective(int64_t n_edges, const int *idx, const double *val, const double *x,
                                             int loss, double loss_reg, double *block_partials,
                                             int *n_blocks_out, cudaStream_t s);
 void launch_sum_blocks(int n_blocks, const double *block_partials, double *out, cudaStream_t s);

@@ -437,7 +437,19 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   if ((rc = upload(h, &h->d_d00, d00))) return rc;
   if ((rc = upload(h, &h->d_xrowptr, xrowptr))) return rc;
   if ((rc = upload(h, &h->d_xrec, xrec))) return rc;
-  if ((rc = upload(h, &h->d_erec, erec))) return rc;
+  {
+    const size_t ne = erec.size();
+    std::vector<int> eidx(3 * ne);
+    std::vector<double> evals(14 * ne, 0.0);
+    for (size_t e = 0; e < ne; ++e) {
+      eidx[e] = erec[e].i; eidx[ne + e] = erec[e].j; eidx[2 * ne + e] = erec[e].inter;
+      evals[e] = erec[e].tau; evals[ne + e] = erec[e].kappa;
+      for (int k = 0; k < 3; ++k) evals[(2 + k) * ne + e] = erec[e].t[k];
+      for (int k = 0; k < 9; ++k) evals[(5 + k) * ne + e] = erec[e].R[k];
+    }
+    if ((rc = upload(h, &h->d_eidx, eidx))) return rc;
+    if ((rc = upload(h, &h->d_eval, evals))) return rc;
+  }
   if ((rc = upload(h, &h->d_ginv, ginv))) return rc;
   if ((rc = upload(h, &h->d_sell_ptr, sell_ptr))) return rc;
   if ((rc = upload(h, &h->d_sell_pack, sell_pack))) return rc;
