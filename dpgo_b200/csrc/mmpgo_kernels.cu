@@ -68,7 +68,7 @@ __device__ __forceinline__ void proj_row(const double *V, const double *Y, int r
 // K2: block-CSR pass.  (d+1) threads per pose, thread `row` owns one output row.
 // =============================================================================
 template <int D, int MODE>
-__global__ void __launch_bounds__(TILE *(D + 1))
+__global__ void __launch_bounds__(TILE *(D + 1), 3)
 k_gpass(Tiles tl, GPassArgs a) {
   constexpr int R = Dim<D>::R, PB = Dim<D>::PB, BB = Dim<D>::BB, SYM = Dim<D>::SYM;
   constexpr int NT = TILE * R;
@@ -95,17 +95,30 @@ k_gpass(Tiles tl, GPassArgs a) {
   }
   if (valid && row_on) {
     const int e0 = a.rowptr[p], e1 = a.rowptr[p + 1];
+    // two entries per trip: the loads of both (column -> neighbour block is a dependent chain) are
+    // in flight together
+#pragma unroll 2
     for (int e = e0; e < e1; ++e) {
       const int q = __ldg(a.col + e);
       const double *b = a.blk + (size_t)e * BB + row * R;
-      const double *xq = a.x + (size_t)q * PB;
-      double br[R];
+      // 128-bit loads: the neighbour's pose block (16-byte aligned for d = 2 and 3) and, for
+      // d = 3, this thread's row of the 4 x 4 block
+      const double2 *xq2 = reinterpret_cast<const double2 *>(a.x + (size_t)q * PB);
+      double br[R], xq[PB];
+      if (R % 2 == 0) {
+        const double2 *b2 = reinterpret_cast<const double2 *>(b);
 #pragma unroll
-      for (int k = 0; k < R; ++k) br[k] = __ldg(b + k);
+        for (int k = 0; k < R / 2; ++k) { const double2 v = __ldg(b2 + k); br[2 * k] = v.x; br[2 * k + 1] = v.y; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) br[k] = __ldg(b + k);
+      }
+#pragma unroll
+      for (int k = 0; k < PB / 2; ++k) { const double2 v = __ldg(xq2 + k); xq[2 * k] = v.x; xq[2 * k + 1] = v.y; }
 #pragma unroll
       for (int k = K0; k < R; ++k) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] = fma(br[k], __ldg(xq + k * D + c), acc[c]);
+        for (int c = 0; c < D; ++c) acc[c] = fma(br[k], xq[k * D + c], acc[c]);
       }
     }
     const double *dg = a.diag + (size_t)p * SYM;
