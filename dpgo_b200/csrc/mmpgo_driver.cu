@@ -699,16 +699,39 @@ template <int D> struct Drv {
     RC(vec(h, V_COPY, allm, h->Xakh, nullptr, Xak, nullptr, nullptr, nullptr, nullptr));
     RC(recover_t(h, Xak, h->gex, allm));
     if (any(refined) && o.max_iterations > 0 && o.max_iterations_accepted > 0) RC(tnt(h, Xak, h->gex, refined, fx));
+    // F(X^{k+1/2}), |X^{k+1/2} - X^k|^2, F(X^{k+1}), |X^{k+1} - X^k|^2: four kernels, one host
+    // synchronisation and ONE all-reduce of four scalars (DPGOStar.cpp:147-159 evaluates them one
+    // after the other; X^{k+1} does not depend on the outcome of the first test)
     double fobjh, fobj, dh, dp;
-    RC(edge_objective(h, h->Xakh, &fobjh));
-    RC(diff2(h, h->Xakh, Xk, &dh));
+    {
+      RC(halo_exchange(h, h->Xakh));
+      RC(halo_exchange(h, Xak));
+      int nb = 0;
+      launch_edge_objective<D>(h->n_edges_owned, h->d_eidx, h->d_eval, h->Xakh, o.loss, o.loss_reg, h->d_block_partials, &nb, h->stream);
+      launch_sum_blocks(nb, h->d_block_partials, h->d_scalar, h->stream);
+      launch_edge_objective<D>(h->n_edges_owned, h->d_eidx, h->d_eval, Xak, o.loss, o.loss_reg, h->d_block_partials, &nb, h->stream);
+      launch_sum_blocks(nb, h->d_block_partials, h->d_scalar + 1, h->stream);
+      h->ctr.launches += 4; h->ctr.inter_passes += 2;
+      RC(vec(h, V_DIFFNORM, allm, h->Xakh, Xk, nullptr, nullptr, nullptr, nullptr, nullptr));
+      launch_reduce(A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
+      RC(vec(h, V_DIFFNORM, allm, Xak, Xk, nullptr, nullptr, nullptr, nullptr, nullptr));
+      launch_reduce(A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal2, h->stream);
+      h->ctr.launches += 2;
+      double *hp = h->h_pinned;
+      CK(cudaMemcpyAsync(hp, h->d_scalar, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(hp + 8, h->d_node_scal, sizeof(double) * A * NS, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(hp + 8 + (size_t)A * NS, h->d_node_scal2, sizeof(double) * A * NS, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      double v[4] = {hp[0], 0.0, hp[1], 0.0};
+      for (int n = 0; n < A; ++n) { v[1] += hp[8 + (size_t)n * NS]; v[3] += hp[8 + (size_t)(A + n) * NS]; }
+      RC(allreduce(h, v, 4));
+      fobjh = v[0]; dh = v[1]; fobj = v[2]; dp = v[3];
+    }
     if (fobjh > h->starF - o.psi * dh) {
       // pm_pgo_n: plain proximal from Xk (DPGOStar.cpp:685-711)
       RC(proximal(h, Xk, nullptr, Dfk, nullptr, nullptr, nullptr, nullptr, h->Xakh, nullptr, allm, nullptr));
       RC(edge_objective(h, h->Xakh, &fobjh));
     }
-    RC(edge_objective(h, Xak, &fobj));
-    RC(diff2(h, Xak, Xk, &dp));
     if (fobj > h->starF - o.psi * dp) {
       // global restart: mm_pgo_n for all nodes + halve s (DPGOStar.cpp:159-169)
       h->star_restarts++;

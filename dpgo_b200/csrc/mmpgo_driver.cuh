@@ -105,6 +105,7 @@ struct Handle {
   // per half-edge
   double *w_cur = nullptr, *w_prev = nullptr, *w_tmp = nullptr;
   // scalars
+  double *d_node_scal2 = nullptr;
   double *d_partials = nullptr, *d_node_scal = nullptr, *d_coef = nullptr, *d_gamma = nullptr;
   double *d_block_partials = nullptr, *d_scalar = nullptr;
   double *h_pinned = nullptr;   // pinned staging (A*NS + A*MAXC + misc)

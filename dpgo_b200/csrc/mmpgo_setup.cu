@@ -493,11 +493,12 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   for (auto q : wv) if ((rc = dalloc(h, q, (size_t)nxe))) return rc;
   if ((rc = dalloc(h, &h->d_partials, (size_t)h->n_tiles * NS))) return rc;
   if ((rc = dalloc(h, &h->d_node_scal, (size_t)A * NS))) return rc;
+  if ((rc = dalloc(h, &h->d_node_scal2, (size_t)A * NS))) return rc;
   if ((rc = dalloc(h, &h->d_coef, (size_t)A * MAXC))) return rc;
   if ((rc = dalloc(h, &h->d_gamma, (size_t)A))) return rc;
   if ((rc = dalloc(h, &h->d_block_partials, (size_t)148 * 8 + 8))) return rc;
   if ((rc = dalloc(h, &h->d_scalar, (size_t)8))) return rc;
-  CK(cudaMallocHost((void **)&h->h_pinned, sizeof(double) * ((size_t)A * (NS + 8) + 64)));
+  CK(cudaMallocHost((void **)&h->h_pinned, sizeof(double) * ((size_t)A * (2 * NS + 8) + 64)));
   CK(cudaStreamSynchronize(h->stream));
   h->st.assign(A, NodeState());
   h->graph_set = true;
