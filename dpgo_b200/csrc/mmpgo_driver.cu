@@ -345,8 +345,7 @@ template <int D> struct Drv {
       if (!any(run)) break;
       RC(stpcg(h, x, run, Delta, hM, inner));
       // trial point: retract, recover translations, evaluate
-      RC(vec(h, V_COPY, run, x, nullptr, h->xprop, nullptr, nullptr, nullptr, nullptr));
-      RC(vec(h, V_RETRACT, run, x, h->cg_s, h->xprop, nullptr, nullptr, nullptr, nullptr));
+      RC(vec(h, V_RETRACT, run, x, h->cg_s, h->xprop, nullptr, nullptr, nullptr, nullptr));   // writes the whole pose block
       RC(recover_t(h, h->xprop, g, run));
       RC(eval_G(h, h->xprop, g, run, fprop));
       // predicted decrease needs grad.h and h.Hess h.  H is linear and the step is s = sum alpha_k p_k,

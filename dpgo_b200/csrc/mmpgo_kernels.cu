@@ -722,105 +722,167 @@ __device__ __forceinline__ void apply_precon(const VecArgs &a, int p, const doub
   for (int rr = 0; rr < D; ++rr) proj_row<D>(u, Y, rr, v + rr * D);
 }
 
+// Tile <-> registers through shared memory: the CTA reads / writes the tile's pose blocks as one
+// contiguous run of doubles (coalesced), every thread then picks up / deposits its own pose.
+// Rows are padded to PB + 1 doubles (2-way bank conflicts at most for 64-bit accesses).
+template <int D>
+__device__ __forceinline__ void tile_load(const double *g, int p0, int cnt, double *sm, double (&v)[(D + 1) * D]) {
+  constexpr int PB = Dim<D>::PB;
+  const int n = cnt * PB;
+  const double *src = g + (size_t)p0 * PB;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += TILE) sm[(i / PB) * (PB + 1) + i % PB] = src[i];
+  __syncthreads();
+  if (threadIdx.x < cnt) {
+#pragma unroll
+    for (int k = 0; k < PB; ++k) v[k] = sm[threadIdx.x * (PB + 1) + k];
+  }
+}
+template <int D>
+__device__ __forceinline__ void tile_store(double *g, int p0, int cnt, double *sm, const double (&v)[(D + 1) * D]) {
+  constexpr int PB = Dim<D>::PB;
+  const int n = cnt * PB;
+  double *dst = g + (size_t)p0 * PB;
+  __syncthreads();
+  if (threadIdx.x < cnt) {
+#pragma unroll
+    for (int k = 0; k < PB; ++k) sm[threadIdx.x * (PB + 1) + k] = v[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += TILE) dst[i] = sm[(i / PB) * (PB + 1) + i % PB];
+}
+
 template <int D, int OP>
 __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
   constexpr int PB = Dim<D>::PB, DD = D * D;
   const int tile = blockIdx.x;
   const int node = tl.node[tile];
   if (tl.active && !tl.active[node]) return;
-  const int p = tl.start[tile] + threadIdx.x;
-  const bool valid = threadIdx.x < tl.cnt[tile];
+  const int p0 = tl.start[tile], cnt = tl.cnt[tile];
+  const int p = p0 + threadIdx.x;
+  const bool valid = threadIdx.x < cnt;
   const double *cf = a.coef ? a.coef + (size_t)node * MAXC : nullptr;
+  __shared__ double sm[TILE * (PB + 1)];
   double sc[3] = {0, 0, 0};
-  if (valid) {
-    const size_t o = (size_t)p * PB + D;  // rotation rows
-    if (OP == V_CG_INIT) {
-      // a = grad; o1 = s, o2 = r, o3 = v, o4 = p
-      double r[DD], v[DD], Y[DD];
-#pragma unroll
-      for (int k = 0; k < DD; ++k) { r[k] = a.a[o + k]; Y[k] = a.y[o + k]; }
-      apply_precon<D>(a, p, r, Y, v);
-#pragma unroll
-      for (int k = 0; k < DD; ++k) {
-        a.o1[o + k] = 0.0; a.o2[o + k] = r[k]; a.o3[o + k] = v[k]; a.o4[o + k] = -v[k];
-        a.o5[o + k] = 0.0;
-        sc[0] += r[k] * v[k];
-      }
-#pragma unroll
-      for (int k = 0; k < D; ++k) { a.o1[o - D + k] = 0.0; a.o4[o - D + k] = 0.0; }
-    } else if (OP == V_CG_STEP) {
-      // a = p, b = Hp; o1 = s, o2 = r, o3 = v; coef[0] = alpha
-      const double al = cf[0];
-      double r[DD], v[DD], Y[DD];
-#pragma unroll
-      for (int k = 0; k < DD; ++k) {
-        a.o1[o + k] = a.o1[o + k] + al * a.a[o + k];
-        a.o5[o + k] = a.o5[o + k] + al * a.b[o + k];
-        r[k] = a.o2[o + k] + al * a.b[o + k];
-        Y[k] = a.y[o + k];
-      }
-      apply_precon<D>(a, p, r, Y, v);
-#pragma unroll
-      for (int k = 0; k < DD; ++k) { a.o2[o + k] = r[k]; a.o3[o + k] = v[k]; sc[0] += r[k] * v[k]; }
-    } else if (OP == V_CG_DIR) {
-      // a = v; o1 = p; coef[1] = beta
-      const double be = cf[1];
-#pragma unroll
-      for (int k = 0; k < DD; ++k) a.o1[o + k] = -a.a[o + k] + be * a.o1[o + k];
-    } else if (OP == V_CG_FINAL) {
-      // o1 = s, a = p; coef[2] = sigma (sign folded in by the host)
-      const double sg = cf[2];
-#pragma unroll
-      for (int k = 0; k < DD; ++k) {
-        a.o1[o + k] = a.o1[o + k] + sg * a.a[o + k];
-        a.o5[o + k] = a.o5[o + k] + sg * a.b[o + k];
-      }
-    } else if (OP == V_RETRACT) {
-      // a = x, b = s; o1 = xprop (rotation rows)
-      double M[DD], Yn[DD];
-#pragma unroll
-      for (int k = 0; k < DD; ++k) M[k] = a.a[o + k] + a.b[o + k];
-      project_to_SOd<D>(M, Yn);
-#pragma unroll
-      for (int k = 0; k < DD; ++k) a.o1[o + k] = Yn[k];
-    } else if (OP == V_DOTS) {
-#pragma unroll
-      for (int k = 0; k < DD; ++k) {
-        const double x = a.a[o + k], y = a.b[o + k];
-        sc[0] += x * y; sc[1] += x * x; sc[2] += y * y;
-      }
-    } else if (OP == V_COPY_ROT) {
-#pragma unroll
-      for (int k = 0; k < DD; ++k) a.o1[o + k] = a.a[o + k];
-    } else if (OP == V_COPY) {
-#pragma unroll
-      for (int k = 0; k < PB; ++k) a.o1[o - D + k] = a.a[o - D + k];
-    } else if (OP == V_PRECOND) {
-      double r[DD], v[DD], Y[DD];
-#pragma unroll
-      for (int k = 0; k < DD; ++k) { r[k] = a.a[o + k]; Y[k] = a.y[o + k]; }
-      apply_precon<D>(a, p, r, Y, v);
-#pragma unroll
-      for (int k = 0; k < DD; ++k) { if (a.o1) a.o1[o + k] = v[k]; sc[0] += v[k] * v[k]; }
-    } else if (OP == V_SET_T) {
-      // a = compact solution (NO x D); o1.t = -a
-#pragma unroll
-      for (int k = 0; k < D; ++k) a.o1[o - D + k] = -a.a[(size_t)p * D + k];
-    } else if (OP == V_DIFFNORM) {
-#pragma unroll
-      for (int k = 0; k < PB; ++k) {
-        const double dlt = a.a[o - D + k] - a.b[o - D + k];
+  // element-wise operations: one thread per double of the tile, fully coalesced
+  if (OP == V_CG_DIR || OP == V_CG_FINAL || OP == V_DOTS || OP == V_COPY_ROT || OP == V_COPY || OP == V_DIFFNORM) {
+    const size_t base = (size_t)p0 * PB;
+    const int n = cnt * PB;
+    for (int i = threadIdx.x; i < n; i += TILE) {
+      const bool rot = i % PB >= D;                 // rotation rows of the pose block
+      const size_t o = base + i;
+      if (OP == V_CG_DIR) {            // a = v; o1 = p; coef[1] = beta
+        if (rot) a.o1[o] = -a.a[o] + cf[1] * a.o1[o];
+      } else if (OP == V_CG_FINAL) {   // o1 = s, a = p, b = Hp, o5 = Hs; coef[2] = sigma (sign folded in by the host)
+        if (rot) { a.o1[o] = a.o1[o] + cf[2] * a.a[o]; a.o5[o] = a.o5[o] + cf[2] * a.b[o]; }
+      } else if (OP == V_DOTS) {
+        if (rot) { const double x = a.a[o], y = a.b[o]; sc[0] += x * y; sc[1] += x * x; sc[2] += y * y; }
+      } else if (OP == V_COPY_ROT) {
+        if (rot) a.o1[o] = a.a[o];
+      } else if (OP == V_COPY) {
+        a.o1[o] = a.a[o];
+      } else {                         // V_DIFFNORM
+        const double dlt = a.a[o] - a.b[o];
         sc[0] += dlt * dlt;
       }
-    } else if (OP == V_GET_T) {
-#pragma unroll
-      for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = -a.a[o - D + k];
-    } else if (OP == V_ZERO_C) {
-#pragma unroll
-      for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = 0.0;
     }
+    if (OP == V_DOTS || OP == V_DIFFNORM) block_reduce_store<3, TILE>(sc, a.partials + (size_t)tile * NS);
+    return;
   }
-  if (OP == V_CG_INIT || OP == V_CG_STEP || OP == V_DOTS || OP == V_PRECOND || OP == V_DIFFNORM)
+  if (OP == V_SET_T || OP == V_GET_T || OP == V_ZERO_C) {
+    if (valid) {
+      const size_t o = (size_t)p * PB;
+      if (OP == V_SET_T) {             // a = compact solution (NO x D); o1.t = -a
+#pragma unroll
+        for (int k = 0; k < D; ++k) a.o1[o + k] = -a.a[(size_t)p * D + k];
+      } else if (OP == V_GET_T) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = -a.a[o + k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = 0.0;
+      }
+    }
+    return;
+  }
+  // per-pose operations (preconditioner / tangent projection / polar projection need the whole
+  // d x d block): tiles go through shared memory so that global accesses stay coalesced
+  double Yb[PB], A1[PB], A2[PB], A3[PB], A4[PB];
+  if (OP == V_CG_INIT) {
+    // a = grad; o1 = s, o2 = r, o3 = v, o4 = p, o5 = Hs
+    tile_load<D>(a.a, p0, cnt, sm, A1);
+    tile_load<D>(a.y, p0, cnt, sm, Yb);
+    if (valid) {
+      double v[DD];
+      apply_precon<D>(a, p, A1 + D, Yb + D, v);
+#pragma unroll
+      for (int k = 0; k < D; ++k) { A1[k] = 0.0; A2[k] = 0.0; A3[k] = 0.0; A4[k] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { A2[D + k] = v[k]; A3[D + k] = -v[k]; A4[D + k] = 0.0; sc[0] += A1[D + k] * v[k]; }
+    }
+    tile_store<D>(a.o2, p0, cnt, sm, A1);     // r = grad (t rows zero)
+    tile_store<D>(a.o3, p0, cnt, sm, A2);     // v
+    tile_store<D>(a.o4, p0, cnt, sm, A3);     // p = -v
+    tile_store<D>(a.o1, p0, cnt, sm, A4);     // s = 0
+    tile_store<D>(a.o5, p0, cnt, sm, A4);     // Hs = 0
+  } else if (OP == V_CG_STEP) {
+    // a = p, b = Hp; o1 = s, o2 = r, o3 = v, o5 = Hs; coef[0] = alpha
+    const double al = cf[0];
+    tile_load<D>(a.a, p0, cnt, sm, A1);       // p
+    tile_load<D>(a.b, p0, cnt, sm, A2);       // Hp
+    tile_load<D>(a.o1, p0, cnt, sm, A3);      // s
+    if (valid) {
+#pragma unroll
+      for (int k = D; k < PB; ++k) A3[k] = A3[k] + al * A1[k];
+    }
+    tile_store<D>(a.o1, p0, cnt, sm, A3);
+    tile_load<D>(a.o5, p0, cnt, sm, A3);      // Hs
+    if (valid) {
+#pragma unroll
+      for (int k = D; k < PB; ++k) A3[k] = A3[k] + al * A2[k];
+    }
+    tile_store<D>(a.o5, p0, cnt, sm, A3);
+    tile_load<D>(a.o2, p0, cnt, sm, A4);      // r
+    tile_load<D>(a.y, p0, cnt, sm, Yb);
+    if (valid) {
+      double v[DD];
+#pragma unroll
+      for (int k = D; k < PB; ++k) A4[k] = A4[k] + al * A2[k];
+      apply_precon<D>(a, p, A4 + D, Yb + D, v);
+#pragma unroll
+      for (int k = 0; k < D; ++k) A1[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { A1[D + k] = v[k]; sc[0] += A4[D + k] * v[k]; }
+    }
+    tile_store<D>(a.o2, p0, cnt, sm, A4);
+    tile_store<D>(a.o3, p0, cnt, sm, A1);
+  } else if (OP == V_RETRACT) {
+    // a = x, b = s; o1 = xprop: rotation rows = proj(x.Y + s.Y), translation rows copied from x
+    tile_load<D>(a.a, p0, cnt, sm, A1);
+    tile_load<D>(a.b, p0, cnt, sm, A2);
+    if (valid) {
+      double M[DD], Yn[DD];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) M[k] = A1[D + k] + A2[D + k];
+      project_to_SOd<D>(M, Yn);
+#pragma unroll
+      for (int k = 0; k < DD; ++k) A1[D + k] = Yn[k];
+    }
+    tile_store<D>(a.o1, p0, cnt, sm, A1);
+  } else if (OP == V_PRECOND) {
+    tile_load<D>(a.a, p0, cnt, sm, A1);
+    tile_load<D>(a.y, p0, cnt, sm, Yb);
+    if (valid) {
+      double v[DD];
+      apply_precon<D>(a, p, A1 + D, Yb + D, v);
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { A2[D + k] = v[k]; sc[0] += v[k] * v[k]; }
+#pragma unroll
+      for (int k = 0; k < D; ++k) A2[k] = 0.0;
+    }
+    if (a.o1) tile_store<D>(a.o1, p0, cnt, sm, A2);
+  }
+  if (OP == V_CG_INIT || OP == V_CG_STEP || OP == V_PRECOND)
     block_reduce_store<3, TILE>(sc, a.partials + (size_t)tile * NS);
 }
 

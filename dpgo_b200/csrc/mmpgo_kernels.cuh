@@ -107,7 +107,7 @@ enum VecOp {
   V_CG_STEP = 1,   // s+=a p; Hs+=a Hp; r+=a Hp; v=P(r);   s0 = r.v
   V_CG_DIR = 2,    // p = -v + b p
   V_CG_FINAL = 3,  // s += sigma p; Hs += sigma Hp  (p optionally negated first)
-  V_RETRACT = 4,   // xprop.Y = proj(x.Y + s.Y)                 (DPGOProblem.cpp:127-143)
+  V_RETRACT = 4,   // xprop.Y = proj(x.Y + s.Y), xprop.t = x.t    (DPGOProblem.cpp:127-143)
   V_DOTS = 5,      // s0 = a.b  s1 = a.a  s2 = b.b (rotation rows)
   V_COPY_ROT = 6,  // out.Y = a.Y
   V_COPY = 7,      // out = a

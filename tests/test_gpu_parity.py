@@ -193,3 +193,22 @@ def test_projection_bitwise_vs_reference_avx2(d):
     from oracle import ref
     if ref.available():                       # the compiled reference travels with the repo
         assert np.array_equal(ref.project(A, nofma=True), want)
+
+
+@pytest.mark.parametrize("alg,loss", [("hash", "trivial"), ("star", "huber")])
+def test_persistent_solve_multi_tile_nodes(alg, loss):
+    """Nodes spanning many CTA tiles and several chunks of the persistent translation solve
+    (1600 poses per node, ragged last tile), masked sub-sets of nodes in the restart paths."""
+    g, _, X0 = D.grid3d(20, 20, 12, seed=8)
+    _check(parity.run_both(g, 3, X0, 6, loss=loss, algorithm=alg, dense_solve_max_n=0), 3)
+
+
+def test_persistent_solve_se2():
+    g, _, X0 = D.city2d(40, 30, seed=6)
+    _check(parity.run_both(g, 5, X0, 6, loss="gm", dense_solve_max_n=0), 2)
+
+
+def test_persistent_solve_many_small_nodes():
+    # more nodes than a CTA has segments to spare: 40 nodes of 45 poses, one tile each
+    g, _, X0 = D.grid3d(15, 12, 10, seed=12)
+    _check(parity.run_both(g, 40, X0, 5, dense_solve_max_n=0), 3)
