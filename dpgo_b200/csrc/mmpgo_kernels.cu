@@ -608,6 +608,43 @@ template <int D> void launch_inter(int mode, const Tiles &tl, const InterArgs &a
 template void launch_inter<2>(int, const Tiles &, const InterArgs &, cudaStream_t);
 template void launch_inter<3>(int, const Tiles &, const InterArgs &, cudaStream_t);
 
+// Tile <-> registers through shared memory: the CTA reads / writes the tile's pose blocks as one
+// contiguous run of doubles (coalesced), every thread then picks up / deposits its own pose.
+// Rows are padded to PB + 1 doubles (2-way bank conflicts at most for 64-bit accesses).
+template <int PB>
+__device__ __forceinline__ void tile_load_n(const double *g, int p0, int cnt, double *sm, double (&v)[PB]) {
+  const int n = cnt * PB;
+  const double *src = g + (size_t)p0 * PB;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += TILE) sm[(i / PB) * (PB + 1) + i % PB] = src[i];
+  __syncthreads();
+  if (threadIdx.x < cnt) {
+#pragma unroll
+    for (int k = 0; k < PB; ++k) v[k] = sm[threadIdx.x * (PB + 1) + k];
+  }
+}
+template <int PB>
+__device__ __forceinline__ void tile_store_n(double *g, int p0, int cnt, double *sm, const double (&v)[PB]) {
+  const int n = cnt * PB;
+  double *dst = g + (size_t)p0 * PB;
+  __syncthreads();
+  if (threadIdx.x < cnt) {
+#pragma unroll
+    for (int k = 0; k < PB; ++k) sm[threadIdx.x * (PB + 1) + k] = v[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += TILE) dst[i] = sm[(i / PB) * (PB + 1) + i % PB];
+}
+
+template <int D>
+__device__ __forceinline__ void tile_load(const double *g, int p0, int cnt, double *sm, double (&v)[(D + 1) * D]) {
+  tile_load_n<(D + 1) * D>(g, p0, cnt, sm, v);
+}
+template <int D>
+__device__ __forceinline__ void tile_store(double *g, int p0, int cnt, double *sm, const double (&v)[(D + 1) * D]) {
+  tile_store_n<(D + 1) * D>(g, p0, cnt, sm, v);
+}
+
 // =============================================================================
 // K3: fused Nesterov extrapolation + proximal step + SO(d) polar projection.
 // One thread per pose.                (DPGOHash.cpp:255-262, DPGOProblem.cpp:600-632)
@@ -720,36 +757,6 @@ __device__ __forceinline__ void apply_precon(const VecArgs &a, int p, const doub
   }
 #pragma unroll
   for (int rr = 0; rr < D; ++rr) proj_row<D>(u, Y, rr, v + rr * D);
-}
-
-// Tile <-> registers through shared memory: the CTA reads / writes the tile's pose blocks as one
-// contiguous run of doubles (coalesced), every thread then picks up / deposits its own pose.
-// Rows are padded to PB + 1 doubles (2-way bank conflicts at most for 64-bit accesses).
-template <int D>
-__device__ __forceinline__ void tile_load(const double *g, int p0, int cnt, double *sm, double (&v)[(D + 1) * D]) {
-  constexpr int PB = Dim<D>::PB;
-  const int n = cnt * PB;
-  const double *src = g + (size_t)p0 * PB;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += TILE) sm[(i / PB) * (PB + 1) + i % PB] = src[i];
-  __syncthreads();
-  if (threadIdx.x < cnt) {
-#pragma unroll
-    for (int k = 0; k < PB; ++k) v[k] = sm[threadIdx.x * (PB + 1) + k];
-  }
-}
-template <int D>
-__device__ __forceinline__ void tile_store(double *g, int p0, int cnt, double *sm, const double (&v)[(D + 1) * D]) {
-  constexpr int PB = Dim<D>::PB;
-  const int n = cnt * PB;
-  double *dst = g + (size_t)p0 * PB;
-  __syncthreads();
-  if (threadIdx.x < cnt) {
-#pragma unroll
-    for (int k = 0; k < PB; ++k) sm[threadIdx.x * (PB + 1) + k] = v[k];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += TILE) dst[i] = sm[(i / PB) * (PB + 1) + i % PB];
 }
 
 template <int D, int OP>
