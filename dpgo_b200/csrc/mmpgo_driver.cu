@@ -207,13 +207,21 @@ template <int D> struct Drv {
   // Hess[x](p): tdot = -G00^{-1} G01 p_Y; Hp = Proj(Y, (G [tdot; p_Y])_Y - sym(nab Y^T) p_Y)
   // returns per-node p.Hp, Hp.Hp, p.p        (DPGOProblem.cpp:552-577)
   static int hess_vec(Handle *h, const double *x, double *p, double *Hp, const Mask &m, std::vector<double> &pHp,
-                      std::vector<double> &HpHp, std::vector<double> &pp) {
+                      std::vector<double> &HpHp, std::vector<double> &pp, bool first = false) {
     Tiles tl; RC(make_tiles(h, m, &tl));
     GPassArgs a = gargs(h);
     a.x = p; a.g = nullptr; a.out = h->rhs_t;
     launch_gpass<D>(G_RHS_T, tl, a, h->stream);
     h->ctr.launches++; h->ctr.intra_passes++;
-    RC(solve_t(h, p, m, false));
+    if (first) {
+      // the first search direction of this call is -P(grad), close to that of the previous outer
+      // iteration: start the solve from the tdot found then (only the initial guess changes)
+      RC(vec(h, V_COPY_T, m, h->tdot_prev, nullptr, p, nullptr, nullptr, nullptr, nullptr));
+      RC(solve_t(h, p, m, true));
+      RC(vec(h, V_COPY_T, m, p, nullptr, h->tdot_prev, nullptr, nullptr, nullptr, nullptr));
+    } else {
+      RC(solve_t(h, p, m, false));
+    }
     RC(make_tiles(h, m, &tl));
     a = gargs(h);
     a.x = p; a.xref = x; a.nab = h->nab; a.out = Hp;
@@ -243,6 +251,7 @@ template <int D> struct Drv {
       target[n] = r0 * std::min(o.STPCG_kappa, std::pow(r0, o.STPCG_theta));
     }
     std::vector<double> kap, HpHp, pp;
+    bool first_hv = true;
     while (any(act)) {
       for (int n = 0; n < A; ++n) if (act[n]) {
         if (inner[n] >= o.max_tCG_iterations || std::sqrt(rv[n]) <= target[n]) {
@@ -250,7 +259,8 @@ template <int D> struct Drv {
         }
       }
       if (!any(act)) break;
-      RC(hess_vec(h, x, h->cg_p, h->cg_Hp, act, kap, HpHp, pp));
+      RC(hess_vec(h, x, h->cg_p, h->cg_Hp, act, kap, HpHp, pp, first_hv));
+      first_hv = false;
       Mask fin(A, 0), cont(A, 0), kern(A, 0);
       for (int n = 0; n < A; ++n) if (act[n]) {
         if (std::sqrt(HpHp[n]) / std::sqrt(pp[n]) < eps) { kern[n] = 1; continue; }
@@ -810,6 +820,7 @@ int driver_initialize(Handle *h, const double *X, int64_t ldx) {
   RC(stage_upload(h, X, ldx));
   h->ik = 0; h->ikm1 = 1; h->iak = 2; h->icur = 0;
   pack_dev(h, h->X[0], h->X[1], h->X[2], h->Xakh, h->xprop);
+  CK(cudaMemsetAsync(h->tdot_prev, 0, sizeof(double) * (size_t)h->NO * (h->d + 1) * h->d, h->stream));
   for (auto &s : h->st) { s = NodeState(); s.updated = false; }
   h->star_restarts = 0;
   if (h->opt.algorithm == MMPGO_ALG_STAR) {

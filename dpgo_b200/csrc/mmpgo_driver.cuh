@@ -89,7 +89,7 @@ struct Handle {
   double *g[2] = {nullptr, nullptr}, *Df[2] = {nullptr, nullptr};
   int icur = 0;
   double *gex = nullptr, *Dfex = nullptr, *nab = nullptr, *grad = nullptr;
-  double *cg_s = nullptr, *cg_r = nullptr, *cg_v = nullptr, *cg_p = nullptr, *cg_Hp = nullptr, *cg_Hs = nullptr;
+  double *cg_s = nullptr, *cg_r = nullptr, *cg_v = nullptr, *cg_p = nullptr, *cg_Hp = nullptr, *cg_Hs = nullptr, *tdot_prev = nullptr;
   // compact (NO x D)
   double *rhs_t = nullptr;
   // persistent translation solve (mmpgo_tsolve.cu)

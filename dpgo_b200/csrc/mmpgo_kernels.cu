@@ -772,7 +772,8 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
   __shared__ double sm[TILE * (PB + 1)];
   double sc[3] = {0, 0, 0};
   // element-wise operations: one thread per double of the tile, fully coalesced
-  if (OP == V_CG_DIR || OP == V_CG_FINAL || OP == V_DOTS || OP == V_COPY_ROT || OP == V_COPY || OP == V_DIFFNORM) {
+  if (OP == V_CG_DIR || OP == V_CG_FINAL || OP == V_DOTS || OP == V_COPY_ROT || OP == V_COPY || OP == V_DIFFNORM ||
+      OP == V_COPY_T) {
     const size_t base = (size_t)p0 * PB;
     const int n = cnt * PB;
     for (int i = threadIdx.x; i < n; i += TILE) {
@@ -781,13 +782,18 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
       if (OP == V_CG_DIR) {            // a = v; o1 = p; coef[1] = beta
         if (rot) a.o1[o] = -a.a[o] + cf[1] * a.o1[o];
       } else if (OP == V_CG_FINAL) {   // o1 = s, a = p, b = Hp, o5 = Hs; coef[2] = sigma (sign folded in by the host)
-        if (rot) { a.o1[o] = a.o1[o] + cf[2] * a.a[o]; a.o5[o] = a.o5[o] + cf[2] * a.b[o]; }
+        // s gets all rows: p.t holds tdot = -G00^{-1} G01 p_Y of the last Hessian-vector product, so
+        // s.t = sum alpha_k tdot_k is the first-order change of the translations along the step
+        a.o1[o] = a.o1[o] + cf[2] * a.a[o];
+        if (rot) a.o5[o] = a.o5[o] + cf[2] * a.b[o];
       } else if (OP == V_DOTS) {
         if (rot) { const double x = a.a[o], y = a.b[o]; sc[0] += x * y; sc[1] += x * x; sc[2] += y * y; }
       } else if (OP == V_COPY_ROT) {
         if (rot) a.o1[o] = a.a[o];
       } else if (OP == V_COPY) {
         a.o1[o] = a.a[o];
+      } else if (OP == V_COPY_T) {
+        if (!rot) a.o1[o] = a.a[o];
       } else {                         // V_DIFFNORM
         const double dlt = a.a[o] - a.b[o];
         sc[0] += dlt * dlt;
@@ -840,7 +846,7 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
     tile_load<D>(a.o1, p0, cnt, sm, A3);      // s
     if (valid) {
 #pragma unroll
-      for (int k = D; k < PB; ++k) A3[k] = A3[k] + al * A1[k];
+      for (int k = 0; k < PB; ++k) A3[k] = A3[k] + al * A1[k];   // all rows, see V_CG_FINAL
     }
     tile_store<D>(a.o1, p0, cnt, sm, A3);
     tile_load<D>(a.o5, p0, cnt, sm, A3);      // Hs
@@ -874,6 +880,8 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
       project_to_SOd<D>(M, Yn);
 #pragma unroll
       for (int k = 0; k < DD; ++k) A1[D + k] = Yn[k];
+#pragma unroll
+      for (int k = 0; k < D; ++k) A1[k] = A1[k] + A2[k];   // t + s.t: first-order guess for recover_translations
     }
     tile_store<D>(a.o1, p0, cnt, sm, A1);
   } else if (OP == V_PRECOND) {
@@ -900,6 +908,7 @@ template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cuda
     MMPGO_VEC_CASE(V_CG_FINAL) MMPGO_VEC_CASE(V_RETRACT) MMPGO_VEC_CASE(V_DOTS)
     MMPGO_VEC_CASE(V_COPY_ROT) MMPGO_VEC_CASE(V_COPY) MMPGO_VEC_CASE(V_PRECOND)
     MMPGO_VEC_CASE(V_SET_T) MMPGO_VEC_CASE(V_DIFFNORM) MMPGO_VEC_CASE(V_GET_T) MMPGO_VEC_CASE(V_ZERO_C)
+    MMPGO_VEC_CASE(V_COPY_T)
   }
 #undef MMPGO_VEC_CASE
 }

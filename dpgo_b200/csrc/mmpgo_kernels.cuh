@@ -104,10 +104,10 @@ struct ProxArgs {
 // ---- generic per-pose vector ops (tCG / TNT bookkeeping) --------------------
 enum VecOp {
   V_CG_INIT = 0,   // s=0; Hs=0; r=grad; v=P(r); p=-v;     s0 = r.v, s1 = p.p... (IterativeSolvers.h:204-262)
-  V_CG_STEP = 1,   // s+=a p; Hs+=a Hp; r+=a Hp; v=P(r);   s0 = r.v
+  V_CG_STEP = 1,   // s+=a p (all rows: s.t collects the first-order translation update); Hs+=a Hp; r+=a Hp; v=P(r);   s0 = r.v
   V_CG_DIR = 2,    // p = -v + b p
   V_CG_FINAL = 3,  // s += sigma p; Hs += sigma Hp  (p optionally negated first)
-  V_RETRACT = 4,   // xprop.Y = proj(x.Y + s.Y), xprop.t = x.t    (DPGOProblem.cpp:127-143)
+  V_RETRACT = 4,   // xprop.Y = proj(x.Y + s.Y), xprop.t = x.t + s.t (initial guess of the solve that follows)  (DPGOProblem.cpp:127-143)
   V_DOTS = 5,      // s0 = a.b  s1 = a.a  s2 = b.b (rotation rows)
   V_COPY_ROT = 6,  // out.Y = a.Y
   V_COPY = 7,      // out = a
@@ -115,7 +115,8 @@ enum VecOp {
   V_SET_T = 9,     // out.t = -tsol
   V_DIFFNORM = 10, // s0 = |a - b|^2 (all rows)
   V_GET_T = 11,    // compact o1 = -a.t   (warm start of the translation solve)
-  V_ZERO_C = 12    // compact o1 = 0
+  V_ZERO_C = 12,   // compact o1 = 0
+  V_COPY_T = 13    // o1.t = a.t
 };
 
 struct VecArgs {

@@ -473,7 +473,7 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   double **pv[] = {&h->Xakh, &h->Yex, &h->xprop, &h->xeval};
   for (auto q : pv) if ((rc = dalloc(h, q, np))) return rc;
   double **ov[] = {&h->g[0], &h->g[1], &h->Df[0], &h->Df[1], &h->gex, &h->Dfex, &h->nab, &h->grad,
-                   &h->cg_s, &h->cg_r, &h->cg_v, &h->cg_p, &h->cg_Hp, &h->cg_Hs};
+                   &h->cg_s, &h->cg_r, &h->cg_v, &h->cg_p, &h->cg_Hp, &h->cg_Hs, &h->tdot_prev};
   for (auto q : ov) if ((rc = dalloc(h, q, no))) return rc;
   double **cv[] = {&h->rhs_t};
   for (auto q : cv) if ((rc = dalloc(h, q, nc))) return rc;
