@@ -212,3 +212,10 @@ def test_persistent_solve_many_small_nodes():
     # more nodes than a CTA has segments to spare: 40 nodes of 45 poses, one tile each
     g, _, X0 = D.grid3d(15, 12, 10, seed=12)
     _check(parity.run_both(g, 40, X0, 5, dense_solve_max_n=0), 3)
+
+
+@pytest.mark.parametrize("alg,loss", [("hash", "gm"), ("star", "welsch")])
+def test_fifty_iterations_trace_robust(alg, loss):
+    # 50 iterations with a robust loss and 20 % outlier loop closures (BASELINE.json config 3 in small)
+    g, _, X0 = D.city2d(14, 12, outlier_fraction=0.2, seed=9)
+    _check(parity.run_both(g, 4, X0, 50, loss=loss, algorithm=alg), 2, iters_checked=50)
