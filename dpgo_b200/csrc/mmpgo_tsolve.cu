@@ -103,7 +103,7 @@ template <int D> struct TSCfg {
   static constexpr int HV = 2 * TS_HALO + 1;     // tiles of z staged for phase A (own tile in the middle)
   static constexpr int SELL_CAP = 40;            // 32-entry ELLPACK rows of one CTA tile that fit a stage
   static constexpr int NSTAGE = 5;
-  static constexpr int THREADS = NGRP * CTILE + 64;   // consumer groups + boundary warp + dispatch warp
+  static constexpr int THREADS = NGRP * CTILE + 96;   // consumer groups + boundary warp + two dispatch warps
   // stage layout (bytes):  Z (HV VEC) | R (record or its {p, Ap, diag} tail) | S (packed ELLPACK rows)
   //   phase A: Z = z of the tiles ct-HALO .. ct+HALO, R = {p, Ap, diag}, S = the tile's rows   (3 bulk copies)
   //   phase B: Z = z of the tile, R = {x, p, Ap, diag}                                        (2 bulk copies)
@@ -133,7 +133,7 @@ __device__ __forceinline__ void consumer_barrier(int group) {
 // tile flags (shared memory): scheduler 0 -> 1 (dispatched), consumers 1 -> 2 (phase executed),
 // scheduler 2 -> 0 (arrived on the node)
 template <int D>
-__global__ void __launch_bounds__(TS_NGRP * CTILE + 64, 1) k_tsolve(TSolveArgs a) {
+__global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a) {
   typedef TSCfg<D> C;
   constexpr int PB = (D + 1) * D;
   constexpr int NST = C::NSTAGE;
@@ -192,12 +192,13 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 64, 1) k_tsolve(TSolveArgs a
   // A segment = this CTA's tiles of one node (contiguous).  Two service warps:
   //   boundary warp : per segment and phase one arrival on the node, the node reduction when it is
   //                   the last arriver, and the poll for the node's next epoch -> opens the phase
-  //   dispatch warp : moves tiles of open phases into the copy ring (shared-memory state only)
+  //   dispatch warps: two; move tiles of open phases into the copy ring (shared-memory state only)
   __shared__ int sg_k0[TS_MAXCT], sg_n[TS_MAXCT], sg_node[TS_MAXCT], sg_target[TS_MAXCT];
   __shared__ int sg_kind[TS_MAXCT];            // kind of the open phase: 0 init, 1 phase A, 2 phase B, 3 publish
   __shared__ double sg_coef[TS_MAXCT];         // beta (phase A) / alpha (phase B) of the open phase
   __shared__ int sg_open[TS_MAXCT];            // last phase opened for dispatch   (boundary -> dispatch, release)
-  __shared__ int n_seg_s, all_done_s;
+  __shared__ int sg_claim[TS_MAXCT];           // tiles claimed so far by the dispatch warps (all phases)
+  __shared__ int n_seg_s, all_done_s, use_ctr_s;
   if (wg >= C::NGRP * WPT) {
     if (wg == C::NGRP * WPT && lane == 0) {
       int ns = 0;
@@ -209,13 +210,14 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 64, 1) k_tsolve(TSolveArgs a
         const int nd = m_node[k];
         const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
         sg_target[ns] = min((ce - 1) / CH - cb / CH + 1, (int)gridDim.x);
-        sg_kind[ns] = 0; sg_coef[ns] = 0.0; sg_open[ns] = 0; sg_done[ns] = 0;   // phase 0 (init) is open
+        sg_kind[ns] = 0; sg_coef[ns] = 0.0; sg_open[ns] = 0; sg_done[ns] = 0; sg_claim[ns] = 0;   // phase 0 (init) is open
         ++ns;
       }
       n_seg_s = ns;
       all_done_s = 0;
+      use_ctr_s = 0;
     }
-    asm volatile("bar.sync 15, 64;" ::: "memory");     // the two service warps
+    asm volatile("bar.sync 15, 96;" ::: "memory");     // the three service warps
     const int n_seg = n_seg_s;
 
     if (wg == C::NGRP * WPT) {
@@ -312,88 +314,96 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 64, 1) k_tsolve(TSolveArgs a
       return;
     }
 
-    // =========================== dispatch warp ===========================
-    __shared__ int dp_round[TS_MAXCT];                 // next phase to hand out, per segment (private)
-    for (int q = lane; q < n_seg; q += 32) dp_round[q] = 0;
-    __syncwarp();
-    int stage = 0;
-    uint32_t pe = 0;                                   // parity bits of the empty barriers
-    int uses = 0;                                      // stages handed out so far
-    int cur = -1, cur_next = 0, cur_n = 0, cur_k0 = 0, cur_kind = 0;   // segment being handed out (warp-uniform)
-    double cur_coef = 0.0;
+    // =========================== dispatch warps (two) ===========================
+    // Each claims tiles of open phases (compare-and-swap on the segment's claim counter: claim c is
+    // tile c % n of phase c / n), takes the next use number of the ring and issues the tile's bulk
+    // copies; two warps, because issuing the copies of one tile costs ~0.4 us.
+    const bool lead = wg == C::NGRP * WPT + 1;          // the lead dispatcher also stops the consumers
+    int cur = -1;                                        // segment tiles are currently claimed from
+    int fenced = -1;                                     // (segment, phase) this warp has proxy-fenced for
     while (true) {
-      int in_flight = uses - ld_acquire_cta_shared(&returned_s);
-      if (in_flight == 0 && ld_acquire_cta_shared(&all_done_s)) break;
-      bool progress = false;
-      while (in_flight < NST) {
-        if (cur < 0 || cur_next >= cur_n) {
-          // pick the open segment with the oldest phase
-          int best = -1, best_round = 0x7fffffff;
-          for (int s0 = 0; s0 < n_seg; s0 += 32) {
-            const int sidx = s0 + lane;
-            int key = 0x7fffffff;
-            if (sidx < n_seg && ld_acquire_cta_shared(&sg_open[sidx]) >= dp_round[sidx]) key = dp_round[sidx];
-            int idx = sidx;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const int k2 = __shfl_xor_sync(0xffffffffu, key, o), i2 = __shfl_xor_sync(0xffffffffu, idx, o);
-              if (k2 < key || (k2 == key && i2 < idx)) { key = k2; idx = i2; }
-            }
-            if (key < best_round) { best_round = key; best = idx; }
-          }
-          cur = best;
-          if (best < 0) break;
-          cur_next = 0; cur_n = sg_n[best]; cur_k0 = sg_k0[best]; cur_kind = sg_kind[best]; cur_coef = sg_coef[best];
-          if (lane == 0) {
-            dp_round[best] = best_round + 1;             // the whole phase is handed out below
-            asm volatile("fence.proxy.async;" ::: "memory");   // bulk copies read what other CTAs stored
-          }
-          __syncwarp();
+      // ---- claim a tile
+      int claim = -1;
+      if (cur >= 0 && lane == 0) {
+        const int n = sg_n[cur];
+        int c = ld_acquire_cta_shared(&sg_claim[cur]);
+        while (ld_acquire_cta_shared(&sg_open[cur]) >= c / n) {
+          const int old = atomicCAS(&sg_claim[cur], c, c + 1);
+          if (old == c) { claim = c; break; }
+          c = old;
         }
-        progress = true;
-        const int kk = cur_k0 + cur_next, kd = cur_kind;
-        ++cur_next;
-        if (lane == 0) {
-          if (uses >= NST) mbar_wait(&empty[stage], (pe >> stage) & 1u);
-          d_k[stage] = kk; d_kind[stage] = kd; d_coef[stage] = cur_coef; d_seg[stage] = cur;
-          if (kd == 1 || kd == 2) {
-            const int ct = tile_of(kk);
-            unsigned char *sb = dyn + (size_t)stage * C::STAGE_BYTES;
-            const double *rc = a.rec + (size_t)ct * C::RL;
-            const size_t v0 = (size_t)ct * C::VEC;
-            if (kd == 1) {
-              const int r0 = m_sell[kk][0], rows = m_sell[kk][WPT] - r0;
-              const bool sell_staged = rows <= C::SELL_CAP && rows > 0;
-              mbar_expect_tx(&full[uses % (C::NGRP * NST)], (C::HV * C::VEC + 2 * C::VEC + CTILE) * 8 + (sell_staged ? rows * 384 : 0));
-              bulk_g2s(sb, a.z + v0 - TS_HALO * C::VEC, C::HV * C::VEC * 8, &full[uses % (C::NGRP * NST)]);   // z is padded by the halo
-              bulk_g2s(sb + C::OFF_R, rc + C::VEC, (2 * C::VEC + CTILE) * 8, &full[uses % (C::NGRP * NST)]);
-              if (sell_staged) bulk_g2s(sb + C::OFF_S, a.sell_pack + (size_t)r0 * 384, rows * 384, &full[uses % (C::NGRP * NST)]);
-            } else {
-              mbar_expect_tx(&full[uses % (C::NGRP * NST)], (C::VEC + C::RL) * 8);
-              bulk_g2s(sb, a.z + v0, C::VEC * 8, &full[uses % (C::NGRP * NST)]);
-              bulk_g2s(sb + C::OFF_R, rc, C::RL * 8, &full[uses % (C::NGRP * NST)]);
-            }
-          } else {
-            mbar_arrive(&full[uses % (C::NGRP * NST)]);                  // no staged data: init / publish use direct loads
-          }
-        }
-        __syncwarp();
-        if (uses >= NST) pe ^= 1u << stage;
-        ++uses;
-        ++in_flight;
-        stage = stage + 1 == NST ? 0 : stage + 1;
       }
-      if (!progress) __nanosleep(20);
+      claim = __shfl_sync(0xffffffffu, claim, 0);
+      if (claim < 0) {
+        // pick the open segment with the oldest unclaimed phase
+        int best = -1, best_round = 0x7fffffff;
+        for (int s0 = 0; s0 < n_seg; s0 += 32) {
+          const int sidx = s0 + lane;
+          int key = 0x7fffffff;
+          if (sidx < n_seg) {
+            const int ph = ld_acquire_cta_shared(&sg_claim[sidx]) / sg_n[sidx];
+            if (ld_acquire_cta_shared(&sg_open[sidx]) >= ph) key = ph;
+          }
+          int idx = sidx;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const int k2 = __shfl_xor_sync(0xffffffffu, key, o), i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (k2 < key || (k2 == key && i2 < idx)) { key = k2; idx = i2; }
+          }
+          if (key < best_round) { best_round = key; best = idx; }
+        }
+        cur = best;
+        if (best < 0) {
+          if (ld_acquire_cta_shared(&all_done_s)) break;
+          __nanosleep(20);
+        }
+        continue;
+      }
+      // ---- hand the tile to the consumers
+      if (lane == 0) {
+        const int n = sg_n[cur];
+        const int kk = sg_k0[cur] + claim % n, kd = sg_kind[cur];
+        const double coef = sg_coef[cur];
+        const int use = atomicAdd(&use_ctr_s, 1);
+        const int stage = use % NST;
+        uint64_t *fb = &full[use % (C::NGRP * NST)];
+        if (use >= NST) mbar_wait(&empty[stage], (unsigned)(use / NST - 1) & 1u);
+        d_k[stage] = kk; d_kind[stage] = kd; d_coef[stage] = coef; d_seg[stage] = cur;
+        if (kd == 1 || kd == 2) {
+          if (fenced != cur * 65536 + claim / n) {
+            asm volatile("fence.proxy.async;" ::: "memory");   // bulk copies read what other threads stored
+            fenced = cur * 65536 + claim / n;
+          }
+          const int ct = tile_of(kk);
+          unsigned char *sb = dyn + (size_t)stage * C::STAGE_BYTES;
+          const double *rc = a.rec + (size_t)ct * C::RL;
+          const size_t v0 = (size_t)ct * C::VEC;
+          if (kd == 1) {
+            const int r0 = m_sell[kk][0], rows = m_sell[kk][WPT] - r0;
+            const bool sell_staged = rows <= C::SELL_CAP && rows > 0;
+            mbar_expect_tx(fb, (C::HV * C::VEC + 2 * C::VEC + CTILE) * 8 + (sell_staged ? rows * 384 : 0));
+            bulk_g2s(sb, a.z + v0 - TS_HALO * C::VEC, C::HV * C::VEC * 8, fb);   // z is padded by the halo
+            bulk_g2s(sb + C::OFF_R, rc + C::VEC, (2 * C::VEC + CTILE) * 8, fb);
+            if (sell_staged) bulk_g2s(sb + C::OFF_S, a.sell_pack + (size_t)r0 * 384, rows * 384, fb);
+          } else {
+            mbar_expect_tx(fb, (C::VEC + C::RL) * 8);
+            bulk_g2s(sb, a.z + v0, C::VEC * 8, fb);
+            bulk_g2s(sb + C::OFF_R, rc, C::RL * 8, fb);
+          }
+        } else {
+          mbar_arrive(fb);                              // no staged data: init / publish use direct loads
+        }
+      }
+      __syncwarp();
     }
-    // ---- every segment retired and every tile handed back: tell the consumers to stop
-    if (lane == 0) {
+    // ---- every segment retired and every tile handed back: the lead tells the consumers to stop
+    if (lead && lane == 0) {
       for (int q = 0; q < C::NGRP; ++q) {                // one stop descriptor per consumer group
-        if (uses >= NST) mbar_wait(&empty[stage], (pe >> stage) & 1u);
+        const int use = atomicAdd(&use_ctr_s, 1);
+        const int stage = use % NST;
+        if (use >= NST) mbar_wait(&empty[stage], (unsigned)(use / NST - 1) & 1u);
         d_kind[stage] = -1;
-        mbar_arrive(&full[uses % (C::NGRP * NST)]);
-        if (uses >= NST) pe ^= 1u << stage;
-        ++uses;
-        stage = stage + 1 == NST ? 0 : stage + 1;
+        mbar_arrive(&full[use % (C::NGRP * NST)]);
       }
     }
     return;
