@@ -802,22 +802,6 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
     if (OP == V_DOTS || OP == V_DIFFNORM) block_reduce_store<3, TILE>(sc, a.partials + (size_t)tile * NS);
     return;
   }
-  if (OP == V_SET_T || OP == V_GET_T || OP == V_ZERO_C) {
-    if (valid) {
-      const size_t o = (size_t)p * PB;
-      if (OP == V_SET_T) {             // a = compact solution (NO x D); o1.t = -a
-#pragma unroll
-        for (int k = 0; k < D; ++k) a.o1[o + k] = -a.a[(size_t)p * D + k];
-      } else if (OP == V_GET_T) {
-#pragma unroll
-        for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = -a.a[o + k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < D; ++k) a.o1[(size_t)p * D + k] = 0.0;
-      }
-    }
-    return;
-  }
   // per-pose operations (preconditioner / tangent projection / polar projection need the whole
   // d x d block): tiles go through shared memory so that global accesses stay coalesced
   double Yb[PB], A1[PB], A2[PB], A3[PB], A4[PB];
@@ -907,8 +891,7 @@ template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cuda
     MMPGO_VEC_CASE(V_CG_INIT) MMPGO_VEC_CASE(V_CG_STEP) MMPGO_VEC_CASE(V_CG_DIR)
     MMPGO_VEC_CASE(V_CG_FINAL) MMPGO_VEC_CASE(V_RETRACT) MMPGO_VEC_CASE(V_DOTS)
     MMPGO_VEC_CASE(V_COPY_ROT) MMPGO_VEC_CASE(V_COPY) MMPGO_VEC_CASE(V_PRECOND)
-    MMPGO_VEC_CASE(V_SET_T) MMPGO_VEC_CASE(V_DIFFNORM) MMPGO_VEC_CASE(V_GET_T) MMPGO_VEC_CASE(V_ZERO_C)
-    MMPGO_VEC_CASE(V_COPY_T)
+    MMPGO_VEC_CASE(V_DIFFNORM) MMPGO_VEC_CASE(V_COPY_T)
   }
 #undef MMPGO_VEC_CASE
 }

@@ -112,10 +112,7 @@ enum VecOp {
   V_COPY_ROT = 6,  // out.Y = a.Y
   V_COPY = 7,      // out = a
   V_PRECOND = 8,   // out = P(a); s0 = out.out
-  V_SET_T = 9,     // out.t = -tsol
   V_DIFFNORM = 10, // s0 = |a - b|^2 (all rows)
-  V_GET_T = 11,    // compact o1 = -a.t   (warm start of the translation solve)
-  V_ZERO_C = 12,   // compact o1 = 0
   V_COPY_T = 13    // o1.t = a.t
 };
 

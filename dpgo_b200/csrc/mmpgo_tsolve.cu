@@ -19,7 +19,9 @@
 // to arrive sums the per-tile partials in a fixed order (deterministic, independent of
 // scheduling and of which other nodes share the GPU), computes alpha / beta / convergence and
 // publishes the node's next epoch.  Nodes drift apart freely, so the rendezvous latency of one
-// node is hidden behind the tiles of the others; converged nodes retire individually.
+// node is hidden behind the tiles of the others; converged nodes retire individually.  Inside a
+// CTA the work is warp-specialised: consumer groups (one pose per thread) do the arithmetic, a
+// boundary warp owns all global synchronisation, two dispatch warps feed the copy ring.
 //
 // Data movement.  Solver vectors are laid out [cta tile][warp][d][32]; the matrix is sliced
 // ELLPACK, one slice per 32-pose warp slice, {slot of the neighbour, -tau}[k][32].  A tile's
@@ -147,10 +149,8 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
   // running ahead could mistake another group's unfinished phase for its own)
   __shared__ uint64_t full[C::NGRP * NST], empty[NST];
   __shared__ int m_node[TS_MAXCT], m_start[TS_MAXCT], m_cnt[TS_MAXCT], m_sell[TS_MAXCT][TS_WPT + 1];
-  __shared__ int t_round[TS_MAXCT];          // next phase of the tile; -1 = retired           (scheduler)
-  __shared__ int t_flag[TS_MAXCT];
+  __shared__ int t_round[TS_MAXCT];          // 0: tile of an active node, -1: masked
   __shared__ int d_k[NST], d_kind[NST], d_seg[NST];   // work descriptor of a stage
-  __shared__ int returned_s;                  // tiles the consumers have handed back (monotone)
   __shared__ int sg_done[TS_MAXCT];           // per segment: tiles of the current phase handed back
   __shared__ double d_coef[NST];
   __shared__ double red[TS_NGRP][2][TS_WPT][3];
@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
     for (int q = 0; q < C::NGRP * NST; ++q) mbar_init(&full[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     n_live_s = 0;
-    returned_s = 0;
   }
   __syncthreads();
   if (threadIdx.x < nb) {
@@ -180,7 +179,6 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
     m_node[k] = node; m_start[k] = __ldg(a.ct_start + ct); m_cnt[k] = __ldg(a.ct_cnt + ct);
     const bool on = !(a.active && !__ldg(a.active + node));
     t_round[k] = on ? 0 : -1;
-    t_flag[k] = 0;
     if (on) atomicAdd(&n_live_s, 1);
   }
   for (int q = threadIdx.x; q < nb * (WPT + 1); q += blockDim.x) {
@@ -561,7 +559,6 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
         // hand the tile back: the scheduler arrives on the node once the whole segment is back
         asm volatile("fence.acq_rel.cta;" ::: "memory");
         atomicAdd(&sg_done[seg], 1);
-        atomicAdd(&returned_s, 1);
       }
     }
     ++tick;
