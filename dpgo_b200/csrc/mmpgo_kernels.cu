@@ -68,7 +68,7 @@ __device__ __forceinline__ void proj_row(const double *V, const double *Y, int r
 // K2: block-CSR pass.  (d+1) threads per pose, thread `row` owns one output row.
 // =============================================================================
 template <int D, int MODE>
-__global__ void __launch_bounds__(TILE *(D + 1), 3)
+__global__ void __launch_bounds__(TILE *(D + 1), (MODE == G_HV ? 3 : 4))
 k_gpass(Tiles tl, GPassArgs a) {
   constexpr int R = Dim<D>::R, PB = Dim<D>::PB, BB = Dim<D>::BB, SYM = Dim<D>::SYM;
   constexpr int NT = TILE * R;
