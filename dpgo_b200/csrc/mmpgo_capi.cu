@@ -187,6 +187,11 @@ int mmpgo_set_sharding(mmpgo_handle hh, int32_t rank, int32_t world_size, const 
   H_OR_FAIL(hh);
   GUARDED(mmpgo::driver_set_sharding(h, rank, world_size, rank_node_begin, exchange, allreduce, user));
 }
+int mmpgo_set_device_allreduce(mmpgo_handle hh, mmpgo_allreduce_dev_fn fn) {
+  H_OR_FAIL(hh);
+  h->allreduce_dev_fn = fn;
+  return MMPGO_OK;
+}
 int mmpgo_halo_counts(mmpgo_handle hh, int64_t *send_poses, int64_t *recv_poses) {
   H_OR_FAIL(hh);
   if (!send_poses || !recv_poses || (int)h->send_poses.size() != h->world) {

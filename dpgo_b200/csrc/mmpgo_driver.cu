@@ -91,7 +91,7 @@ template <int D> struct Drv {
     if (h->world <= 1) return 0;
     launch_gather_poses<D>(h->n_send, h->d_send_idx, x, h->d_send, h->stream);
     h->ctr.launches++;
-    CK(cudaStreamSynchronize(h->stream));
+    // no host synchronisation: the transport orders itself on the handle's stream (mmpgo.h)
     h->halo_exchanges++;
     if (h->exchange_fn(h->cb_user, h->d_send, h->send_dbl.data(), x + (size_t)h->NO * PB, h->recv_dbl.data()) != 0) {
       set_error("exchange callback failed");
@@ -727,13 +727,26 @@ template <int D> struct Drv {
       launch_reduce(A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal2, h->stream);
       h->ctr.launches += 2;
       double *hp = h->h_pinned;
-      CK(cudaMemcpyAsync(hp, h->d_scalar, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaMemcpyAsync(hp + 8, h->d_node_scal, sizeof(double) * A * NS, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaMemcpyAsync(hp + 8 + (size_t)A * NS, h->d_node_scal2, sizeof(double) * A * NS, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      double v[4] = {hp[0], 0.0, hp[1], 0.0};
-      for (int n = 0; n < A; ++n) { v[1] += hp[8 + (size_t)n * NS]; v[3] += hp[8 + (size_t)(A + n) * NS]; }
-      RC(allreduce(h, v, 4));
+      double v[4];
+      if (h->world > 1 && h->allreduce_dev_fn) {
+        // the four scalars are reduced on the device (stream-ordered), then read back once
+        launch_sum_strided(A, h->d_node_scal, NS, h->d_scalar + 2, h->stream);
+        launch_sum_strided(A, h->d_node_scal2, NS, h->d_scalar + 3, h->stream);
+        h->ctr.launches += 2;
+        h->allreduces++;
+        if (h->allreduce_dev_fn(h->cb_user, h->d_scalar, 4) != 0) { set_error("device allreduce callback failed"); return MMPGO_ERR_ARG; }
+        CK(cudaMemcpyAsync(hp, h->d_scalar, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        v[0] = hp[0]; v[2] = hp[1]; v[1] = hp[2]; v[3] = hp[3];
+      } else {
+        CK(cudaMemcpyAsync(hp, h->d_scalar, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(hp + 8, h->d_node_scal, sizeof(double) * A * NS, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(hp + 8 + (size_t)A * NS, h->d_node_scal2, sizeof(double) * A * NS, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        v[0] = hp[0]; v[1] = 0.0; v[2] = hp[1]; v[3] = 0.0;
+        for (int n = 0; n < A; ++n) { v[1] += hp[8 + (size_t)n * NS]; v[3] += hp[8 + (size_t)(A + n) * NS]; }
+        RC(allreduce(h, v, 4));
+      }
       fobjh = v[0]; dh = v[1]; fobj = v[2]; dp = v[3];
     }
     if (fobjh > h->starF - o.psi * dh) {

@@ -123,6 +123,7 @@ struct Handle {
   double *d_send = nullptr;
   mmpgo_exchange_fn exchange_fn = nullptr;
   mmpgo_allreduce_fn allreduce_fn = nullptr;
+  mmpgo_allreduce_dev_fn allreduce_dev_fn = nullptr;
   void *cb_user = nullptr;
   int64_t halo_exchanges = 0, allreduces = 0;
   mmpgo_counters ctr;

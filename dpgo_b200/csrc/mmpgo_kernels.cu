@@ -1014,6 +1014,17 @@ template void launch_edge_objective<2>(int64_t, const int *, const double *, con
                                        cudaStream_t);
 template void launch_edge_objective<3>(int64_t, const int *, const double *, const double *, int, double, double *, int *,
                                        cudaStream_t);
+// out[0] = sum_i v[i * stride], fixed order (one warp)
+__global__ void k_sum_strided(int n, const double *v, int stride, double *out) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) s += v[(size_t)i * stride];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) out[0] = s;
+}
+void launch_sum_strided(int n, const double *v, int stride, double *out, cudaStream_t s) {
+  k_sum_strided<<<1, 32, 0, s>>>(n, v, stride, out);
+}
 void launch_sum_blocks(int n_blocks, const double *bp, double *out, cudaStream_t s) {
   k_sum_blocks<<<1, 256, 0, s>>>(n_blocks, bp, out);
 }

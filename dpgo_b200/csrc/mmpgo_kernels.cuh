@@ -185,6 +185,7 @@ template <int D> void launch_edge_objective(int64_t n_edges, const int *idx, con
                                             int loss, double loss_reg, double *block_partials,
                                             int *n_blocks_out, cudaStream_t s);
 void launch_sum_blocks(int n_blocks, const double *block_partials, double *out, cudaStream_t s);
+void launch_sum_strided(int n, const double *v, int stride, double *out, cudaStream_t s);
 
 // translation solve, dense path (small nodes): t = -G00^{-1} rhs
 template <int D> void launch_dense_solve(int num_nodes, const int *node_off, const long long *node_dense_off,

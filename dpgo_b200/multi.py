@@ -70,24 +70,37 @@ class ShardedDriver:
         L.check(self.drv.lib.mmpgo_set_sharding(self.drv._h, rank, world, L.iptr(rnb), self._ex, self._ar,
                                                 None))
         self._scratch = torch.zeros(16, dtype=torch.float64, device="cuda") if world > 1 else None
+        # collectives are issued with the library's stream current: ProcessGroupNCCL orders its
+        # own stream after / before it with events, so no host synchronisation is needed
+        self._ext = torch.cuda.ExternalStream(self.drv.stream()) if world > 1 else None
+        self._views = {}
+        self._ard = L.ALLREDUCE_DEV_FN(self._allreduce_dev)
+        if world > 1:
+            L.check(self.drv.lib.mmpgo_set_device_allreduce(self.drv._h, self._ard))
 
-    # ---- transport callbacks (called from inside libmmpgo with its stream idle) ----------
+    def _view(self, ptr, n):
+        """torch view of n device doubles at ptr (cached: the buffers of a handle are fixed)."""
+        key = (ptr, n)
+        t = self._views.get(key)
+        if t is None:
+            dev = self.torch.device("cuda", self.torch.cuda.current_device())
+            t = self.torch.as_tensor(_DevArray(ptr, n), device=dev) if n else \
+                self.torch.empty(0, dtype=self.torch.float64, device=dev)
+            self._views[key] = t
+        return t
+
+    # ---- transport callbacks (called from inside libmmpgo, ordered on its stream) ----------
     def _exchange(self, user, send_ptr, send_counts, recv_ptr, recv_counts):
         try:
             torch, dist = self.torch, self.dist
             W = self.world
             sc = [int(send_counts[q]) for q in range(W)]
             rc = [int(recv_counts[q]) for q in range(W)]
-            ns, nr = sum(sc), sum(rc)
-            dev = torch.device("cuda", torch.cuda.current_device())
-            send = torch.as_tensor(_DevArray(send_ptr, ns), device=dev) if ns else \
-                torch.empty(0, dtype=torch.float64, device=dev)
-            recv = torch.as_tensor(_DevArray(recv_ptr, nr), device=dev) if nr else \
-                torch.empty(0, dtype=torch.float64, device=dev)
-            dist.all_to_all_single(recv, send, rc, sc)
-            torch.cuda.current_stream().synchronize()
+            send, recv = self._view(send_ptr, sum(sc)), self._view(recv_ptr, sum(rc))
+            with torch.cuda.stream(self._ext):
+                dist.all_to_all_single(recv, send, rc, sc)
             self.exchanges += 1
-            self.exchange_bytes += 8 * ns
+            self.exchange_bytes += 8 * sum(sc)
             return 0
         except Exception as e:          # never let an exception cross the C boundary
             print("mmpgo exchange callback failed:", repr(e))
@@ -98,13 +111,24 @@ class ShardedDriver:
             torch, dist = self.torch, self.dist
             host = np.ctypeslib.as_array(vals, shape=(n,))
             t = self._scratch[:n]
-            t.copy_(torch.from_numpy(host))
-            dist.all_reduce(t)
-            host[:] = t.cpu().numpy()
+            with torch.cuda.stream(self._ext):
+                t.copy_(torch.from_numpy(host))
+                dist.all_reduce(t)
+                host[:] = t.cpu().numpy()
             self.allreduces += 1
             return 0
         except Exception as e:
             print("mmpgo allreduce callback failed:", repr(e))
+            return 1
+
+    def _allreduce_dev(self, user, ptr, n):
+        try:
+            with self.torch.cuda.stream(self._ext):
+                self.dist.all_reduce(self._view(ptr, n))
+            self.allreduces += 1
+            return 0
+        except Exception as e:
+            print("mmpgo device allreduce callback failed:", repr(e))
             return 1
 
     # ---- driver interface ------------------------------------------------------------

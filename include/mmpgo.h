@@ -155,8 +155,11 @@ int mmpgo_current_objective(mmpgo_handle h, double *fobj, double *grad_sqnorm);
  * restart test for AMM-PGO* (DPGOStar.cpp:147-171).  The transport is supplied
  * by the caller as two callbacks (NCCL through torch.distributed in this repo):
  *   exchange(user, send_dev, send_counts, recv_dev, recv_counts): all-to-all of
- *     pose blocks; counts are in doubles per peer rank; the library's stream is
- *     idle during the call and the data must have landed when it returns;
+ *     pose blocks; counts are in doubles per peer rank.  The call is ordered on the
+ *     handle's stream (mmpgo_stream): the send buffer is produced by work already
+ *     enqueued there, and the library reads recv_dev from kernels it enqueues there
+ *     afterwards -- the transport must enqueue on, or synchronise with, that stream
+ *     (no host synchronisation is required);
  *   allreduce(user, vals, n): in-place sum of n host doubles over all ranks.
  * rank_node_begin has world+1 entries: rank r owns nodes [begin[r], begin[r+1]).
  * Call after mmpgo_set_graph and before mmpgo_initialize. */
@@ -166,6 +169,10 @@ typedef int (*mmpgo_allreduce_fn)(void *user, double *vals, int32_t n);
 int mmpgo_set_sharding(mmpgo_handle h, int32_t rank, int32_t world_size,
                        const int32_t *rank_node_begin, mmpgo_exchange_fn exchange,
                        mmpgo_allreduce_fn allreduce, void *user);
+/* Optional: in-place sum over all ranks of n DEVICE doubles, ordered on the handle's stream
+ * (ncclAllReduce).  When set, the AMM-PGO* scalars are reduced on the device and read back once. */
+typedef int (*mmpgo_allreduce_dev_fn)(void *user, void *vals_dev, int32_t n);
+int mmpgo_set_device_allreduce(mmpgo_handle h, mmpgo_allreduce_dev_fn allreduce_dev);
 /* per-peer number of boundary poses sent / received each exchange (length world_size) */
 int mmpgo_halo_counts(mmpgo_handle h, int64_t *send_poses, int64_t *recv_poses);
 /* Host-only (no CUDA) restatement of the exchange plan for rank `rank`: the global ids
