@@ -219,3 +219,50 @@ def test_fifty_iterations_trace_robust(alg, loss):
     # 50 iterations with a robust loss and 20 % outlier loop closures (BASELINE.json config 3 in small)
     g, _, X0 = D.city2d(14, 12, outlier_fraction=0.2, seed=9)
     _check(parity.run_both(g, 4, X0, 50, loss=loss, algorithm=alg), 2, iters_checked=50)
+
+
+def test_poses_absent_from_every_measurement():
+    """generate_data_info indexes only poses that occur in a measurement (DPGO_utils.cpp:358-372):
+    ids without edges stay untouched in X, and the partition still counts them."""
+    g, _, X0 = D.grid3d(5, 5, 4, seed=21)
+    # renumber: insert two unused ids (7 and 60) by shifting the poses above them
+    def shift(v):
+        v = v.astype(np.int64)
+        v = v + (v >= 7)
+        return v + (v >= 60)
+    N2 = g.num_poses + 2
+    g2 = D.PoseGraph(3, N2, shift(g.i), shift(g.j), g.R, g.t, g.kappa, g.tau)
+    keep = np.array([k for k in range(N2) if k not in (7, 60)])
+    X2 = np.zeros((4 * N2, 3))
+    X2[keep] = X0[:g.num_poses]
+    X2[7], X2[60] = 123.0, -5.0                                    # sentinels in the unused rows
+    for r in range(3):
+        X2[N2 + 3 * keep + r] = X0[g.num_poses + 3 * np.arange(g.num_poses) + r]
+        X2[N2 + 3 * np.array([7, 60]) + r, r] = 1.0
+    out = parity.run_both(g2, 4, X2, 5)
+    X = out["X_gpu"].copy()
+    # the driver leaves rows of unused ids as the caller passed them; dist_pgo's own assembly of X
+    # starts from zeros (dist_pgo.cpp:475), which is what the oracle returns there
+    assert (X[7] == 123.0).all() and (X[60] == -5.0).all()
+    # (the reference addresses a node's rows as [first id, first id + n0), DPGOStar.cpp:541-547,
+    # which misplaces rows when ids are missing inside a node; only the objective is comparable)
+    assert parity.rel_trace_error(out).max() < F_TOL
+    assert (out["refined_ref"] == out["refined_gpu"]).all()
+    Y = X[N2:].reshape(N2, 3, 3)[keep]
+    assert np.abs(Y @ np.swapaxes(Y, 1, 2) - np.eye(3)).max() < 1e-12
+
+
+def test_set_graph_rejects_bad_input():
+    g, _, _ = D.grid3d(4, 4, 2, seed=3)
+    bad = D.PoseGraph(3, g.num_poses, g.i.copy(), g.j.copy(), g.R, g.t, g.kappa, g.tau)
+    bad.j[5] = g.num_poses + 3                    # endpoint out of range
+    with pytest.raises(D.MmpgoError):
+        D.DPGOHash(bad, 2)
+    with pytest.raises(D.MmpgoError):
+        D.DPGOHash(g, g.num_poses + 1)            # more nodes than poses
+    # a node without any measurement (the reference would build an empty problem and fail later)
+    iso = D.PoseGraph(3, 64, g.i % 16, (g.j % 16 + 1) % 16, g.R, g.t, g.kappa, g.tau)
+    keep = iso.i != iso.j
+    iso = D.PoseGraph(3, 64, iso.i[keep], iso.j[keep], g.R[keep], g.t[keep], g.kappa[keep], g.tau[keep])
+    with pytest.raises(D.MmpgoError):
+        D.DPGOHash(iso, 4)
