@@ -153,6 +153,48 @@ template <int D> struct Drv {
       ta.tol2 = h->opt.translation_solve_tol * h->opt.translation_solve_tol;
       ta.max_iters = h->opt.translation_solve_max_iters;
       CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (2 * h->A + 8), h->stream));
+      // small shards (few CTA tiles per SM) are rendezvous bound: k_tsolve_lite; large ones are
+      // HBM bound: the copy-ring kernel.  MMPGO_TS_KERNEL=ring|lite overrides (experiments).
+      const int lgrid = std::max(1, std::min(h->tsl_max_grid, h->n_ctiles));
+      const int tpc = (h->n_ctiles + lgrid - 1) / lgrid;
+      const char *kenv = getenv("MMPGO_TS_KERNEL");
+      const int lite_max = getenv("MMPGO_TS_LITE_MAX_TILES") ? atoi(getenv("MMPGO_TS_LITE_MAX_TILES")) : h->ts_lite_max_tiles;
+      bool lite = tpc <= std::min(lite_max, TSL_MAXT);
+      if (kenv && !strcmp(kenv, "ring")) lite = false;
+      if (kenv && !strcmp(kenv, "lite")) lite = tpc <= TSL_MAXT;
+      if (lite) {
+        ta.chunk = tpc;
+        if (h->tsl_plan_tpc != tpc) {
+          // shared-memory plan, in order of benefit per byte: the CTA's own z tiles, the tile
+          // records {x, p, Ap, diag}, the ELLPACK rows (of the fullest CTA)
+          const int64_t zb = (int64_t)tpc * CTILE * D * 8, vb = (int64_t)tpc * (3 * CTILE * D + CTILE) * 8;
+          int64_t eb = 0;
+          for (int c0 = 0; c0 < h->n_ctiles; c0 += tpc) {
+            const int c1 = std::min(c0 + tpc, h->n_ctiles);
+            eb = std::max<int64_t>(eb, (int64_t)(h->h_sell_ptr[(size_t)TS_WPT * c1] - h->h_sell_ptr[(size_t)TS_WPT * c0]) * 384);
+          }
+          int64_t used = 0;
+          h->tsl_stage_bytes = 0; h->tsl_vec_off = -1; h->tsl_z_off = -1;
+          const bool want_z = used + zb <= TSL_STAGE_MAX; if (want_z) used += zb;
+          const bool want_v = used + vb <= TSL_STAGE_MAX; if (want_v) used += vb;
+          const bool want_e = used + eb <= TSL_STAGE_MAX; if (want_e) used += eb;
+          int64_t off = 0;
+          if (want_e) { h->tsl_stage_bytes = (int)eb; off += (eb + 127) / 128 * 128; }
+          if (want_v) { h->tsl_vec_off = (int)off; off += vb; }
+          if (want_z) { h->tsl_z_off = (int)off; off += zb; }
+          h->tsl_dyn_bytes = (int)off;
+          h->tsl_plan_tpc = tpc;
+        }
+        const bool nores = getenv("MMPGO_TS_NORES") != nullptr;   // experiments: everything from L2
+        ta.lite_stage_bytes = nores ? 0 : h->tsl_stage_bytes;
+        ta.lite_vec_off = nores ? -1 : h->tsl_vec_off;
+        ta.lite_z_off = nores ? -1 : h->tsl_z_off;
+        ta.lite_dyn_bytes = nores ? 0 : h->tsl_dyn_bytes;
+        CK((cudaError_t)launch_tsolve_lite<D>(ta, (h->n_ctiles + tpc - 1) / tpc, h->stream));
+        h->ctr.launches++;
+        h->ctr.reserved[1]++;                                 // solves served by k_tsolve_lite
+        return 0;
+      }
       int grid = std::max(1, std::min(h->ts_max_grid, h->n_ctiles));
       if (h->ts_grid_override > 0) grid = std::min(grid, h->ts_grid_override);
       if (((int64_t)h->n_ctiles / ((int64_t)grid * ta.chunk) + 1) * ta.chunk > TS_MAXCT) {

@@ -101,7 +101,11 @@ struct Handle {
   double *ts_partials = nullptr, *ts_nstate = nullptr;
   unsigned long long *d_ts_stats = nullptr;
   int ts_max_grid = 0, ts_grid_override = 0;
+  int ts_lite_max_tiles = 16;    // use k_tsolve_lite when a CTA gets at most this many CTA tiles
+  int tsl_max_grid = 0;          // co-resident CTAs of k_tsolve_lite
   int64_t sell_entries = 0;
+  std::vector<int> h_sell_ptr;      // ELLPACK slice offsets (host copy: staging size of k_tsolve_lite)
+  int tsl_plan_tpc = -1, tsl_stage_bytes = 0, tsl_vec_off = -1, tsl_z_off = -1, tsl_dyn_bytes = 0;   // shared-memory plan for `tpc` tiles per CTA
   // per half-edge
   double *w_cur = nullptr, *w_prev = nullptr, *w_tmp = nullptr;
   // scalars

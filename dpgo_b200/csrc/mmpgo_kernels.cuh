@@ -160,9 +160,20 @@ struct TSolveArgs {
   const int *node_off;            // [nodes+1] own pose offsets
   double tol2;
   int max_iters;
+  // k_tsolve_lite, dynamic shared memory plan (byte offsets; what does not fit stays in L2):
+  int lite_stage_bytes;           // ELLPACK rows staged at offset 0 (0 = read from L2)
+  int lite_vec_off;               // tile records {x, p, Ap, diag} resident (-1 = in global memory)
+  int lite_z_off;                 // copy of the CTA's own z tiles (-1 = none)
+  int lite_dyn_bytes;             // total
 };
 template <int D> int launch_tsolve(const TSolveArgs &a, int grid, cudaStream_t s);
 template <int D> int tsolve_max_grid(int device);
+// small-shard variant (k_tsolve_lite): `chunk` = contiguous CTA tiles per CTA, `partials` holds two
+// buffers of [n_ct][4]
+constexpr int TSL_STAGE_MAX = 216 * 1024;   // dynamic shared memory of k_tsolve_lite (staged ELLPACK rows)
+constexpr int TSL_MAXT = 32;      // CTA tiles (hence node segments) one lite CTA can own
+template <int D> int launch_tsolve_lite(const TSolveArgs &a, int grid, cudaStream_t s);
+template <int D> int tsolve_lite_max_grid(int device);
 
 // ---- edge-parallel global objective (AMM-PGO*, DPGOStar.cpp:713-761) ----------
 struct EdgeRec {            // host-side staging record; the device keeps the fields as struct-of-arrays

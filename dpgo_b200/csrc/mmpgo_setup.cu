@@ -366,6 +366,7 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     sell_ptr[sl + 1] = sell_ptr[sl] + (c0 > 0 ? width : 0);
   }
   h->sell_entries = sell_ptr.back();
+  h->h_sell_ptr = sell_ptr;
   // per-tile records {x, p, Ap, diag} (one bulk copy per phase) and the packed ELLPACK rows
   const size_t RL = (size_t)3 * CTILE * d + CTILE;
   std::vector<double> rec((size_t)h->n_ctiles * RL, 0.0);
@@ -482,12 +483,14 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     // z is staged with a TS_HALO-tile halo on both sides: pad the array accordingly at each end
     if ((rc = dalloc(h, &h->ts_z_base, nv + (size_t)2 * TS_HALO * CTILE * d))) return rc;
     h->ts_z = h->ts_z_base + (size_t)TS_HALO * CTILE * d;
-    if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4))) return rc;
+    if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4 * 2))) return rc;   // two buffers (k_tsolve_lite)
     if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_sync, (size_t)2 * A + 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
     h->ts_max_grid = d == 2 ? tsolve_max_grid<2>(h->opt.device) : tsolve_max_grid<3>(h->opt.device);
     if (h->ts_max_grid <= 0) { set_error("occupancy query for the translation solve failed"); return MMPGO_ERR_CUDA; }
+    h->tsl_max_grid = d == 2 ? tsolve_lite_max_grid<2>(h->opt.device) : tsolve_lite_max_grid<3>(h->opt.device);
+    if (h->tsl_max_grid <= 0) { set_error("occupancy query for the small-shard translation solve failed"); return MMPGO_ERR_CUDA; }
   }
   double **wv[] = {&h->w_cur, &h->w_prev, &h->w_tmp};
   for (auto q : wv) if ((rc = dalloc(h, q, (size_t)nxe))) return rc;

@@ -50,6 +50,9 @@ __device__ __forceinline__ int atom_add_acq_rel(int *p, int v) {
   asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
   return o;
 }
+__device__ __forceinline__ void red_add_release(int *p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
@@ -564,6 +567,316 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
     ++tick;
   }
 }
+
+
+// =============================================================================
+// K2b, small-shard variant ("lite").  Same algorithm, data layout, per-pose arithmetic and
+// fixed-order reductions as k_tsolve (the two kernels give bit-identical solutions), but built
+// for the regime where a GPU holds so few poses per SM that an iteration is bound by the
+// rendezvous, not by HBM (<= ~250 k poses per GPU: 4 and 8 GPUs on the 1 M-pose graph):
+//   * every CTA owns a contiguous run of `chunk` CTA tiles; a group of four warps works on one
+//     tile with plain loads (the working set is L2 resident), no copy ring, no service warps;
+//   * one rendezvous per phase and node: arrive on the node's monotonic counter, spin until all
+//     CTAs that hold tiles of the node have arrived, then EVERY such CTA sums the node's
+//     per-tile partials itself (same fixed order => same scalars everywhere).  The chain
+//     "last arriver reduces -> publishes epoch -> pollers read coefficients -> dispatch" of the
+//     ring kernel (~10 us per phase) shrinks to atomic + poll + one read of the partials.
+// Partials are double buffered by round parity: a CTA that is already in round r+1 must not
+// overwrite what a slower CTA still sums for round r.
+// =============================================================================
+constexpr int TSL_MAXSEG = 32;
+constexpr int TSL_NG = 7;        // four-warp groups per lite CTA (one tile each at a time)    // node segments (runs of tiles of one active node) per CTA
+
+template <int D, int NG>
+__global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
+  typedef TSCfg<D> C;
+  constexpr int PB = (D + 1) * D;
+  constexpr int WPT = C::WPT;
+  const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
+  const int wi = wg % WPT, grp = wg / WPT;
+  const int tpc = a.chunk;
+  const int k0 = blockIdx.x * tpc, nb = max(0, min(tpc, a.n_ct - k0));
+  __shared__ int m_start[TSL_MAXT], m_cnt[TSL_MAXT], m_seg[TSL_MAXT], m_sell[TSL_MAXT][TS_WPT + 1];
+  __shared__ int sg_node[TSL_MAXSEG], sg_target[TSL_MAXSEG], sg_state[TSL_MAXSEG], sg_owner[TSL_MAXSEG];
+  __shared__ double sg_coef[TSL_MAXSEG], sg_rz[TSL_MAXSEG], sg_bb[TSL_MAXSEG], sg_it[TSL_MAXSEG];
+  __shared__ int n_seg_s;
+  __shared__ double red[NG][2][TS_WPT][3];
+
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    const int ct = k0 + k;
+    m_start[k] = __ldg(a.ct_start + ct); m_cnt[k] = __ldg(a.ct_cnt + ct);
+  }
+  for (int q = threadIdx.x; q < nb * (WPT + 1); q += blockDim.x) {
+    const int k = q / (WPT + 1), r = q % (WPT + 1);
+    m_sell[k][r] = __ldg(a.sell_ptr + WPT * (k0 + k) + r);
+  }
+  // the ELLPACK rows of this CTA's tiles are one contiguous run of sell_pack: staged in shared
+  // memory once per launch when they fit (a.lite_stage_bytes > 0), so that phase A is one
+  // shared-memory read + one L2 gather deep instead of two dependent L2 round trips
+  extern __shared__ __align__(128) unsigned char dyn[];
+  const int row_first = nb > 0 ? __ldg(a.sell_ptr + WPT * k0) : 0;
+  const bool staged = a.lite_stage_bytes > 0;
+  if (staged && nb > 0) {
+    const int row_end = __ldg(a.sell_ptr + WPT * (k0 + nb));
+    const int n16 = (row_end - row_first) * 24;                       // 384-byte rows as 16-byte words
+    const int4 *src = reinterpret_cast<const int4 *>(a.sell_pack + (size_t)row_first * 384);
+    int4 *dst = reinterpret_cast<int4 *>(dyn);
+    for (int q = threadIdx.x; q < n16; q += blockDim.x) dst[q] = __ldg(src + q);
+  }
+  // tile-private solver state {x, p, Ap, diag} and a copy of the CTA's own z tiles live in shared
+  // memory when they fit (a.lite_vec_off / a.lite_z_off >= 0): per iteration only the z values
+  // and the gathers of neighbours owned by other CTAs touch L2
+  const bool vres = a.lite_vec_off >= 0, zres = a.lite_z_off >= 0;
+  double *vec_s = reinterpret_cast<double *>(dyn + (vres ? a.lite_vec_off : 0));
+  double *z_s = reinterpret_cast<double *>(dyn + (zres ? a.lite_z_off : 0));
+  const int zbase = WPT * k0 * (32 * D);                   // slot of the CTA's first pose
+  const unsigned zlim = zres ? (unsigned)(nb * C::VEC) : 0u;
+  if (vres) {
+    for (int q = threadIdx.x; q < nb * CTILE; q += blockDim.x) {
+      const int k = q / CTILE, r = q % CTILE;
+      vec_s[(size_t)k * C::RL + 3 * C::VEC + r] = __ldg(a.rec + (size_t)(k0 + k) * C::RL + 3 * C::VEC + r);
+    }
+  }
+  if (threadIdx.x == 0) {
+    // segments: runs of this CTA's tiles that belong to one active node
+    int ns = 0, prev = -1;
+    for (int k = 0; k < nb; ++k) {
+      const int nd = __ldg(a.ct_node + k0 + k);
+      const bool on = !(a.active && !__ldg(a.active + nd));
+      if (!on) { m_seg[k] = -1; continue; }
+      if (nd != prev) {
+        const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
+        sg_node[ns] = nd;
+        sg_target[ns] = (ce - 1) / tpc - cb / tpc + 1;      // CTAs that hold tiles of the node
+        sg_owner[ns] = (cb >= k0 && cb < k0 + nb) ? 1 : 0;  // this CTA reports the node's statistics
+        sg_state[ns] = 0; sg_coef[ns] = 0.0; sg_rz[ns] = 0.0; sg_bb[ns] = 0.0; sg_it[ns] = 0.0;
+        prev = nd; ++ns;
+      }
+      m_seg[k] = ns - 1;
+    }
+    n_seg_s = ns;
+  }
+  __syncthreads();
+  const int n_seg = n_seg_s;
+  if (n_seg == 0) return;
+  for (int round = 0;; ++round) {
+    double *pbuf = a.partials + (size_t)(round & 1) * a.n_ct * 4;
+    // ---------------- the phase, one tile per group at a time ----------------
+    for (int k = grp; k < nb; k += NG) {
+      const int seg = m_seg[k];
+      if (seg < 0) continue;
+      const int st = sg_state[seg];
+      if (st == 2) continue;
+      const int kd = st == 1 ? 3 : (round == 0 ? 0 : ((round & 1) ? 1 : 2));
+      const double coef = sg_coef[seg];
+      const int ct = k0 + k;
+      const bool valid = 32 * wi + lane < m_cnt[k];
+      const int p = m_start[k] + 32 * wi + lane;
+      const size_t vb = (size_t)(WPT * ct + wi) * (32 * D) + lane;
+      double part[3] = {0.0, 0.0, 0.0};
+      double *rc = vres ? vec_s + (size_t)k * C::RL : a.rec + (size_t)ct * C::RL;
+      const int lo = wi * (32 * D) + lane;
+      double *zown = z_s + (size_t)k * C::VEC + lo;        // this pose in the CTA's z copy (zres)
+      if (kd == 3) {
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) a.xio[(size_t)p * PB + c] = -rc[lo + 32 * c];
+        }
+      } else if (kd == 0) {
+        if (valid) {
+          double x0[D], acc[D], b[D];
+          const double dg = __ldg(a.d00 + p);
+#pragma unroll
+          for (int c = 0; c < D; ++c) { x0[c] = 0.0; acc[c] = 0.0; b[c] = a.rhs[(size_t)p * D + c]; }
+          if (a.warm) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) { x0[c] = -a.xio[(size_t)p * PB + c]; acc[c] = dg * x0[c]; }
+            const int e0 = __ldg(a.rowptr + p), e1 = __ldg(a.rowptr + p + 1);
+            for (int e = e0; e < e1; ++e) {
+              const double av = __ldg(a.a00 + e);
+              const double *xq = a.xio + (size_t)__ldg(a.col + e) * PB;
+#pragma unroll
+              for (int c = 0; c < D; ++c) acc[c] = fma(av, -xq[c], acc[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            const double rv = b[c] - acc[c], zv = rv / dg;
+            rc[lo + 32 * c] = x0[c];
+            a.z[vb + 32 * c] = zv;
+            if (zres) zown[32 * c] = zv;
+            rc[C::VEC + lo + 32 * c] = 0.0;
+            rc[2 * C::VEC + lo + 32 * c] = 0.0;
+            part[0] += rv * zv; part[1] += b[c] * b[c]; part[2] += rv * rv;
+          }
+        }
+      } else if (kd == 1) {
+        const double beta = coef;
+        const double *sp = rc + C::VEC + lo;
+        const double *sap = sp + C::VEC;
+        const int r0 = m_sell[k][0], rows = m_sell[k][WPT] - r0;
+        const int s0 = m_sell[k][wi] - r0, s1 = m_sell[k][wi + 1] - r0;
+        const unsigned char *pack = staged ? dyn + (size_t)(r0 - row_first) * 384 : a.sell_pack + (size_t)r0 * 384;
+        const double *sval = reinterpret_cast<const double *>(pack);
+        const int *scol = reinterpret_cast<const int *>(pack + (size_t)rows * 256);
+        double zo[D], acc[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) zo[c] = zres ? zown[32 * c] : __ldcg(a.z + vb + 32 * c);
+        const double dg = rc[3 * C::VEC + 32 * wi + lane];
+        // gathers four entries at a time (twelve loads in flight per thread; the register budget
+        // of a 1024-thread CTA); the accumulation order is that of k_tsolve
+        constexpr int EB = 4;
+        double zq[EB][D];
+        auto gather = [&](int s) {
+#pragma unroll
+          for (int q = 0; q < EB; ++q) {
+            const int slot = s + q < s1 ? scol[(s + q) * 32 + lane] : (int)vb;
+            const unsigned rel = (unsigned)(slot - zbase);
+            if (rel < zlim) {                               // neighbour owned by this CTA
+#pragma unroll
+              for (int c = 0; c < D; ++c) zq[q][c] = z_s[rel + 32 * c];
+            } else {
+#pragma unroll
+              for (int c = 0; c < D; ++c) zq[q][c] = __ldcg(a.z + (size_t)slot + 32 * c);
+            }
+          }
+        };
+        if (s0 < s1) gather(s0);
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = dg * zo[c];
+        for (int s = s0; s < s1; s += EB) {
+#pragma unroll
+          for (int q = 0; q < EB; ++q) {
+            const double av = s + q < s1 ? sval[(s + q) * 32 + lane] : 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] = fma(av, zq[q][c], acc[c]);
+          }
+          if (s + EB < s1) gather(s + EB);
+        }
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            const double apv = acc[c] + beta * sap[32 * c];
+            const double pv = zo[c] + beta * sp[32 * c];
+            rc[2 * C::VEC + lo + 32 * c] = apv;
+            rc[C::VEC + lo + 32 * c] = pv;
+            part[0] += pv * apv;
+          }
+        }
+      } else {
+        const double alpha = coef;
+        const double *sx = rc + lo;
+        const double *sp = sx + C::VEC, *sap = sx + 2 * C::VEC;
+        const double dg = rc[3 * C::VEC + 32 * wi + lane];
+        if (valid) {
+          double xo[D], po[D], apo[D], zo[D];              // all loads first: one round trip
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            xo[c] = sx[32 * c]; po[c] = sp[32 * c]; apo[c] = sap[32 * c];
+            zo[c] = zres ? zown[32 * c] : __ldcg(a.z + vb + 32 * c);
+          }
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            const double xv = xo[c] + alpha * po[c];
+            const double rv = dg * zo[c] - alpha * apo[c];
+            const double zv = rv / dg;
+            rc[lo + 32 * c] = xv;
+            a.z[vb + 32 * c] = zv;
+            if (zres) zown[32 * c] = zv;
+            part[0] += rv * zv; part[2] += rv * rv;
+          }
+        }
+      }
+      if (kd != 3) {
+        const int rb = (k / NG) & 1;                       // red is double buffered per group
+        const double p0 = warp_sum(part[0]), p1 = warp_sum(part[1]), p2 = warp_sum(part[2]);
+        if (lane == 0) { red[grp][rb][wi][0] = p0; red[grp][rb][wi][1] = p1; red[grp][rb][wi][2] = p2; }
+        consumer_barrier(grp);                             // red[grp][rb] complete
+        if (wi == 0 && lane < 3) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int q = 0; q < WPT; ++q) sacc += red[grp][rb][q][lane];
+          pbuf[(size_t)ct * 4 + lane] = sacc;
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- rendezvous + node scalars, one warp per segment ----------------
+    // all arrivals first, then the waits (a warp may serve several segments)
+    for (int s = wg; s < n_seg; s += NG * WPT) {
+      // release: the stores of the whole CTA (ordered before this by the barrier above)
+      if (sg_state[s] == 0 && lane == 0) red_add_release(a.cnt + sg_node[s], 1);
+    }
+    __syncwarp();
+    for (int s = wg; s < n_seg; s += NG * WPT) {
+      const int st = sg_state[s];
+      if (st == 1) { if (lane == 0) sg_state[s] = 2; continue; }
+      if (st != 0) continue;
+      const int nd = sg_node[s];
+      const int target = sg_target[s] * (round + 1);
+      {
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (ld_relaxed(a.cnt + nd) < target) {
+          if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();   // never hang the GPU
+        }
+        fence_acq_rel();                                   // acquire: what the other CTAs stored before arriving
+      }
+      const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
+      bool done = false;
+      if (round == 0) {
+        double sm[3];
+        node_sum<3>(pbuf, cb, ce, lane, sm);
+        if (lane == 0) { sg_rz[s] = sm[0]; sg_bb[s] = sm[1]; sg_it[s] = 0.0; sg_coef[s] = 0.0; }
+        done = !(sm[0] > 0.0) || !(sm[2] > a.tol2 * sm[1]);
+      } else if (round & 1) {
+        double sm[1];
+        node_sum<1>(pbuf, cb, ce, lane, sm);
+        if (sm[0] > 0.0) { if (lane == 0) sg_coef[s] = sg_rz[s] / sm[0]; }      // alpha for phase B
+        else done = true;
+      } else {
+        double sm[3];
+        node_sum<3>(pbuf, cb, ce, lane, sm);
+        const double rz = sg_rz[s], bb = sg_bb[s], it = sg_it[s] + 1.0;
+        __syncwarp();
+        if (lane == 0) { sg_coef[s] = sm[0] / rz; sg_rz[s] = sm[0]; sg_it[s] = it; }   // beta for phase A
+        done = !(sm[2] > a.tol2 * bb) || !(sm[0] > 0.0) || it >= (double)a.max_iters;
+      }
+      if (done && lane == 0) {
+        sg_state[s] = 1;                                   // publish in the next pass, then retire
+        if (sg_owner[s] && a.stats) {
+          const unsigned long long it = (unsigned long long)(round / 2);
+          atomicAdd(a.stats, it);
+          atomicAdd(a.stats + 1, it * (unsigned long long)(__ldg(a.node_off + nd + 1) - __ldg(a.node_off + nd)));
+        }
+      }
+    }
+    __syncthreads();
+    int live = 0;
+    for (int s = 0; s < n_seg; ++s) live += sg_state[s] != 2;
+    if (live == 0) break;
+  }
+}
+
+template <int D> int launch_tsolve_lite(const TSolveArgs &a, int grid, cudaStream_t s) {
+  TSolveArgs args = a;
+  void *params[] = {&args};
+  return (int)cudaLaunchCooperativeKernel((const void *)k_tsolve_lite<D, TSL_NG>, dim3(grid), dim3(TSL_NG * CTILE), params,
+                                          (size_t)a.lite_dyn_bytes, s);
+}
+template int launch_tsolve_lite<2>(const TSolveArgs &, int, cudaStream_t);
+template int launch_tsolve_lite<3>(const TSolveArgs &, int, cudaStream_t);
+
+template <int D> int tsolve_lite_max_grid(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaFuncSetAttribute(k_tsolve_lite<D, TSL_NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSL_STAGE_MAX) != cudaSuccess)
+    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tsolve_lite<D, TSL_NG>, TSL_NG * CTILE, TSL_STAGE_MAX) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  return per_sm * sms;
+}
+template int tsolve_lite_max_grid<2>(int);
+template int tsolve_lite_max_grid<3>(int);
 
 template <int D> int launch_tsolve(const TSolveArgs &a, int grid, cudaStream_t s) {
   TSolveArgs args = a;

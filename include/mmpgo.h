@@ -95,7 +95,7 @@ typedef struct mmpgo_counters {
   int64_t solve_calls, solve_iters;   /* K2b G00 solves / PCG iterations */
   int64_t tcg_iterations, tnt_iterations;
   int64_t vector_passes;
-  int64_t reserved[7];
+  int64_t reserved[7];            /* [0] pose-iterations of the G00 PCG, [1] solves served by the small-shard kernel */
 } mmpgo_counters;
 
 const char *mmpgo_version(void);

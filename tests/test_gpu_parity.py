@@ -195,23 +195,57 @@ def test_projection_bitwise_vs_reference_avx2(d):
         assert np.array_equal(ref.project(A, nofma=True), want)
 
 
+TS_KERNELS = ["ring", "lite"]    # copy-ring kernel (large shards) / rendezvous-lean kernel (small shards)
+
+
+@pytest.mark.parametrize("kernel", TS_KERNELS)
 @pytest.mark.parametrize("alg,loss", [("hash", "trivial"), ("star", "huber")])
-def test_persistent_solve_multi_tile_nodes(alg, loss):
+def test_persistent_solve_multi_tile_nodes(alg, loss, kernel, monkeypatch):
     """Nodes spanning many CTA tiles and several chunks of the persistent translation solve
     (1600 poses per node, ragged last tile), masked sub-sets of nodes in the restart paths."""
+    monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
     g, _, X0 = D.grid3d(20, 20, 12, seed=8)
     _check(parity.run_both(g, 3, X0, 6, loss=loss, algorithm=alg, dense_solve_max_n=0), 3)
 
 
-def test_persistent_solve_se2():
+@pytest.mark.parametrize("kernel", TS_KERNELS)
+def test_persistent_solve_se2(kernel, monkeypatch):
+    monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
     g, _, X0 = D.city2d(40, 30, seed=6)
     _check(parity.run_both(g, 5, X0, 6, loss="gm", dense_solve_max_n=0), 2)
 
 
-def test_persistent_solve_many_small_nodes():
+@pytest.mark.parametrize("kernel", TS_KERNELS)
+def test_persistent_solve_many_small_nodes(kernel, monkeypatch):
     # more nodes than a CTA has segments to spare: 40 nodes of 45 poses, one tile each
+    monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
     g, _, X0 = D.grid3d(15, 12, 10, seed=12)
     _check(parity.run_both(g, 40, X0, 5, dense_solve_max_n=0), 3)
+
+
+def _run_star(g, X0, nodes, iters):
+    drv = D.DPGOStar(g, nodes, D.Options(loss="trivial", dense_solve_max_n=0))
+    assert drv.initialize(X0) == 0 and drv.update() == 0
+    for _ in range(iters):
+        assert drv.iterate() == 0, D.load().mmpgo_last_error()
+        assert drv.communicate() == 0 and drv.update() == 0
+    c = drv.counters()
+    return drv.X(), drv.objective()[0], c.solve_iters
+
+
+@pytest.mark.parametrize("dims,nodes", [((30, 30, 30), 5), ((24, 24, 16), 3)])
+def test_tsolve_lite_bitwise_equals_ring(dims, nodes, monkeypatch):
+    """The two translation-solve kernels share the data layout, the per-pose arithmetic and the
+    fixed-order reductions: same iterates to the last bit, same iteration counts.  The first case
+    gives every lite CTA two CTA tiles, some straddling a node boundary (two segments per CTA)."""
+    g, _, X0 = D.grid3d(*dims, seed=21)
+    out = {}
+    for kernel in TS_KERNELS:
+        monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
+        out[kernel] = _run_star(g, X0, nodes, 3)
+    assert out["ring"][2] == out["lite"][2] and out["ring"][2] > 0
+    assert out["ring"][1] == out["lite"][1]
+    assert np.array_equal(out["ring"][0], out["lite"][0]), np.abs(out["ring"][0] - out["lite"][0]).max()
 
 
 @pytest.mark.parametrize("alg,loss", [("hash", "gm"), ("star", "welsch")])
