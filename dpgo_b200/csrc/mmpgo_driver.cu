@@ -70,6 +70,22 @@ static int reduce_to_host(Handle *h, const double **out) {
   *out = h->h_pinned;
   return 0;
 }
+// Deferred variant: several kernels' per-node sums are reduced into separate slots and read back
+// with ONE host synchronisation (the tile partials buffer is reused as soon as its reduce kernel
+// has been enqueued).  slot < RED_SLOTS.
+static int reduce_async(Handle *h, int slot) {
+  double *d = h->d_slot + (size_t)slot * h->A * NS;
+  launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, d, h->stream);
+  h->ctr.launches++;
+  CK(cudaMemcpyAsync(h->h_slot + (size_t)slot * h->A * NS, d, sizeof(double) * h->A * NS, cudaMemcpyDeviceToHost,
+                     h->stream));
+  return 0;
+}
+static const double *slot_host(Handle *h, int slot) { return h->h_slot + (size_t)slot * h->A * NS; }
+static int host_sync(Handle *h) {
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 static int upload_coef(Handle *h, const std::vector<double> &c) {
   CK(cudaMemcpyAsync(h->d_coef, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice, h->stream));
   return 0;
@@ -374,12 +390,17 @@ template <int D> struct Drv {
       a.x = x; a.g = g; a.out = h->nab; a.out2 = h->grad;
       launch_gpass<D>(G_REDGRAD, tl, a, h->stream);
       h->ctr.launches++; h->ctr.intra_passes++;
-      const double *s; RC(reduce_to_host(h, &s));
-      for (int n = 0; n < A; ++n) if (mm[n]) { gnorm[n] = std::sqrt(s[n * NS]); fx[n] = s[n * NS + 1]; }
+      // gradient norm and preconditioned gradient norm: two kernels, one host synchronisation
+      RC(reduce_async(h, 0));
       if (o.preconditioner != MMPGO_PRECON_NONE) {
         RC(vec(h, V_PRECOND, mm, h->grad, nullptr, nullptr, nullptr, nullptr, nullptr, x));
-        RC(reduce_to_host(h, &s));
-        for (int n = 0; n < A; ++n) if (mm[n]) pgnorm[n] = std::sqrt(s[n * NS]);
+        RC(reduce_async(h, 1));
+      }
+      RC(host_sync(h));
+      const double *s = slot_host(h, 0), *s1 = slot_host(h, 1);
+      for (int n = 0; n < A; ++n) if (mm[n]) { gnorm[n] = std::sqrt(s[n * NS]); fx[n] = s[n * NS + 1]; }
+      if (o.preconditioner != MMPGO_PRECON_NONE) {
+        for (int n = 0; n < A; ++n) if (mm[n]) pgnorm[n] = std::sqrt(s1[n * NS]);
       } else {
         for (int n = 0; n < A; ++n) if (mm[n]) pgnorm[n] = gnorm[n];
       }
@@ -399,18 +420,32 @@ template <int D> struct Drv {
       // trial point: retract, recover translations, evaluate
       RC(vec(h, V_RETRACT, run, x, h->cg_s, h->xprop, nullptr, nullptr, nullptr, nullptr));   // writes the whole pose block
       RC(recover_t(h, h->xprop, g, run));
-      RC(eval_G(h, h->xprop, g, run, fprop));
-      // predicted decrease needs grad.h and h.Hess h.  H is linear and the step is s = sum alpha_k p_k,
-      // so H s was accumulated from the H p_k of the tCG iterations (cg_Hs): no further
-      // Hessian-vector product (the reference recomputes it, TNT.h:514-515; same value up to rounding)
+      // G at the trial point, grad.h, |h|^2 and h.Hess h: three kernels, one host synchronisation.
+      // H is linear and the step is s = sum alpha_k p_k, so H s was accumulated from the H p_k of the
+      // tCG iterations (cg_Hs): no further Hessian-vector product (the reference recomputes it,
+      // TNT.h:514-515; same value up to rounding)
+      {
+        Tiles tl; RC(make_tiles(h, run, &tl));
+        GPassArgs a = gargs(h);
+        a.x = h->xprop; a.g = g;
+        launch_gpass<D>(G_EVAL, tl, a, h->stream);
+        h->ctr.launches++; h->ctr.intra_passes++;
+        RC(reduce_async(h, 0));
+      }
       RC(vec(h, V_DOTS, run, h->grad, h->cg_s, nullptr, nullptr, nullptr, nullptr, nullptr));
-      const double *s; RC(reduce_to_host(h, &s));
-      std::vector<double> gh(A, 0);
-      ss.assign(A, 0.0); sHs.assign(A, 0.0);
-      for (int n = 0; n < A; ++n) { gh[n] = s[n * NS]; ss[n] = s[n * NS + 2]; }
+      RC(reduce_async(h, 1));
       RC(vec(h, V_DOTS, run, h->cg_s, h->cg_Hs, nullptr, nullptr, nullptr, nullptr, nullptr));
-      RC(reduce_to_host(h, &s));
-      for (int n = 0; n < A; ++n) sHs[n] = s[n * NS];
+      RC(reduce_async(h, 2));
+      RC(host_sync(h));
+      std::vector<double> gh(A, 0);
+      fprop.assign(A, 0.0); ss.assign(A, 0.0); sHs.assign(A, 0.0);
+      {
+        const double *s0 = slot_host(h, 0), *s1 = slot_host(h, 1), *s2 = slot_host(h, 2);
+        for (int n = 0; n < A; ++n) {
+          if (run[n]) fprop[n] = s0[n * NS];
+          gh[n] = s1[n * NS]; ss[n] = s1[n * NS + 2]; sHs[n] = s2[n * NS];
+        }
+      }
       Mask accm(A, 0), requad(A, 0);
       for (int n = 0; n < A; ++n) if (run[n]) {
         h->st[n].tcg_iterations += inner[n];
@@ -476,16 +511,18 @@ template <int D> struct Drv {
     }
     launch_inter<D>(trivial ? I_TRIVIAL : I_ROBUST, tl, ia, h->stream);
     h->ctr.launches++; h->ctr.inter_passes++;
-    const double *s; RC(reduce_to_host(h, &s));
-    std::vector<double> i0(A), i1(A), i2(A), i3(A), i4(A), i5(A);
-    for (int n = 0; n < A; ++n) { i0[n] = s[n*NS]; i1[n] = s[n*NS+1]; i2[n] = s[n*NS+2]; i3[n] = s[n*NS+3]; i4[n] = s[n*NS+4]; i5[n] = s[n*NS+5]; }
-    // gradient pass: Dfobj = g + G x
+    RC(reduce_async(h, 0));
+    // gradient pass: Dfobj = g + G x   (its sums are read back with those of K1: one synchronisation)
     GPassArgs a = gargs(h);
     a.x = Xk; a.g = gk; a.out = Dfk;
-    RC(make_tiles(h, m, &tl));
     launch_gpass<D>(G_GRAD, tl, a, h->stream);
     h->ctr.launches++; h->ctr.intra_passes++;
-    RC(reduce_to_host(h, &s));
+    RC(reduce_async(h, 1));
+    RC(host_sync(h));
+    const double *s = slot_host(h, 0);
+    std::vector<double> i0(A), i1(A), i2(A), i3(A), i4(A), i5(A);
+    for (int n = 0; n < A; ++n) { i0[n] = s[n*NS]; i1[n] = s[n*NS+1]; i2[n] = s[n*NS+2]; i3[n] = s[n*NS+3]; i4[n] = s[n*NS+4]; i5[n] = s[n*NS+5]; }
+    s = slot_host(h, 1);
     const double xi = o.regularizer;
     for (int n = 0; n < A; ++n) if (m[n]) {
       NodeState &st = h->st[n];
@@ -603,8 +640,20 @@ template <int D> struct Drv {
       h->st[n].refined = refined[n];
     }
     std::vector<double> dist2, Gkh, Gk, fx;
-    RC(amm_proximal(h, allm, &dist2));
-    RC(eval_G(h, h->Xakh, gk, allm, Gkh));
+    // |X^{k+1/2} - X^k|^2 (K3) and G(X^{k+1/2}) (K2): two kernels, one host synchronisation
+    RC(amm_proximal(h, allm, nullptr));
+    RC(reduce_async(h, 0));
+    {
+      Tiles tl; RC(make_tiles(h, allm, &tl));
+      GPassArgs a = gargs(h);
+      a.x = h->Xakh; a.g = gk;
+      launch_gpass<D>(G_EVAL, tl, a, h->stream);
+      h->ctr.launches++; h->ctr.intra_passes++;
+      RC(reduce_async(h, 1));
+    }
+    RC(host_sync(h));
+    dist2.assign(A, 0.0); Gkh.assign(A, 0.0);
+    for (int n = 0; n < A; ++n) { dist2[n] = slot_host(h, 0)[n * NS]; Gkh[n] = slot_host(h, 1)[n * NS]; }
     std::vector<double> minG(A);
     for (int n = 0; n < A; ++n) { Gkh[n] += h->st[n].f; minG[n] = h->st[n].Fk[0] - o.psi * dist2[n]; }
     // Xak.R = Xakh.R ; t = recover(g_extrapolated)

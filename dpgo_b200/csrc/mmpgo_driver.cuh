@@ -42,6 +42,7 @@ template <typename T> struct DevBuf {
   size_t n = 0;
 };
 
+constexpr int RED_SLOTS = 4;
 struct Handle {
   mmpgo_options opt;
   int d = 0;
@@ -113,6 +114,7 @@ struct Handle {
   double *d_partials = nullptr, *d_node_scal = nullptr, *d_coef = nullptr, *d_gamma = nullptr;
   double *d_block_partials = nullptr, *d_scalar = nullptr;
   double *h_pinned = nullptr;   // pinned staging (A*NS + A*MAXC + misc)
+  double *d_slot = nullptr, *h_slot = nullptr;   // RED_SLOTS x [A][NS] per-node sums read back with one synchronisation
   int *h_pinned_i = nullptr;
   // AMM-PGO* global state (DPGOStar.cpp:126-213)
   double starF = 0.0, star_fobj = 0.0;

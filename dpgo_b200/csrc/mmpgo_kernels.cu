@@ -97,9 +97,13 @@ k_gpass(Tiles tl, GPassArgs a) {
     const int e0 = a.rowptr[p], e1 = a.rowptr[p + 1];
     // two entries per trip: the loads of both (column -> neighbour block is a dependent chain) are
     // in flight together
+    // the column index of the next entry is fetched one trip ahead, so that the dependent
+    // column -> neighbour-block gather costs one round trip per trip instead of two
+    int qn = e0 < e1 ? __ldg(a.col + e0) : 0;
 #pragma unroll 2
     for (int e = e0; e < e1; ++e) {
-      const int q = __ldg(a.col + e);
+      const int q = qn;
+      qn = e + 1 < e1 ? __ldg(a.col + e + 1) : 0;
       const double *b = a.blk + (size_t)e * BB + row * R;
       // 128-bit loads: the neighbour's pose block (16-byte aligned for d = 2 and 3) and, for
       // d = 3, this thread's row of the 4 x 4 block

@@ -51,6 +51,8 @@ void driver_free(Handle *h) {
   h->allocs.clear();
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   h->h_pinned = nullptr;
+  if (h->h_slot) cudaFreeHost(h->h_slot);
+  h->h_slot = nullptr;
 }
 
 // the `index` lambda of read_g2o, DPGO_utils.cpp:147-158
@@ -502,6 +504,9 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   if ((rc = dalloc(h, &h->d_block_partials, (size_t)148 * 8 + 8))) return rc;
   if ((rc = dalloc(h, &h->d_scalar, (size_t)8))) return rc;
   CK(cudaMallocHost((void **)&h->h_pinned, sizeof(double) * ((size_t)A * (2 * NS + 8) + 64)));
+  if ((rc = dalloc(h, &h->d_slot, (size_t)RED_SLOTS * A * NS))) return rc;
+  CK(cudaMallocHost((void **)&h->h_slot, sizeof(double) * (size_t)RED_SLOTS * A * NS));
+  std::memset(h->h_slot, 0, sizeof(double) * (size_t)RED_SLOTS * A * NS);
   CK(cudaStreamSynchronize(h->stream));
   h->st.assign(A, NodeState());
   h->graph_set = true;
