@@ -116,6 +116,23 @@ template <int D> struct Drv {
     return 0;
   }
 
+  // the same for two pose arrays in ONE all-to-all (per-peer chunks [a | b])
+  static int halo_exchange2(Handle *h, double *xa, double *xb) {
+    if (h->world <= 1) return 0;
+    launch_copy_poses<D>(h->n_send, h->d_send_idx, h->d_send2_a, xa, h->d_send2, h->stream);
+    launch_copy_poses<D>(h->n_send, h->d_send_idx, h->d_send2_b, xb, h->d_send2, h->stream);
+    h->ctr.launches += 2;
+    h->halo_exchanges++;
+    if (h->exchange_fn(h->cb_user, h->d_send2, h->send_dbl2.data(), h->d_recv2, h->recv_dbl2.data()) != 0) {
+      set_error("exchange callback failed");
+      return MMPGO_ERR_ARG;
+    }
+    launch_copy_poses<D>(h->NH, h->d_recv2_a, h->d_halo_row, h->d_recv2, xa, h->stream);
+    launch_copy_poses<D>(h->NH, h->d_recv2_b, h->d_halo_row, h->d_recv2, xb, h->stream);
+    h->ctr.launches += 2;
+    return 0;
+  }
+
   static GPassArgs gargs(Handle *h, const double *diag = nullptr) {
     GPassArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -804,8 +821,7 @@ template <int D> struct Drv {
     // after the other; X^{k+1} does not depend on the outcome of the first test)
     double fobjh, fobj, dh, dp;
     {
-      RC(halo_exchange(h, h->Xakh));
-      RC(halo_exchange(h, Xak));
+      RC(halo_exchange2(h, h->Xakh, Xak));
       int nb = 0;
       launch_edge_objective<D>(h->n_edges_owned, h->d_eidx, h->d_eval, h->Xakh, o.loss, o.loss_reg, h->d_block_partials, &nb, h->stream);
       launch_sum_blocks(nb, h->d_block_partials, h->d_scalar, h->stream);
@@ -868,6 +884,9 @@ template <int D> struct Drv {
     }
     h->star_fobj = fobj;
     h->starF = h->starF * (1 - o.eta[0]) + fobj * o.eta[0];
+    // every path above ends with a halo exchange of the final X^{k+1} (the merged exchange, or the
+    // one inside edge_objective after a restart / safeguard): communicate() need not repeat it
+    h->next_halo_current = true;
     return 0;
   }
 
@@ -887,6 +906,7 @@ template <int D> struct Drv {
   static int communicate(Handle *h) {
     const int old_km1 = h->ikm1;
     h->ikm1 = h->ik; h->ik = h->iak; h->iak = old_km1;
+    if (h->next_halo_current) { h->next_halo_current = false; return 0; }
     return halo_exchange(h, h->X[h->ik]);
   }
 };
@@ -923,6 +943,7 @@ int driver_initialize(Handle *h, const double *X, int64_t ldx) {
   if (ldx < (int64_t)(h->d + 1) * h->N) { set_error("ldx too small"); return MMPGO_ERR_ARG; }
   RC(stage_upload(h, X, ldx));
   h->ik = 0; h->ikm1 = 1; h->iak = 2; h->icur = 0;
+  h->next_halo_current = false;
   pack_dev(h, h->X[0], h->X[1], h->X[2], h->Xakh, h->xprop);
   CK(cudaMemsetAsync(h->tdot_prev, 0, sizeof(double) * (size_t)h->NO * (h->d + 1) * h->d, h->stream));
   for (auto &s : h->st) { s = NodeState(); s.updated = false; }

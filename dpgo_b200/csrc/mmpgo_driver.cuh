@@ -127,6 +127,11 @@ struct Handle {
   int *d_send_idx = nullptr;
   int64_t n_send = 0;
   double *d_send = nullptr;
+  // two-array exchange: per-peer chunks [array a | array b]
+  std::vector<int64_t> send_dbl2, recv_dbl2;
+  int *d_send2_a = nullptr, *d_send2_b = nullptr, *d_recv2_a = nullptr, *d_recv2_b = nullptr, *d_halo_row = nullptr;
+  double *d_send2 = nullptr, *d_recv2 = nullptr;
+  bool next_halo_current = false;   // the halo rows of X^{k+1} already hold the peers' final X^{k+1}
   mmpgo_exchange_fn exchange_fn = nullptr;
   mmpgo_allreduce_fn allreduce_fn = nullptr;
   mmpgo_allreduce_dev_fn allreduce_dev_fn = nullptr;

@@ -1112,6 +1112,23 @@ template <int D> void launch_scatter_poses(int64_t n, const int *idx, const doub
   const int64_t tot = n * Dim<D>::PB;
   k_scatter_poses<D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(n, idx, src, dst);
 }
+template <int D>
+__global__ void k_copy_poses(int64_t n, const int *src_idx, const int *dst_idx, const double *src, double *dst) {
+  constexpr int PB = Dim<D>::PB;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * PB) return;
+  const int64_t p = i / PB;
+  const int k = (int)(i % PB);
+  dst[(size_t)dst_idx[p] * PB + k] = src[(size_t)src_idx[p] * PB + k];
+}
+template <int D>
+void launch_copy_poses(int64_t n, const int *src_idx, const int *dst_idx, const double *src, double *dst, cudaStream_t s) {
+  if (n <= 0) return;
+  const int64_t tot = n * Dim<D>::PB;
+  k_copy_poses<D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(n, src_idx, dst_idx, src, dst);
+}
+template void launch_copy_poses<2>(int64_t, const int *, const int *, const double *, double *, cudaStream_t);
+template void launch_copy_poses<3>(int64_t, const int *, const int *, const double *, double *, cudaStream_t);
 template void launch_gather_poses<2>(int64_t, const int *, const double *, double *, cudaStream_t);
 template void launch_gather_poses<3>(int64_t, const int *, const double *, double *, cudaStream_t);
 template void launch_scatter_poses<2>(int64_t, const int *, const double *, double *, cudaStream_t);

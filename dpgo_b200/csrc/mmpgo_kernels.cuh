@@ -206,6 +206,9 @@ template <int D> void launch_dense_solve(int num_nodes, const int *node_off, con
 // halo pack / unpack (DPGOHash::receive wire format, DPGOHash.cpp:45-82)
 template <int D> void launch_gather_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);
 template <int D> void launch_scatter_poses(int64_t n, const int *idx, const double *src, double *dst, cudaStream_t s);
+// dst pose dst_idx[i] = src pose src_idx[i]  (pack / unpack of the two-array halo exchange)
+template <int D> void launch_copy_poses(int64_t n, const int *src_idx, const int *dst_idx, const double *src, double *dst,
+                                        cudaStream_t s);
 
 // global iterate (column-major, rows [t; R blocks]) <-> pose blocks, on the device
 template <int D> void launch_pack_poses(int64_t n, const int64_t *gid, const double *X, int64_t ld, int64_t N,

@@ -583,6 +583,30 @@ int driver_set_sharding(Handle *h, int rank, int world, const int32_t *rnb, mmpg
   int rc = 0;
   if ((rc = upload(h, &h->d_send_idx, idx))) return rc;
   if ((rc = dalloc(h, &h->d_send, (size_t)h->n_send * PB))) return rc;
+  // two-array exchange (AMM-PGO*: X^{k+1/2} and X^{k+1} travel in ONE all-to-all): per peer the
+  // chunk is [poses of array a | poses of array b]; index maps for the pack / unpack copies
+  {
+    std::vector<int> sa, sb, ra, rb, hrow;
+    int64_t so = 0, ro = 0;
+    for (int q = 0; q < world; ++q) {
+      const int64_t sc = h->send_poses[q], rcq = h->recv_poses[q];
+      for (int64_t i = 0; i < sc; ++i) { sa.push_back((int)(2 * so + i)); sb.push_back((int)(2 * so + sc + i)); }
+      for (int64_t i = 0; i < rcq; ++i) {
+        ra.push_back((int)(2 * ro + i)); rb.push_back((int)(2 * ro + rcq + i));
+        hrow.push_back((int)(h->NO + ro + i));
+      }
+      so += sc; ro += rcq;
+    }
+    h->send_dbl2.resize(world); h->recv_dbl2.resize(world);
+    for (int q = 0; q < world; ++q) { h->send_dbl2[q] = 2 * h->send_dbl[q]; h->recv_dbl2[q] = 2 * h->recv_dbl[q]; }
+    if ((rc = upload(h, &h->d_send2_a, sa))) return rc;
+    if ((rc = upload(h, &h->d_send2_b, sb))) return rc;
+    if ((rc = upload(h, &h->d_recv2_a, ra))) return rc;
+    if ((rc = upload(h, &h->d_recv2_b, rb))) return rc;
+    if ((rc = upload(h, &h->d_halo_row, hrow))) return rc;
+    if ((rc = dalloc(h, &h->d_send2, (size_t)2 * h->n_send * PB))) return rc;
+    if ((rc = dalloc(h, &h->d_recv2, (size_t)2 * h->NH * PB))) return rc;
+  }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
