@@ -99,6 +99,47 @@ static int allreduce(Handle *h, double *v, int n) {
   return 0;
 }
 
+// Tile dealing of the copy-ring translation solve: every node's CTA tiles are cut into chunks of
+// `chunk` consecutive tiles, chunks go round-robin to the persistent CTAs.  A node's rendezvous
+// involves the CTAs that hold one of its chunks.  (Measured on the 1M-pose grid: dealing the two
+// slowest-converging nodes in chunks of 1-2 tiles, to put more CTAs on the tail of the solve, does
+// not pay: 3.37 -> 3.6 ms per cold solve; chunk 8 beats 4 and 16.)
+static int plan_ring(Handle *h, int grid, int chunk) {
+  if (h->ts_plan_grid == grid && h->ts_plan_chunk == chunk) return 0;
+  std::vector<std::vector<int>> lists(grid);
+  std::vector<int> parts(h->A, 0);
+  int rr = 0;
+  for (int a = 0; a < h->A; ++a) {
+    const int c = chunk;
+    int nch = 0;
+    for (int t = h->h_node_ctb[a]; t < h->h_node_cte[a]; t += c, ++rr, ++nch)
+      for (int u = t; u < std::min(t + c, h->h_node_cte[a]); ++u) lists[rr % grid].push_back(u);
+    parts[a] = std::min(nch, grid);
+  }
+  std::vector<int> ptr(grid + 1, 0), tiles;
+  h->ts_plan_max = 0;
+  for (int b = 0; b < grid; ++b) {
+    std::sort(lists[b].begin(), lists[b].end());
+    tiles.insert(tiles.end(), lists[b].begin(), lists[b].end());
+    ptr[b + 1] = (int)tiles.size();
+    h->ts_plan_max = std::max(h->ts_plan_max, (int)lists[b].size());
+  }
+  // the plan buffers may still be read by a solve in flight on the stream: stream-ordered copies
+  // from a staging vector that outlives them
+  h->ts_plan_stage.assign(ptr.begin(), ptr.end());
+  h->ts_plan_stage.insert(h->ts_plan_stage.end(), tiles.begin(), tiles.end());
+  h->ts_plan_stage.insert(h->ts_plan_stage.end(), parts.begin(), parts.end());
+  const int *st = h->ts_plan_stage.data();
+  CK(cudaMemcpyAsync(h->d_cta_ptr, st, sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, h->stream));
+  if (!tiles.empty())
+    CK(cudaMemcpyAsync(h->d_cta_tiles, st + ptr.size(), sizeof(int) * tiles.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_node_parts, st + ptr.size() + tiles.size(), sizeof(int) * parts.size(), cudaMemcpyHostToDevice,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->ts_plan_grid = grid; h->ts_plan_chunk = chunk;
+  return 0;
+}
+
 template <int D> struct Drv {
   static constexpr int PB = (D + 1) * D;
 
@@ -228,12 +269,14 @@ template <int D> struct Drv {
         h->ctr.reserved[1]++;                                 // solves served by k_tsolve_lite
         return 0;
       }
-      int grid = std::max(1, std::min(h->ts_max_grid, h->n_ctiles));
+      int grid = std::max(1, std::min(std::min(h->ts_max_grid, 1024), h->n_ctiles));
       if (h->ts_grid_override > 0) grid = std::min(grid, h->ts_grid_override);
-      if (((int64_t)h->n_ctiles / ((int64_t)grid * ta.chunk) + 1) * ta.chunk > TS_MAXCT) {
+      RC(plan_ring(h, grid, ta.chunk));
+      if (h->ts_plan_max > TS_MAXCT) {
         set_error("translation solve: too many poses per GPU for the persistent kernel (shard over more GPUs)");
         return MMPGO_ERR_UNSUPPORTED;
       }
+      ta.cta_ptr = h->d_cta_ptr; ta.cta_tiles = h->d_cta_tiles; ta.node_parts = h->d_node_parts;
       CK((cudaError_t)launch_tsolve<D>(ta, grid, h->stream));
       h->ctr.launches++;
     }

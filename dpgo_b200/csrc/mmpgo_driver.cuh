@@ -102,6 +102,11 @@ struct Handle {
   double *ts_partials = nullptr, *ts_nstate = nullptr;
   unsigned long long *d_ts_stats = nullptr;
   int ts_max_grid = 0, ts_grid_override = 0;
+  // tile dealing of the copy-ring kernel (host-built table)
+  std::vector<int> h_node_ctb, h_node_cte;
+  int *d_cta_ptr = nullptr, *d_cta_tiles = nullptr, *d_node_parts = nullptr;
+  int ts_plan_grid = -1, ts_plan_chunk = -1, ts_plan_max = 0;
+  std::vector<int> ts_plan_stage;
   int ts_lite_max_tiles = 16;    // use k_tsolve_lite when a CTA gets at most this many CTA tiles
   int tsl_max_grid = 0;          // co-resident CTAs of k_tsolve_lite
   int64_t sell_entries = 0;

@@ -144,7 +144,9 @@ struct TSolveArgs {
                                   // {slot of the neighbour's column 0}[rows][32] ints; tile at byte 384 sell_ptr[TS_WPT ct]
   const int *ct_node, *ct_start, *ct_cnt;
   int n_ct;
-  int chunk;                      // consecutive CTA tiles dealt to one CTA at a time
+  int chunk;                      // k_tsolve_lite: contiguous CTA tiles per CTA
+  const int *cta_ptr, *cta_tiles; // k_tsolve: CTA tiles of every persistent CTA (CSR over the grid), ascending per CTA
+  const int *node_parts;          // k_tsolve: CTAs that hold tiles of the node (arrivals per phase)
   const int *node_ctb, *node_cte; // CTA-tile range of every node
   const int *active;              // per-node mask or nullptr
   const double *rhs;              // [NO][D]

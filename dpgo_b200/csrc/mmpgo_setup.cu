@@ -357,6 +357,8 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     node_cte[a] = (int)ct_node.size();
   }
   h->n_ctiles = (int)ct_node.size();
+  h->h_node_ctb = node_ctb; h->h_node_cte = node_cte;
+  h->ts_plan_grid = -1;
   const int n_sl = TS_WPT * h->n_ctiles;
   std::vector<int> sell_ptr((size_t)n_sl + 1, 0), slot_of(NO, 0);
   for (int c = 0; c < h->n_ctiles; ++c)
@@ -489,6 +491,9 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_sync, (size_t)2 * A + 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
+    if ((rc = dalloc(h, &h->d_cta_ptr, (size_t)1024 + 1))) return rc;
+    if ((rc = dalloc(h, &h->d_cta_tiles, (size_t)h->n_ctiles + 1))) return rc;
+    if ((rc = dalloc(h, &h->d_node_parts, (size_t)A))) return rc;
     h->ts_max_grid = d == 2 ? tsolve_max_grid<2>(h->opt.device) : tsolve_max_grid<3>(h->opt.device);
     if (h->ts_max_grid <= 0) { set_error("occupancy query for the translation solve failed"); return MMPGO_ERR_CUDA; }
     h->tsl_max_grid = d == 2 ? tsolve_lite_max_grid<2>(h->opt.device) : tsolve_lite_max_grid<3>(h->opt.device);

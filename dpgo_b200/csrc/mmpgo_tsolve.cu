@@ -162,11 +162,14 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
   // CTA tiles are dealt to the CTAs in chunks of `chunk` consecutive tiles, round-robin: a node's
   // rendezvous involves only the CTAs that hold one of its chunks, yet a node that needs many more
   // iterations than the others still keeps ~tiles/chunk CTAs busy in the tail
-  const int CH = a.chunk;
-  const int n_chunks = (a.n_ct + CH - 1) / CH;
-  auto tile_of = [&](int k) { return (int)(blockIdx.x + (k / CH) * gridDim.x) * CH + k % CH; };
-  int nb = 0;                                                                        // <= TS_MAXCT (host-checked)
-  for (int j = blockIdx.x; j < n_chunks; j += gridDim.x) nb += min(CH, a.n_ct - j * CH);
+  // (the dealing is a host-built table, a.cta_ptr / a.cta_tiles: nodes known to need many more
+  // iterations than the rest are dealt in smaller chunks, i.e. spread over more CTAs)
+  __shared__ int m_tile[TS_MAXCT];
+  const int tb0 = __ldg(a.cta_ptr + blockIdx.x);
+  const int nb = __ldg(a.cta_ptr + blockIdx.x + 1) - tb0;                            // <= TS_MAXCT (host-checked)
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) m_tile[k] = __ldg(a.cta_tiles + tb0 + k);
+  __syncthreads();
+  auto tile_of = [&](int k) { return m_tile[k]; };
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int q = 0; q < NST; ++q) mbar_init(&empty[q], 1);
@@ -209,8 +212,7 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
         sg_k0[ns] = k; sg_n[ns] = 1; sg_node[ns] = m_node[k];
         // CTAs that share the node = arrivals the node expects per phase
         const int nd = m_node[k];
-        const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
-        sg_target[ns] = min((ce - 1) / CH - cb / CH + 1, (int)gridDim.x);
+        sg_target[ns] = __ldg(a.node_parts + nd);
         sg_kind[ns] = 0; sg_coef[ns] = 0.0; sg_open[ns] = 0; sg_done[ns] = 0; sg_claim[ns] = 0;   // phase 0 (init) is open
         ++ns;
       }
