@@ -226,7 +226,7 @@ template <int D> struct Drv {
       ta.stats = h->d_ts_stats; ta.node_off = h->d_node_off;
       ta.tol2 = h->opt.translation_solve_tol * h->opt.translation_solve_tol;
       ta.max_iters = h->opt.translation_solve_max_iters;
-      CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (2 * h->A + 8), h->stream));
+      CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (3 * h->A + 8), h->stream));
       // small shards (few CTA tiles per SM) are rendezvous bound: k_tsolve_lite; large ones are
       // HBM bound: the copy-ring kernel.  MMPGO_TS_KERNEL=ring|lite overrides (experiments).
       const int lgrid = std::max(1, std::min(h->tsl_max_grid, h->n_ctiles));
@@ -277,8 +277,22 @@ template <int D> struct Drv {
         return MMPGO_ERR_UNSUPPORTED;
       }
       ta.cta_ptr = h->d_cta_ptr; ta.cta_tiles = h->d_cta_tiles; ta.node_parts = h->d_node_parts;
+      // the tail of the solve (a few slowly converging nodes still iterating) is rendezvous bound:
+      // those nodes are handed to k_tsolve_lite with their CG state (same arithmetic, same result)
+      int max_nt = 1;
+      for (int n = 0; n < h->A; ++n) max_nt = std::max(max_nt, h->h_node_cte[n] - h->h_node_ctb[n]);
+      int hl = std::max(2, ta.n_active / 16);
+      hl = std::min(hl, (int)((int64_t)lgrid * TSL_MAXT / max_nt));
+      if (getenv("MMPGO_TS_HANDOFF")) hl = std::min(atoi(getenv("MMPGO_TS_HANDOFF")), (int)((int64_t)lgrid * TSL_MAXT / max_nt));
+      ta.handoff_live = std::max(hl, 0);
       CK((cudaError_t)launch_tsolve<D>(ta, grid, h->stream));
       h->ctr.launches++;
+      if (ta.handoff_live > 0) {
+        ta.resume = 1; ta.chunk = 1;
+        ta.lite_stage_bytes = 0; ta.lite_vec_off = -1; ta.lite_z_off = -1; ta.lite_dyn_bytes = 0;
+        CK((cudaError_t)launch_tsolve_lite<D>(ta, lgrid, h->stream));
+        h->ctr.launches++;
+      }
     }
     return 0;
   }

@@ -156,7 +156,7 @@ struct TSolveArgs {
   double *z;                      // [TS_WPT n_ct][D][32], padded by TS_HALO tiles at both ends; r is kept as z = r / diag
   double *partials;               // [n_ct][4]
   double *nstate;                 // [nodes][8]: rz, bb, alpha, beta, iters, rr, finished-in-round + 1
-  int *cnt;                       // [2 nodes] arrival counters, then epochs (zeroed before launch)
+  int *cnt;                       // [3 nodes + 8] arrival counters, epochs, hand-off flags, finished count (zeroed before launch)
   int n_nodes, n_active;
   unsigned long long *stats;      // [2]: sum of node iterations, sum of iterations x poses of the node
   const int *node_off;            // [nodes+1] own pose offsets
@@ -167,6 +167,10 @@ struct TSolveArgs {
   int lite_vec_off;               // tile records {x, p, Ap, diag} resident (-1 = in global memory)
   int lite_z_off;                 // copy of the CTA's own z tiles (-1 = none)
   int lite_dyn_bytes;             // total
+  // hand-off k_tsolve -> k_tsolve_lite.  cnt layout: [n_nodes] arrivals, [n_nodes] epochs, [n_nodes]
+  // hand-off flags, then the count of finished nodes (all zeroed before the first launch)
+  int handoff_live;               // k_tsolve: nodes still iterating at which the rest is handed off (0 = never)
+  int resume;                     // k_tsolve_lite: continue the flagged nodes instead of starting a solve
 };
 template <int D> int launch_tsolve(const TSolveArgs &a, int grid, cudaStream_t s);
 template <int D> int tsolve_max_grid(int device);

@@ -489,7 +489,7 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     h->ts_z = h->ts_z_base + (size_t)TS_HALO * CTILE * d;
     if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4 * 2))) return rc;   // two buffers (k_tsolve_lite)
     if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
-    if ((rc = dalloc(h, &h->d_ts_sync, (size_t)2 * A + 8))) return rc;
+    if ((rc = dalloc(h, &h->d_ts_sync, (size_t)3 * A + 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
     if ((rc = dalloc(h, &h->d_cta_ptr, (size_t)1024 + 1))) return rc;
     if ((rc = dalloc(h, &h->d_cta_tiles, (size_t)h->n_ctiles + 1))) return rc;

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
             const int round = __shfl_sync(0xffffffffu, rnd, src);
             double *nst = a.nstate + (size_t)nd * 8;
             const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
-            bool done = false;
+            bool done = false, handoff = false;
             if (round == 0) {
               double sm[3];
               node_sum<3>(a.partials, cb, ce, lane, sm);
@@ -279,10 +279,18 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
               __syncwarp();
               if (lane == 0) { nst[3] = sm[0] / rz; nst[0] = sm[0]; nst[5] = sm[2]; nst[4] = it; }
               done = !(sm[2] > a.tol2 * bb) || !(sm[0] > 0.0) || it >= (double)a.max_iters;
+              // hand-off: once only a few nodes are still iterating, a phase is bound by this kernel's
+              // rendezvous chain (~17 us) and not by HBM; those nodes leave here with their CG state
+              // in place and k_tsolve_lite (resume mode, ~4 us per rendezvous, all SMs) finishes them
+              if (!done && a.handoff_live > 0 && a.n_active - ld_relaxed(a.cnt + 3 * a.n_nodes) <= a.handoff_live)
+                handoff = true;
             }
+            handoff = __shfl_sync(0xffffffffu, (int)handoff, 0) != 0;
             if (lane == 0) {
               a.cnt[nd] = 0;
-              if (done && a.stats) {
+              if (handoff) { a.cnt[2 * a.n_nodes + nd] = 1; done = true; }
+              else if (done) atomicAdd(a.cnt + 3 * a.n_nodes, 1);
+              if (done && !handoff && a.stats) {
                 const unsigned long long it = (unsigned long long)(round / 2);
                 atomicAdd(a.stats, it);
                 atomicAdd(a.stats + 1, it * (unsigned long long)(__ldg(a.node_off + nd + 1) - __ldg(a.node_off + nd)));
@@ -596,21 +604,78 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
   constexpr int WPT = C::WPT;
   const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
   const int wi = wg % WPT, grp = wg / WPT;
-  const int tpc = a.chunk;
-  const int k0 = blockIdx.x * tpc, nb = max(0, min(tpc, a.n_ct - k0));
-  __shared__ int m_start[TSL_MAXT], m_cnt[TSL_MAXT], m_seg[TSL_MAXT], m_sell[TSL_MAXT][TS_WPT + 1];
+  // Tile dealing.  Fresh solve: CTA b owns the contiguous CTA tiles [b chunk, (b+1) chunk).  Resume
+  // (a.resume, after a hand-off from k_tsolve): only the nodes flagged in a.cnt[2 n_nodes + node]
+  // continue; their tiles are numbered consecutively and dealt evenly over the whole grid, and the
+  // CG state {x, p, Ap, z; rz, |b|^2, beta, iterations} is picked up where k_tsolve left it.
+  const bool resume = a.resume != 0;
+  __shared__ int m_tile[TSL_MAXT], m_start[TSL_MAXT], m_cnt[TSL_MAXT], m_seg[TSL_MAXT], m_sell[TSL_MAXT][TS_WPT + 1];
   __shared__ int sg_node[TSL_MAXSEG], sg_target[TSL_MAXSEG], sg_state[TSL_MAXSEG], sg_owner[TSL_MAXSEG];
   __shared__ double sg_coef[TSL_MAXSEG], sg_rz[TSL_MAXSEG], sg_bb[TSL_MAXSEG], sg_it[TSL_MAXSEG];
-  __shared__ int n_seg_s;
+  __shared__ int n_seg_s, nb_s;
   __shared__ double red[NG][2][TS_WPT][3];
-
+  const int k0 = blockIdx.x * a.chunk;                      // first tile (fresh solve only)
+  if (threadIdx.x == 0) {
+    int ns = 0, nbl = 0;
+    if (!resume) {
+      const int tpc = a.chunk;
+      nbl = max(0, min(tpc, a.n_ct - k0));
+      // segments: runs of this CTA's tiles that belong to one active node
+      int prev = -1;
+      for (int k = 0; k < nbl; ++k) {
+        m_tile[k] = k0 + k;
+        const int nd = __ldg(a.ct_node + k0 + k);
+        const bool on = !(a.active && !__ldg(a.active + nd));
+        if (!on) { m_seg[k] = -1; continue; }
+        if (nd != prev) {
+          const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
+          sg_node[ns] = nd;
+          sg_target[ns] = (ce - 1) / tpc - cb / tpc + 1;      // CTAs that hold tiles of the node
+          sg_owner[ns] = (cb >= k0 && cb < k0 + nbl) ? 1 : 0;  // this CTA reports the node's statistics
+          sg_state[ns] = 0; sg_coef[ns] = 0.0; sg_rz[ns] = 0.0; sg_bb[ns] = 0.0; sg_it[ns] = 0.0;
+          prev = nd; ++ns;
+        }
+        m_seg[k] = ns - 1;
+      }
+    } else {
+      const int *flag = a.cnt + 2 * a.n_nodes;
+      int T = 0;
+      for (int nd = 0; nd < a.n_nodes; ++nd)
+        if (__ldcg(flag + nd)) T += __ldg(a.node_cte + nd) - __ldg(a.node_ctb + nd);
+      const int tpc = max(1, (T + (int)gridDim.x - 1) / (int)gridDim.x);
+      if (tpc > TSL_MAXT) __trap();                          // host-checked bound
+      const int c0 = min((int)blockIdx.x * tpc, T), c1 = min(c0 + tpc, T);
+      nbl = c1 - c0;
+      int off = 0;
+      for (int nd = 0; nd < a.n_nodes && off < c1; ++nd) {
+        if (!__ldcg(flag + nd)) continue;
+        const int cb = __ldg(a.node_ctb + nd), n = __ldg(a.node_cte + nd) - cb;
+        const int lo = max(c0, off), hi = min(c1, off + n);
+        if (lo < hi) {
+          const double *nst = a.nstate + (size_t)nd * 8;
+          sg_node[ns] = nd;
+          sg_target[ns] = (off + n - 1) / tpc - off / tpc + 1;
+          sg_owner[ns] = (off >= c0 && off < c1) ? 1 : 0;
+          sg_state[ns] = 0;
+          sg_coef[ns] = __ldcg(nst + 3);                     // beta of the phase A that comes next
+          sg_rz[ns] = __ldcg(nst + 0); sg_bb[ns] = __ldcg(nst + 1); sg_it[ns] = __ldcg(nst + 4);
+          for (int c = lo; c < hi; ++c) { m_tile[c - c0] = cb + (c - off); m_seg[c - c0] = ns; }
+          ++ns;
+        }
+        off += n;
+      }
+    }
+    n_seg_s = ns; nb_s = nbl;
+  }
+  __syncthreads();
+  const int nb = nb_s;
   for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-    const int ct = k0 + k;
+    const int ct = m_tile[k];
     m_start[k] = __ldg(a.ct_start + ct); m_cnt[k] = __ldg(a.ct_cnt + ct);
   }
   for (int q = threadIdx.x; q < nb * (WPT + 1); q += blockDim.x) {
     const int k = q / (WPT + 1), r = q % (WPT + 1);
-    m_sell[k][r] = __ldg(a.sell_ptr + WPT * (k0 + k) + r);
+    m_sell[k][r] = __ldg(a.sell_ptr + WPT * m_tile[k] + r);
   }
   // the ELLPACK rows of this CTA's tiles are one contiguous run of sell_pack: staged in shared
   // memory once per launch when they fit (a.lite_stage_bytes > 0), so that phase A is one
@@ -639,29 +704,11 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
       vec_s[(size_t)k * C::RL + 3 * C::VEC + r] = __ldg(a.rec + (size_t)(k0 + k) * C::RL + 3 * C::VEC + r);
     }
   }
-  if (threadIdx.x == 0) {
-    // segments: runs of this CTA's tiles that belong to one active node
-    int ns = 0, prev = -1;
-    for (int k = 0; k < nb; ++k) {
-      const int nd = __ldg(a.ct_node + k0 + k);
-      const bool on = !(a.active && !__ldg(a.active + nd));
-      if (!on) { m_seg[k] = -1; continue; }
-      if (nd != prev) {
-        const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
-        sg_node[ns] = nd;
-        sg_target[ns] = (ce - 1) / tpc - cb / tpc + 1;      // CTAs that hold tiles of the node
-        sg_owner[ns] = (cb >= k0 && cb < k0 + nb) ? 1 : 0;  // this CTA reports the node's statistics
-        sg_state[ns] = 0; sg_coef[ns] = 0.0; sg_rz[ns] = 0.0; sg_bb[ns] = 0.0; sg_it[ns] = 0.0;
-        prev = nd; ++ns;
-      }
-      m_seg[k] = ns - 1;
-    }
-    n_seg_s = ns;
-  }
   __syncthreads();
   const int n_seg = n_seg_s;
   if (n_seg == 0) return;
-  for (int round = 0;; ++round) {
+  const int round0 = resume ? 1 : 0;                        // a resumed solve starts with a phase A
+  for (int round = round0;; ++round) {
     double *pbuf = a.partials + (size_t)(round & 1) * a.n_ct * 4;
     // ---------------- the phase, one tile per group at a time ----------------
     for (int k = grp; k < nb; k += NG) {
@@ -671,7 +718,7 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
       if (st == 2) continue;
       const int kd = st == 1 ? 3 : (round == 0 ? 0 : ((round & 1) ? 1 : 2));
       const double coef = sg_coef[seg];
-      const int ct = k0 + k;
+      const int ct = m_tile[k];
       const bool valid = 32 * wi + lane < m_cnt[k];
       const int p = m_start[k] + 32 * wi + lane;
       const size_t vb = (size_t)(WPT * ct + wi) * (32 * D) + lane;
@@ -815,7 +862,7 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
       if (st == 1) { if (lane == 0) sg_state[s] = 2; continue; }
       if (st != 0) continue;
       const int nd = sg_node[s];
-      const int target = sg_target[s] * (round + 1);
+      const int target = sg_target[s] * (round - round0 + 1);
       {
         const long long t0 = clock64();
         unsigned spins = 0;
@@ -847,7 +894,7 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
       if (done && lane == 0) {
         sg_state[s] = 1;                                   // publish in the next pass, then retire
         if (sg_owner[s] && a.stats) {
-          const unsigned long long it = (unsigned long long)(round / 2);
+          const unsigned long long it = (unsigned long long)sg_it[s];   // completed CG iterations (= round / 2)
           atomicAdd(a.stats, it);
           atomicAdd(a.stats + 1, it * (unsigned long long)(__ldg(a.node_off + nd + 1) - __ldg(a.node_off + nd)));
         }
