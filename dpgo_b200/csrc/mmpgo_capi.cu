@@ -168,6 +168,15 @@ int mmpgo_evaluate_f(mmpgo_handle hh, const double *X, int64_t ldx, double *fobj
   GUARDED(mmpgo::driver_evaluate_f(h, X, ldx, fobj));
 }
 
+int mmpgo_evaluate_grad(mmpgo_handle hh, const double *X, int64_t ldx, double *G, int64_t ldg) {
+  H_OR_FAIL(hh);
+  if (!X || !G || ldx < (int64_t)(h->d + 1) * h->N || ldg < (int64_t)(h->d + 1) * h->N) {
+    mmpgo::set_error("bad X / G / leading dimension");
+    return MMPGO_ERR_ARG;
+  }
+  GUARDED(mmpgo::driver_evaluate_grad(h, X, ldx, G, ldg));
+}
+
 int mmpgo_current_objective(mmpgo_handle hh, double *fobj, double *grad_sqnorm) {
   H_OR_FAIL(hh);
   if (!fobj || !grad_sqnorm) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }

@@ -1079,6 +1079,52 @@ int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f) {
   return rc;
 }
 
+// DPGOStar::evaluate_grad (DPGOStar.cpp:763-829).  At Z = X the surrogate's gradient is the
+// gradient of F, so the Euclidean gradient of the own poses is K1 (inter-node edges, weights
+// evaluated at X) + the K2 gradient pass, exactly what update() computes for X^k; the
+// reduced-gradient pass adds the tangent projection of the rotation rows.  Scratch only
+// (TNT vectors, the evaluation pose array): the solver state is not touched.
+template <int D> static int evaluate_grad_t(Handle *h, const double *X, int64_t ldx, double *G, int64_t ldg) {
+  typedef Drv<D> Dr;
+  const mmpgo_options &o = h->opt;
+  const Mask allm(h->A, 1);
+  RC(stage_upload(h, X, ldx));
+  pack_dev(h, h->xeval, nullptr, nullptr, nullptr, nullptr);
+  Tiles tl; RC(make_tiles(h, allm, &tl));
+  double *g = h->cg_r, *Df = h->cg_v, *grad = h->cg_p;
+  InterArgs ia; std::memset(&ia, 0, sizeof(ia));
+  ia.rowptr = h->d_xrowptr; ia.rec = h->d_xrec; ia.xa = h->xeval; ia.dinter = h->d_dinter;
+  ia.loss = o.loss; ia.loss_reg = o.loss_reg; ia.xi = o.regularizer;
+  ia.w_out = h->w_tmp; ia.g = g; ia.partials = h->d_partials;
+  launch_inter<D>(o.loss == MMPGO_LOSS_NONE ? I_TRIVIAL : I_ROBUST, tl, ia, h->stream);
+  GPassArgs a = Dr::gargs(h);
+  a.x = h->xeval; a.g = g; a.out = Df;
+  launch_gpass<D>(G_GRAD, tl, a, h->stream);                 // all rows of the Euclidean gradient
+  a.out = h->cg_Hp; a.out2 = grad;
+  launch_gpass<D>(G_REDGRAD, tl, a, h->stream);              // rotation rows, projected (SOdProduct::Proj)
+  VecArgs v; std::memset(&v, 0, sizeof(v));
+  v.a = Df; v.o1 = grad; v.partials = h->d_partials;
+  launch_vec<D>(V_COPY_T, tl, v, h->stream);                 // translation rows stay Euclidean
+  h->ctr.launches += 4; h->ctr.inter_passes++; h->ctr.intra_passes += 2; h->ctr.vector_passes++;
+  // pose blocks -> the caller's layout; only the rows of the local nodes travel back
+  const int d = h->d;
+  const int64_t ld = (int64_t)(d + 1) * h->N;
+  launch_unpack_poses<D>(h->NO, h->d_pose_gid, grad, h->d_xstage, ld, h->N, h->stream);
+  h->ctr.launches++;
+  const int64_t g_lo = h->own_gid.front(), g_hi = h->own_gid.back() + 1;
+  CK(cudaMemcpy2DAsync(G + g_lo, (size_t)ldg * sizeof(double), h->d_xstage + g_lo, (size_t)ld * sizeof(double),
+                       (size_t)(g_hi - g_lo) * sizeof(double), d, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpy2DAsync(G + h->N + d * g_lo, (size_t)ldg * sizeof(double), h->d_xstage + h->N + d * g_lo,
+                       (size_t)ld * sizeof(double), (size_t)(g_hi - g_lo) * d * sizeof(double), d,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int driver_evaluate_grad(Handle *h, const double *X, int64_t ldx, double *G, int64_t ldg) {
+  if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
+  return h->d == 2 ? evaluate_grad_t<2>(h, X, ldx, G, ldg) : evaluate_grad_t<3>(h, X, ldx, G, ldg);
+}
+
 // Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA
 // events (bench.py's live roofline measurement).  kind: 0 G_EVAL, 1 G_GRAD, 2 inter pass,
 // 3 fused proximal, 4 edge objective, 5 G00 SpMV, 6 G_HV, 7 G_RHS_T.

@@ -156,6 +156,7 @@ int driver_communicate(Handle *h);
 int driver_get_poses(Handle *h, double *X, int64_t ldx);
 int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *count);
 int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f);
+int driver_evaluate_grad(Handle *h, const double *X, int64_t ldx, double *G, int64_t ldg);
 int driver_current_objective(Handle *h, double *f, double *g2);
 int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg);
 int driver_sync_counters(Handle *h);

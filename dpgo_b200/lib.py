@@ -103,6 +103,7 @@ SIGNATURES = {
     "mmpgo_get_node_scalars": (C.c_int, [_P, C.c_int32, C.POINTER(NodeScalars)]),
     "mmpgo_get_weights": (C.c_int, [_P, C.c_int32, _dp, C.c_int64, C.POINTER(C.c_int64)]),
     "mmpgo_evaluate_f": (C.c_int, [_P, _dp, C.c_int64, _dp]),
+    "mmpgo_evaluate_grad": (C.c_int, [_P, _dp, C.c_int64, _dp, C.c_int64]),
     "mmpgo_current_objective": (C.c_int, [_P, _dp, _dp]),
     "mmpgo_star_objective": (C.c_int, [_P, _dp, _dp, _ip]),
     "mmpgo_graph_sizes": (C.c_int, [_P, C.POINTER(C.c_int64)]),

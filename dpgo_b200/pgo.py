@@ -109,6 +109,14 @@ class _Driver:
         L.check(self.lib.mmpgo_evaluate_f(self._h, L.dptr(X), X.shape[0], C.byref(out)))
         return out.value
 
+    def evaluate_grad(self, X):
+        """DPGOStar::evaluate_grad (DPGOStar.cpp:763-829): Riemannian gradient of the global
+        objective at X, in the layout of X (rows of the poses owned here; zero elsewhere)."""
+        X = np.asfortranarray(X, dtype=np.float64)
+        G = np.zeros_like(X, order="F")
+        L.check(self.lib.mmpgo_evaluate_grad(self._h, L.dptr(X), X.shape[0], L.dptr(G), G.shape[0]))
+        return G
+
     # -- results() ----------------------------------------------------------
     def X(self, out=None):
         """Global-layout copy of the current iterate (rows of local nodes).  `out`: an

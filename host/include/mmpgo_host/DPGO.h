@@ -5,7 +5,7 @@
 //   DPGO::Options, Loss, Scheme                      C++/DPGO/include/DPGO/DPGO_types.h:35-201
 //   DPGO::read_g2o_file                              C++/DPGO/src/DPGO_utils.cpp:8-138
 //   DPGO::DPGOHash  (initialize/update/iterate/communicate/results)   include/DPGO/DPGOHash.h:13-107
-//   DPGO::DPGOStar  (+ evaluate_f)                                    include/DPGO/DPGOStar.h:13-93
+//   DPGO::DPGOStar  (+ evaluate_f, evaluate_grad)                                    include/DPGO/DPGOStar.h:13-93
 // but one object drives ALL robot nodes [node_begin, node_end) that live on one GPU: the loops
 // `for alpha: dpgo_hash[alpha]->iterate()` of C++/examples/dist_pgo.cpp:497-520 become one
 // batched call through the C ABI (include/mmpgo.h).  All arithmetic happens in libmmpgo.so; there
@@ -164,6 +164,13 @@ class DPGODriver {
   int results(int node, DPGOResult &out) const { return mmpgo_get_node_scalars(h_, node, &out); }
   /** DPGOStar::evaluate_f (DPGOStar.cpp:713-761) over the edges owned by the local nodes. */
   int evaluate_f(const Matrix &X, Scalar &fobj) const { return mmpgo_evaluate_f(h_, X.data(), X.rows(), &fobj); }
+  /** DPGOStar::evaluate_grad (DPGOStar.cpp:763-829): Riemannian gradient of the global objective at X
+   *  (rows of the poses owned by the local nodes). */
+  int evaluate_grad(const Matrix &X, Matrix &grad) const {
+    if (X.rows() != (int64_t)(d_ + 1) * N_ || X.cols() != d_) return -1;
+    if (grad.rows() != X.rows() || grad.cols() != X.cols()) grad = Matrix(X.rows(), X.cols());
+    return mmpgo_evaluate_grad(h_, X.data(), X.rows(), grad.data(), grad.rows());
+  }
   /** F and |grad F|^2 of the current device iterate (what dist_pgo logs, dist_pgo.cpp:523-530). */
   int objective(Scalar &F, Scalar &grad_sqnorm) const { return mmpgo_current_objective(h_, &F, &grad_sqnorm); }
   int weights(int node, std::vector<double> &w) const {

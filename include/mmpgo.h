@@ -144,6 +144,12 @@ int mmpgo_get_weights(mmpgo_handle h, int32_t node, double *w, int64_t capacity,
  * by the local nodes (each inter-node edge is owned by the node of its i
  * endpoint); summing over handles gives F.  X is a full GLOBAL iterate. */
 int mmpgo_evaluate_f(mmpgo_handle h, const double *X, int64_t ldx, double *fobj);
+/* DPGOStar::evaluate_grad (DPGOStar.cpp:763-829): Riemannian gradient of the global
+ * objective at the GLOBAL iterate X (robust weights evaluated at X; rotation rows projected
+ * onto the tangent space of SO(d)^n, translation rows Euclidean).  G has the layout of X
+ * (column-major ((d+1)N) x d, leading dimension ldg); only the rows of the poses owned by the
+ * local nodes are written (all rows for a single handle).  Does not touch the solver state. */
+int mmpgo_evaluate_grad(mmpgo_handle h, const double *X, int64_t ldx, double *G, int64_t ldg);
 /* Objective of the CURRENT device iterate, no host<->device pose traffic
  * (what dist_pgo logs each iteration, dist_pgo.cpp:523-530). */
 int mmpgo_current_objective(mmpgo_handle h, double *fobj, double *grad_sqnorm);

@@ -65,6 +65,14 @@ def test_se2_with_outliers(loss):
     _check(out, 2)
 
 
+def test_config2_grid3d_standin():
+    """BASELINE.json configs[1]: grid3D (8000 poses, dense loop closures), 8 nodes, Huber, AMM-PGO*.
+    dataset/grid3D.g2o is not shipped with the reference; a seeded 20 x 20 x 20 grid in the style of
+    smallGrid3D.g2o stands in."""
+    g, _, X0 = D.grid3d(20, 20, 20, seed=2)
+    _check(parity.run_both(g, 8, X0, 10, loss="huber", algorithm="star"), 3)
+
+
 def test_ragged_partition():
     # N not divisible by the node count (DPGO_utils.cpp:147-158)
     g, _, X0 = D.grid3d(5, 5, 3, seed=5)        # 75 poses over 4 nodes: 19,19,19,18
@@ -144,6 +152,28 @@ def test_evaluate_f_matches_oracle(grid):
         f = drv.evaluate_f(X0)
         want = gobj.evaluate_f(X0)
         assert abs(f - want) <= 1e-12 * abs(want)
+
+
+@pytest.mark.parametrize("case", ["se3", "se2"])
+def test_evaluate_grad_matches_oracle(grid, case):
+    """DPGOStar::evaluate_grad (DPGOStar.cpp:763-829) at a perturbed iterate, all four losses; the
+    call must not disturb a solve in progress."""
+    from oracle import dpgo as odpgo, g2o as og2o
+    g, _, X0 = grid if case == "se3" else D.city2d(14, 12, outlier_fraction=0.2, seed=3)
+    meas = parity.to_measurements(g)
+    for loss in ("trivial", "huber", "gm", "welsch"):
+        _, _, part = og2o.partition(g.num_poses, 4, meas)
+        gobj = odpgo.GlobalObjective(g.num_poses, 4, meas, part, odpgo.Options(loss=loss))
+        drv = D.DPGOStar(g, 4, D.Options(loss=loss))
+        assert drv.initialize(X0) == 0 and drv.update() == 0 and drv.iterate() == 0
+        assert drv.communicate() == 0 and drv.update() == 0
+        f_before = drv.objective()
+        X1 = drv.X()
+        got, want = drv.evaluate_grad(X1), gobj.evaluate_grad(X1)
+        assert np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+        # |grad F| from the per-node sums of update() is the norm of the same gradient
+        assert abs(np.linalg.norm(got) - f_before[1]) <= 1e-9 * max(1.0, f_before[1])
+        assert drv.objective() == f_before and drv.iterate() == 0
 
 
 def test_error_codes(grid):
