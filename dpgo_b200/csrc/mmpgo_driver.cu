@@ -212,7 +212,7 @@ template <int D> struct Drv {
       ta.rowptr = h->d_rowptr; ta.col = h->d_col; ta.a00 = h->d_a00; ta.d00 = h->d_d00;
       ta.sell_ptr = h->d_sell_ptr; ta.sell_pack = h->d_sell_pack;
       ta.ct_node = h->d_ct_node; ta.ct_start = h->d_ct_start; ta.ct_cnt = h->d_ct_cnt;
-      ta.n_ct = h->n_ctiles; ta.chunk = getenv("MMPGO_TS_CHUNK") ? std::max(1, atoi(getenv("MMPGO_TS_CHUNK"))) : 8; ta.node_ctb = h->d_node_ctb; ta.node_cte = h->d_node_cte;
+      ta.n_ct = h->n_ctiles; ta.chunk = h->ts_chunk; ta.node_ctb = h->d_node_ctb; ta.node_cte = h->d_node_cte;
       if (all(mp)) ta.active = nullptr;
       else {
         CK(cudaMemcpyAsync(h->d_active2, mp.data(), sizeof(int) * mp.size(), cudaMemcpyHostToDevice, h->stream));
@@ -228,14 +228,12 @@ template <int D> struct Drv {
       ta.max_iters = h->opt.translation_solve_max_iters;
       CK(cudaMemsetAsync(h->d_ts_sync, 0, sizeof(int) * (3 * h->A + 8), h->stream));
       // small shards (few CTA tiles per SM) are rendezvous bound: k_tsolve_lite; large ones are
-      // HBM bound: the copy-ring kernel.  MMPGO_TS_KERNEL=ring|lite overrides (experiments).
+      // HBM bound: the copy-ring kernel.  MMPGO_TS_KERNEL=ring|lite (read at set_graph) overrides (experiments).
       const int lgrid = std::max(1, std::min(h->tsl_max_grid, h->n_ctiles));
       const int tpc = (h->n_ctiles + lgrid - 1) / lgrid;
-      const char *kenv = getenv("MMPGO_TS_KERNEL");
-      const int lite_max = getenv("MMPGO_TS_LITE_MAX_TILES") ? atoi(getenv("MMPGO_TS_LITE_MAX_TILES")) : h->ts_lite_max_tiles;
-      bool lite = tpc <= std::min(lite_max, TSL_MAXT);
-      if (kenv && !strcmp(kenv, "ring")) lite = false;
-      if (kenv && !strcmp(kenv, "lite")) lite = tpc <= TSL_MAXT;
+      bool lite = tpc <= std::min(h->ts_lite_max_tiles, TSL_MAXT);
+      if (h->ts_force_kernel == 1) lite = false;
+      if (h->ts_force_kernel == 2) lite = tpc <= TSL_MAXT;
       if (lite) {
         ta.chunk = tpc;
         if (h->tsl_plan_tpc != tpc) {
@@ -259,7 +257,7 @@ template <int D> struct Drv {
           h->tsl_dyn_bytes = (int)off;
           h->tsl_plan_tpc = tpc;
         }
-        const bool nores = getenv("MMPGO_TS_NORES") != nullptr;   // experiments: everything from L2
+        const bool nores = h->ts_nores;                          // experiments: everything from L2
         ta.lite_stage_bytes = nores ? 0 : h->tsl_stage_bytes;
         ta.lite_vec_off = nores ? -1 : h->tsl_vec_off;
         ta.lite_z_off = nores ? -1 : h->tsl_z_off;
@@ -283,7 +281,7 @@ template <int D> struct Drv {
       for (int n = 0; n < h->A; ++n) max_nt = std::max(max_nt, h->h_node_cte[n] - h->h_node_ctb[n]);
       int hl = std::max(2, ta.n_active / 16);
       hl = std::min(hl, (int)((int64_t)lgrid * TSL_MAXT / max_nt));
-      if (getenv("MMPGO_TS_HANDOFF")) hl = std::min(atoi(getenv("MMPGO_TS_HANDOFF")), (int)((int64_t)lgrid * TSL_MAXT / max_nt));
+      if (h->ts_handoff >= 0) hl = std::min(h->ts_handoff, (int)((int64_t)lgrid * TSL_MAXT / max_nt));
       ta.handoff_live = std::max(hl, 0);
       CK((cudaError_t)launch_tsolve<D>(ta, grid, h->stream));
       h->ctr.launches++;

@@ -108,6 +108,12 @@ struct Handle {
   int ts_plan_grid = -1, ts_plan_chunk = -1, ts_plan_max = 0;
   std::vector<int> ts_plan_stage;
   int ts_lite_max_tiles = 16;    // use k_tsolve_lite when a CTA gets at most this many CTA tiles
+  // development knobs of the translation solve, read ONCE per handle (set_graph) from the environment:
+  // MMPGO_TS_KERNEL=ring|lite, MMPGO_TS_CHUNK, MMPGO_TS_LITE_MAX_TILES, MMPGO_TS_NORES, MMPGO_TS_HANDOFF
+  int ts_force_kernel = 0;       // 0 automatic, 1 copy-ring kernel, 2 small-shard kernel
+  int ts_chunk = 8;              // consecutive CTA tiles dealt to one CTA at a time (ring kernel)
+  bool ts_nores = false;         // small-shard kernel without shared-memory residency
+  int ts_handoff = -1;           // nodes still iterating at which the ring kernel hands off (-1: max(2, nodes/16))
   int tsl_max_grid = 0;          // co-resident CTAs of k_tsolve_lite
   int64_t sell_entries = 0;
   std::vector<int> h_sell_ptr;      // ELLPACK slice offsets (host copy: staging size of k_tsolve_lite)

@@ -10,6 +10,7 @@
 //   preconditioner)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -359,6 +360,15 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   h->n_ctiles = (int)ct_node.size();
   h->h_node_ctb = node_ctb; h->h_node_cte = node_cte;
   h->ts_plan_grid = -1;
+  {
+    const char *e;
+    h->ts_force_kernel = 0;
+    if ((e = getenv("MMPGO_TS_KERNEL"))) h->ts_force_kernel = !strcmp(e, "ring") ? 1 : !strcmp(e, "lite") ? 2 : 0;
+    if ((e = getenv("MMPGO_TS_CHUNK"))) h->ts_chunk = std::max(1, atoi(e));
+    if ((e = getenv("MMPGO_TS_LITE_MAX_TILES"))) h->ts_lite_max_tiles = atoi(e);
+    h->ts_nores = getenv("MMPGO_TS_NORES") != nullptr;
+    if ((e = getenv("MMPGO_TS_HANDOFF"))) h->ts_handoff = atoi(e);
+  }
   const int n_sl = TS_WPT * h->n_ctiles;
   std::vector<int> sell_ptr((size_t)n_sl + 1, 0), slot_of(NO, 0);
   for (int c = 0; c < h->n_ctiles; ++c)
