@@ -336,8 +336,8 @@ template <int D> struct Drv {
 
   // Hess[x](p): tdot = -G00^{-1} G01 p_Y; Hp = Proj(Y, (G [tdot; p_Y])_Y - sym(nab Y^T) p_Y)
   // returns per-node p.Hp, Hp.Hp, p.p        (DPGOProblem.cpp:552-577)
-  static int hess_vec(Handle *h, const double *x, double *p, double *Hp, const Mask &m, std::vector<double> &pHp,
-                      std::vector<double> &HpHp, std::vector<double> &pp, bool first = false) {
+  // (launch part: enqueues everything and the read-back of the three sums into slot 3, no synchronisation)
+  static int hess_vec_launch(Handle *h, const double *x, double *p, double *Hp, const Mask &m, bool first) {
     Tiles tl; RC(make_tiles(h, m, &tl));
     GPassArgs a = gargs(h);
     a.x = p; a.g = nullptr; a.out = h->rhs_t;
@@ -357,23 +357,40 @@ template <int D> struct Drv {
     a.x = p; a.xref = x; a.nab = h->nab; a.out = Hp;
     launch_gpass<D>(G_HV, tl, a, h->stream);
     h->ctr.launches++; h->ctr.intra_passes++;
-    const double *s; RC(reduce_to_host(h, &s));
+    return reduce_async(h, 3);
+  }
+  static int hess_vec(Handle *h, const double *x, double *p, double *Hp, const Mask &m, std::vector<double> &pHp,
+                      std::vector<double> &HpHp, std::vector<double> &pp, bool first = false, bool launched = false) {
+    if (!launched) {
+      RC(hess_vec_launch(h, x, p, Hp, m, first));
+      RC(host_sync(h));
+    }
+    const double *s = slot_host(h, 3);
     pHp.assign(h->A, 0.0); HpHp.assign(h->A, 0.0); pp.assign(h->A, 0.0);
     for (int n = 0; n < h->A; ++n) { pHp[n] = s[n * NS]; HpHp[n] = s[n * NS + 1]; pp[n] = s[n * NS + 2]; }
     return 0;
   }
 
   // ---- Steihaug-Toint truncated PCG, all nodes of `m` in lock step.  Result in h->cg_s.
+  // `pre`: CG_INIT (sums in slot 2) and the first Hessian-vector product (slot 3) were already
+  // launched for a superset of `m` and read back by the caller (speculation in tnt()).
+  static int stpcg_init_launch(Handle *h, const double *x, const Mask &m) {
+    RC(vec(h, V_CG_INIT, m, h->grad, nullptr, h->cg_s, h->cg_r, h->cg_v, h->cg_p, x, h->cg_Hs));
+    return reduce_async(h, 2);
+  }
   static int stpcg(Handle *h, const double *x, const Mask &m, const std::vector<double> &Delta,
-                   std::vector<double> &hMnorm, std::vector<int> &inner) {
+                   std::vector<double> &hMnorm, std::vector<int> &inner, bool pre = false) {
     const int A = h->A;
     const mmpgo_options &o = h->opt;
     const double eps = 1e-8;                                      // IterativeSolvers.h:179
     std::vector<double> rv(A, 0), sk_M_pk(A, 0), sk_M_2(A, 0), pk_M_2(A, 0), target(A, 0), coef((size_t)A * MAXC, 0.0);
     Mask act = m;
     hMnorm.assign(A, 0.0); inner.assign(A, 0);
-    RC(vec(h, V_CG_INIT, m, h->grad, nullptr, h->cg_s, h->cg_r, h->cg_v, h->cg_p, x, h->cg_Hs));
-    const double *s; RC(reduce_to_host(h, &s));
+    if (!pre) {
+      RC(stpcg_init_launch(h, x, m));
+      RC(host_sync(h));
+    }
+    const double *s = slot_host(h, 2);
     for (int n = 0; n < A; ++n) if (m[n]) {
       rv[n] = s[n * NS];
       pk_M_2[n] = rv[n];
@@ -389,7 +406,7 @@ template <int D> struct Drv {
         }
       }
       if (!any(act)) break;
-      RC(hess_vec(h, x, h->cg_p, h->cg_Hp, act, kap, HpHp, pp, first_hv));
+      RC(hess_vec(h, x, h->cg_p, h->cg_Hp, act, kap, HpHp, pp, first_hv, pre && first_hv));
       first_hv = false;
       Mask fin(A, 0), cont(A, 0), kern(A, 0);
       for (int n = 0; n < A; ++n) if (act[n]) {
@@ -456,6 +473,7 @@ template <int D> struct Drv {
     // the quadratic model pass (reduced gradient) also yields the surrogate value G(x): one pass
     // instead of evaluate_G + gradient (TNT.h:369-382)
     fx.assign(A, 0.0);
+    bool speculate = false;
     auto quad_model = [&](const Mask &mm) -> int {
       Tiles tl; RC(make_tiles(h, mm, &tl));
       GPassArgs a = gargs(h);
@@ -468,6 +486,14 @@ template <int D> struct Drv {
         RC(vec(h, V_PRECOND, mm, h->grad, nullptr, nullptr, nullptr, nullptr, nullptr, x));
         RC(reduce_async(h, 1));
       }
+      if (speculate) {
+        // The tCG start (CG_INIT) and its first Hessian-vector product do not depend on these norms
+        // except through the node mask (a node whose gradient is already small drops out): launch
+        // them for all nodes of `mm` behind the model pass and read everything back with ONE
+        // synchronisation; results of nodes that drop out are ignored.
+        RC(stpcg_init_launch(h, x, mm));
+        RC(hess_vec_launch(h, x, h->cg_p, h->cg_Hp, mm, true));
+      }
       RC(host_sync(h));
       const double *s = slot_host(h, 0), *s1 = slot_host(h, 1);
       for (int n = 0; n < A; ++n) if (mm[n]) { gnorm[n] = std::sqrt(s[n * NS]); fx[n] = s[n * NS + 1]; }
@@ -478,7 +504,10 @@ template <int D> struct Drv {
       }
       return 0;
     };
+    speculate = o.max_iterations > 0 && o.max_iterations_accepted > 0;
     RC(quad_model(m));
+    bool pre = speculate;
+    speculate = false;
     std::vector<double> hM, sHs, HsHs, ss, fprop;
     std::vector<int> inner;
     while (true) {
@@ -488,7 +517,8 @@ template <int D> struct Drv {
         else if (pgnorm[n] < o.preconditioned_grad_norm_tol) run[n] = 0;
       }
       if (!any(run)) break;
-      RC(stpcg(h, x, run, Delta, hM, inner));
+      RC(stpcg(h, x, run, Delta, hM, inner, pre));
+      pre = false;
       // trial point: retract, recover translations, evaluate
       RC(vec(h, V_RETRACT, run, x, h->cg_s, h->xprop, nullptr, nullptr, nullptr, nullptr));   // writes the whole pose block
       RC(recover_t(h, h->xprop, g, run));
