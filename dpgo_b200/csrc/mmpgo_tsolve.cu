@@ -585,7 +585,9 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
 // for the regime where a GPU holds so few poses per SM that an iteration is bound by the
 // rendezvous, not by HBM (<= ~250 k poses per GPU: 4 and 8 GPUs on the 1 M-pose graph):
 //   * every CTA owns a contiguous run of `chunk` CTA tiles; a group of four warps works on one
-//     tile with plain loads (the working set is L2 resident), no copy ring, no service warps;
+//     tile with plain loads, no copy ring, no service warps; the tile records, the CTA's own z
+//     tiles and its ELLPACK rows stay in shared memory for the whole solve when they fit (host
+//     plan in TSolveArgs::lite_*), the rest of the working set is L2 resident;
 //   * one rendezvous per phase and node: arrive on the node's monotonic counter, spin until all
 //     CTAs that hold tiles of the node have arrived, then EVERY such CTA sums the node's
 //     per-tile partials itself (same fixed order => same scalars everywhere).  The chain
@@ -594,8 +596,8 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
 // Partials are double buffered by round parity: a CTA that is already in round r+1 must not
 // overwrite what a slower CTA still sums for round r.
 // =============================================================================
-constexpr int TSL_MAXSEG = 32;
-constexpr int TSL_NG = 7;        // four-warp groups per lite CTA (one tile each at a time)    // node segments (runs of tiles of one active node) per CTA
+constexpr int TSL_MAXSEG = TSL_MAXT;   // node segments (runs of tiles of one active node) per CTA
+constexpr int TSL_NG = 7;              // four-warp groups per CTA, one tile each at a time (896 threads, 72 registers)
 
 template <int D, int NG>
 __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
