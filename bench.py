@@ -37,6 +37,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", default="100,100,100", help="nx,ny,nz of the synthetic SE(3) grid")
+    ap.add_argument("--workload", default="grid", choices=["grid", "sphere"],
+                    help="grid: BASELINE.json configs[3] (the metric's workload); sphere: configs[4]-shaped multi-robot "
+                         "sphere, --nodes robots of --poses-per-robot poses (secondary line, not the headline)")
+    ap.add_argument("--poses-per-robot", type=int, default=39063)
     ap.add_argument("--nodes", type=int, default=64)
     ap.add_argument("--loss", default="trivial")
     ap.add_argument("--algorithm", default="star", choices=["star", "hash"])
@@ -46,6 +50,10 @@ def parse():
 
 
 def workload_name(args, N, E):
+    if args.workload == "sphere":
+        return ("synthetic multi-robot SE(3) sphere (BASELINE.json configs[4] shape), %d poses / %d edges, %d robot "
+                "nodes of %d poses, %s loss, %s" % (N, E, args.nodes, args.poses_per_robot, args.loss,
+                                                    "AMM-PGO*" if args.algorithm == "star" else "AMM-PGO#"))
     return ("synthetic %s SE(3) grid, %d poses / %d edges, %d robot nodes, %s loss, %s"
             % (args.grid.replace(",", "x"), N, E, args.nodes, args.loss,
                "AMM-PGO*" if args.algorithm == "star" else "AMM-PGO#"))
@@ -181,8 +189,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    nx, ny, nz = (int(v) for v in args.grid.split(","))
-    g, _, X0 = D.grid3d(nx, ny, nz)
+    if args.workload == "sphere":
+        g, _, X0 = D.sphere_rings(args.nodes, args.poses_per_robot)
+    else:
+        nx, ny, nz = (int(v) for v in args.grid.split(","))
+        g, _, X0 = D.grid3d(nx, ny, nz)
     N, E, d = g.num_poses, g.num_edges, g.d
     opts = D.Options(loss=args.loss, device=local_rank)
     drv = multi.make_driver(g, args.nodes, opts, args.algorithm, rank, world)
@@ -319,12 +330,14 @@ def run_ours(args):
         e2e = multi.e2e_multi(drv, X0, args.e2e_steps, E, d, N)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "grid":
         cpu, _, _ = cpu_baseline_run(args, 2, 0)
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "metric": METRIC if args.workload == "grid" else
+            "AMM-PGO%s edge-updates/s on a multi-robot SE(3) sphere shard" % ("*" if args.algorithm == "star" else "#"),
+            "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, N, E),
