@@ -219,6 +219,16 @@ int mmpgo_plan_halo(int64_t num_poses, int32_t num_nodes, int64_t num_edges, con
                            send_counts, recv_counts, send_gids, send_capacity, recv_gids, recv_capacity));
 }
 
+int mmpgo_plan_halo_pair(int32_t world_size, const int64_t *send_poses, const int64_t *recv_poses, int64_t n_own,
+                         int32_t *send_a, int32_t *send_b, int32_t *recv_a, int32_t *recv_b, int32_t *halo_row) {
+  if (world_size < 1 || !send_poses || !recv_poses || !send_a || !send_b || !recv_a || !recv_b || !halo_row) {
+    mmpgo::set_error("bad argument");
+    return MMPGO_ERR_ARG;
+  }
+  mmpgo::plan_halo_pair(world_size, send_poses, recv_poses, n_own, send_a, send_b, recv_a, recv_b, halo_row);
+  return MMPGO_OK;
+}
+
 int mmpgo_profile_pass(mmpgo_handle hh, int32_t kind, int32_t reps, float *ms_avg) {
   H_OR_FAIL(hh);
   if (!ms_avg) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }

@@ -161,6 +161,8 @@ int driver_iterate(Handle *h);
 int driver_communicate(Handle *h);
 int driver_get_poses(Handle *h, double *X, int64_t ldx);
 int driver_get_weights(Handle *h, int node, double *w, int64_t cap, int64_t *count);
+void plan_halo_pair(int world, const int64_t *send_poses, const int64_t *recv_poses, int64_t n_own, int32_t *sa,
+                    int32_t *sb, int32_t *ra, int32_t *rb, int32_t *hrow);
 int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f);
 int driver_evaluate_grad(Handle *h, const double *X, int64_t ldx, double *G, int64_t ldg);
 int driver_current_objective(Handle *h, double *f, double *g2);

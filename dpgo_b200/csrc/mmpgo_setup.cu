@@ -561,6 +561,20 @@ int plan_halo(int64_t N, int num_nodes, int64_t E, const int32_t *ei, const int3
   return 0;
 }
 
+void plan_halo_pair(int world, const int64_t *send_poses, const int64_t *recv_poses, int64_t n_own, int32_t *sa,
+                    int32_t *sb, int32_t *ra, int32_t *rb, int32_t *hrow) {
+  int64_t so = 0, ro = 0;
+  for (int q = 0; q < world; ++q) {
+    const int64_t sc = send_poses[q], rcq = recv_poses[q];
+    for (int64_t i = 0; i < sc; ++i) { sa[so + i] = (int32_t)(2 * so + i); sb[so + i] = (int32_t)(2 * so + sc + i); }
+    for (int64_t i = 0; i < rcq; ++i) {
+      ra[ro + i] = (int32_t)(2 * ro + i); rb[ro + i] = (int32_t)(2 * ro + rcq + i);
+      hrow[ro + i] = (int32_t)(n_own + ro + i);
+    }
+    so += sc; ro += rcq;
+  }
+}
+
 int driver_set_sharding(Handle *h, int rank, int world, const int32_t *rnb, mmpgo_exchange_fn ex,
                         mmpgo_allreduce_fn ar, void *user) {
   if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
@@ -601,17 +615,9 @@ int driver_set_sharding(Handle *h, int rank, int world, const int32_t *rnb, mmpg
   // two-array exchange (AMM-PGO*: X^{k+1/2} and X^{k+1} travel in ONE all-to-all): per peer the
   // chunk is [poses of array a | poses of array b]; index maps for the pack / unpack copies
   {
-    std::vector<int> sa, sb, ra, rb, hrow;
-    int64_t so = 0, ro = 0;
-    for (int q = 0; q < world; ++q) {
-      const int64_t sc = h->send_poses[q], rcq = h->recv_poses[q];
-      for (int64_t i = 0; i < sc; ++i) { sa.push_back((int)(2 * so + i)); sb.push_back((int)(2 * so + sc + i)); }
-      for (int64_t i = 0; i < rcq; ++i) {
-        ra.push_back((int)(2 * ro + i)); rb.push_back((int)(2 * ro + rcq + i));
-        hrow.push_back((int)(h->NO + ro + i));
-      }
-      so += sc; ro += rcq;
-    }
+    std::vector<int> sa((size_t)h->n_send), sb((size_t)h->n_send), ra((size_t)h->NH), rb((size_t)h->NH), hrow((size_t)h->NH);
+    plan_halo_pair(world, h->send_poses.data(), h->recv_poses.data(), h->NO, sa.data(), sb.data(), ra.data(), rb.data(),
+                   hrow.data());
     h->send_dbl2.resize(world); h->recv_dbl2.resize(world);
     for (int q = 0; q < world; ++q) { h->send_dbl2[q] = 2 * h->send_dbl[q]; h->recv_dbl2[q] = 2 * h->recv_dbl[q]; }
     if ((rc = upload(h, &h->d_send2_a, sa))) return rc;

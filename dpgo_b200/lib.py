@@ -88,6 +88,7 @@ SIGNATURES = {
     "mmpgo_halo_counts": (C.c_int, [_P, _lp, _lp]),
     "mmpgo_plan_halo": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _ip, _ip, C.c_int32, _ip, C.c_int32,
                                   _lp, _lp, _lp, C.c_int64, _lp, C.c_int64]),
+    "mmpgo_plan_halo_pair": (C.c_int, [C.c_int32, _lp, _lp, C.c_int64, _ip, _ip, _ip, _ip, _ip]),
     "mmpgo_version": (C.c_char_p, []),
     "mmpgo_last_error": (C.c_char_p, []),
     "mmpgo_default_options": (None, [C.POINTER(Options)]),

@@ -42,6 +42,20 @@ def plan_halo(graph, num_nodes, world, rank):
     return sc, rc, sg[: int(sc.sum())], rg[: int(rc.sum())]
 
 
+def plan_halo_pair(send_counts, recv_counts, n_own):
+    """Host-only index maps of the two-array exchange (mmpgo_plan_halo_pair): (send_a, send_b,
+    recv_a, recv_b, halo_row), in poses."""
+    lib = L.load()
+    sc = np.ascontiguousarray(send_counts, dtype=np.int64)
+    rc = np.ascontiguousarray(recv_counts, dtype=np.int64)
+    ns, nr = max(int(sc.sum()), 1), max(int(rc.sum()), 1)
+    out = [np.zeros(ns, dtype=np.int32), np.zeros(ns, dtype=np.int32), np.zeros(nr, dtype=np.int32),
+           np.zeros(nr, dtype=np.int32), np.zeros(nr, dtype=np.int32)]
+    lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    L.check(lib.mmpgo_plan_halo_pair(len(sc), lp(sc), lp(rc), int(n_own), *[L.iptr(a) for a in out]))
+    return [a[: int(sc.sum())] for a in out[:2]] + [a[: int(rc.sum())] for a in out[2:]]
+
+
 class _DevArray:
     """Zero-copy view of a raw device pointer for torch.as_tensor."""
 

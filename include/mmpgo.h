@@ -190,6 +190,15 @@ int mmpgo_plan_halo(int64_t num_poses, int32_t num_nodes, int64_t num_edges, con
                     int32_t rank, int64_t *send_counts, int64_t *recv_counts, int64_t *send_gids,
                     int64_t send_capacity, int64_t *recv_gids, int64_t recv_capacity);
 
+/* Host-only: index maps of the TWO-array halo exchange of AMM-PGO* (the boundary poses of
+ * X^{k+1/2} and X^{k+1}, whose global objectives DPGOStar::iterate evaluates, DPGOStar.cpp:147-159,
+ * travel in one all-to-all).  Per peer the wire chunk is [poses of array a | poses of array b].
+ * send_a/send_b[i]: slot (in poses) of the i-th boundary pose of the send list in the send buffer;
+ * recv_a/recv_b[k], halo_row[k]: slot of the k-th halo pose in the receive buffer and its row in the
+ * pose arrays (n_own + k).  Lengths: sum(send_poses) and sum(recv_poses). */
+int mmpgo_plan_halo_pair(int32_t world_size, const int64_t *send_poses, const int64_t *recv_poses, int64_t n_own,
+                         int32_t *send_a, int32_t *send_b, int32_t *recv_a, int32_t *recv_b, int32_t *halo_row);
+
 /* AMM-PGO* master-node scalars: F (the running average, DPGOStar.cpp:210),
  * the last accepted global objective and the number of global restarts. */
 int mmpgo_star_objective(mmpgo_handle h, double *F, double *fobj, int32_t *restarts);

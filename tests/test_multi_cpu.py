@@ -47,6 +47,22 @@ def _worker(rank, world, port, nodes, q):
             from oracle import g2o as og2o
             node, _ = og2o.partition_index(g.num_poses, nodes, ids)
             ok = ok and bool(np.all((node >= rnb[peer]) & (node < rnb[peer + 1])))
+        # two-array exchange of AMM-PGO* (per-peer chunks [a | b]): pack with the library's index
+        # maps, ONE all_to_all with doubled counts, unpack into the halo rows of both arrays
+        n_own = 1000 + rank                        # any row offset of the halo
+        sa, sb, ra, rb, hrow = multi.plan_halo_pair(sc, rc, n_own)
+        ns, nr = int(sc.sum()), int(rc.sum())
+        buf = np.zeros(2 * ns)
+        buf[sa] = sg                               # array a carries the pose id, array b its negative
+        buf[sb] = -sg.astype(np.float64) - 0.5
+        recv2 = torch.empty(2 * nr, dtype=torch.float64)
+        dist.all_to_all_single(recv2, torch.from_numpy(buf), [2 * int(x) for x in rc], [2 * int(x) for x in sc])
+        xa, xb = np.zeros(n_own + nr), np.zeros(n_own + nr)
+        xa[hrow] = recv2.numpy()[ra]
+        xb[hrow] = recv2.numpy()[rb]
+        ok = ok and np.array_equal(xa[n_own:], rg.astype(np.float64))
+        ok = ok and np.array_equal(xb[n_own:], -rg.astype(np.float64) - 0.5)
+        ok = ok and np.array_equal(hrow, n_own + np.arange(nr))
         q.put((rank, bool(ok), int(sc.sum())))
     finally:
         dist.destroy_process_group()
