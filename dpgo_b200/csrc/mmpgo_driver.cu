@@ -177,7 +177,7 @@ template <int D> struct Drv {
   static GPassArgs gargs(Handle *h, const double *diag = nullptr) {
     GPassArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.rowptr = h->d_rowptr; a.col = h->d_col; a.blk = h->d_blk;
+    a.rowptr = h->d_rowptr; a.col = h->d_col; a.blk = h->d_blk; a.blk0 = h->d_blk0;
     a.diag = diag ? diag : h->d_gdiag; a.partials = h->d_partials;
     return a;
   }

@@ -68,6 +68,7 @@ struct Handle {
   int *d_active2 = nullptr;
   // static operators
   int *d_rowptr = nullptr, *d_col = nullptr;
+  double *d_blk0 = nullptr;       // [nnz][d+1] row 0 of every off-diagonal block (G01 pass)
   double *d_blk = nullptr, *d_gdiag = nullptr, *d_dintra = nullptr, *d_dinter = nullptr;
   double *d_tnv = nullptr, *d_pinv = nullptr;
   double *d_a00 = nullptr, *d_d00 = nullptr;

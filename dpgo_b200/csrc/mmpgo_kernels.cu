@@ -268,12 +268,60 @@ k_gpass(Tiles tl, GPassArgs a) {
   }
 }
 
+// G_RHS_T as its own kernel: rhs_t = g_t + G01 Y needs only row 0 of every block and the rotation
+// rows of the neighbours.  One thread per pose (in k_gpass three of the four row threads idle in this
+// mode), row 0 of the blocks from the compact array blk0; same accumulation order as k_gpass.
+template <int D>
+__global__ void __launch_bounds__(TILE) k_g01(Tiles tl, GPassArgs a) {
+  constexpr int R = Dim<D>::R, PB = Dim<D>::PB, SYM = Dim<D>::SYM, DD = D * D;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  if ((int)threadIdx.x >= tl.cnt[tile]) return;
+  const int p = tl.start[tile] + threadIdx.x;
+  double acc[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) acc[c] = 0.0;
+  const int e0 = a.rowptr[p], e1 = a.rowptr[p + 1];
+  int qn = e0 < e1 ? __ldg(a.col + e0) : 0;
+#pragma unroll 2
+  for (int e = e0; e < e1; ++e) {
+    const int q = qn;
+    qn = e + 1 < e1 ? __ldg(a.col + e + 1) : 0;
+    const double *b = a.blk0 + (size_t)e * R;
+    const double *xq = a.x + (size_t)q * PB + D;          // rotation rows of the neighbour
+    double br[R], xr[DD];
+#pragma unroll
+    for (int k = 1; k < R; ++k) br[k] = __ldg(b + k);
+#pragma unroll
+    for (int k = 0; k < DD; ++k) xr[k] = __ldg(xq + k);
+#pragma unroll
+    for (int k = 1; k < R; ++k) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[c] = fma(br[k], xr[(k - 1) * D + c], acc[c]);
+    }
+  }
+  const double *dg = a.diag + (size_t)p * SYM;
+  const double *xp = a.x + (size_t)p * PB + D;
+#pragma unroll
+  for (int k = 1; k < R; ++k) {
+    const double dv = dg[symidx(0, k)];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = fma(dv, xp[(k - 1) * D + c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const double gv = a.g ? a.g[(size_t)p * PB + c] : 0.0;
+    a.out[(size_t)p * D + c] = gv + acc[c];
+  }
+}
+
 template <int D> void launch_gpass(int mode, const Tiles &tl, const GPassArgs &a, cudaStream_t s) {
   const dim3 grid(tl.n_tiles), block(TILE * (D + 1));
   switch (mode) {
     case G_EVAL: k_gpass<D, G_EVAL><<<grid, block, 0, s>>>(tl, a); break;
     case G_GRAD: k_gpass<D, G_GRAD><<<grid, block, 0, s>>>(tl, a); break;
-    case G_RHS_T: k_gpass<D, G_RHS_T><<<grid, block, 0, s>>>(tl, a); break;
+    case G_RHS_T: k_g01<D><<<grid, TILE, 0, s>>>(tl, a); break;
     case G_REDGRAD: k_gpass<D, G_REDGRAD><<<grid, block, 0, s>>>(tl, a); break;
     case G_HV: k_gpass<D, G_HV><<<grid, block, 0, s>>>(tl, a); break;
   }

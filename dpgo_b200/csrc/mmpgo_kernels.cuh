@@ -44,6 +44,7 @@ struct GPassArgs {
   const int *rowptr;      // [NO+1]
   const int *col;         // [nnz] own pose index
   const double *blk;      // [nnz][(d+1)^2] off-diagonal blocks, row-major
+  const double *blk0;     // [nnz][d+1] row 0 of every block (G_RHS_T reads only these)
   const double *diag;     // [NO][SYM] packed lower-triangular diagonal block
   const double *x;        // input pose-block vector (gathered)
   const double *g;        // additive vector (may be null)

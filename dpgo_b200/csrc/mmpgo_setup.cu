@@ -443,6 +443,14 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   if ((rc = upload(h, &h->d_rowptr, rowptr))) return rc;
   if ((rc = upload(h, &h->d_col, col))) return rc;
   if ((rc = upload(h, &h->d_blk, blk))) return rc;
+  {
+    // row 0 of every off-diagonal block, contiguous: the G01 pass (k_g01) streams only these
+    const int Rr0 = d + 1;
+    std::vector<double> blk0((size_t)nnz * Rr0);
+    for (int64_t s2 = 0; s2 < nnz; ++s2)
+      for (int c = 0; c < Rr0; ++c) blk0[(size_t)s2 * Rr0 + c] = blk[(size_t)s2 * BB + c];
+    if ((rc = upload(h, &h->d_blk0, blk0))) return rc;
+  }
   if ((rc = upload(h, &h->d_gdiag, gdiag))) return rc;
   if ((rc = upload(h, &h->d_dintra, dintra))) return rc;
   if ((rc = upload(h, &h->d_dinter, dinter))) return rc;
