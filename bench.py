@@ -63,28 +63,68 @@ def workload_name(args, N, E):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md, the nvidia-smi clocks
+    line).  Sampled in-process through NVML (the library nvidia-smi itself queries): spawning nvidia-smi
+    from a process with torch loaded holds the GIL for tens of milliseconds per fork, which showed up as
+    a 30 % slower 0.2 s timed region in one run.  Falls back to the nvidia-smi subprocess without pynvml."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.samples = []
+        self.samples = []          # [sm_mhz, sm_max_mhz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap]
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                          pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)       # probe once outside the timed region
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self._nvml, self._h, self.source = pynvml, h, "nvml"
+        except Exception:
+            self._nvml = None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._h
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        self.samples.append([sm, self._mx] + [bool(r & b) for b in self._bits])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip().splitlines()
+        if out:
+            f = [x.strip() for x in out[0].split(",")]
+            self.samples.append([float(f[0]), float(f[1])] + [v.lower().startswith("active") for v in f[2:6]])
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip().splitlines()
-                if out:
-                    self.samples.append([x.strip() for x in out[0].split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t.start()
@@ -97,12 +137,11 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({n for s in self.samples for n, v in zip(self.NAMES, s[2:6]) if v})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": reasons,
+                "samples": len(self.samples), "source": self.source}
 
 
 def measured_peak():
@@ -219,12 +258,20 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     drv.reset_counters()
     barrier()
-    with ClockSampler(local_rank) as clk:
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    import gc
+    gc.collect()
+    gc.disable()                     # no collector pause inside the timed region
+    with ClockSampler(local_rank, dev_uuid) as clk:
         e0.record(stream)
         for _ in range(args.steps):
             step()
         e1.record(stream)
         barrier()
+    gc.enable()
     ms = e0.elapsed_time(e1)
     ctr = drv.counters()
     if world > 1:
