@@ -160,7 +160,7 @@ def ncu_traffic(kernel_key):
 
 
 # ---------------------------------------------------------------------------
-def cpu_baseline_run(args, steps, warmup, sample_grid=(100, 125, 5), sample_nodes=4):
+def cpu_baseline_run(args, steps, warmup, sample_grid=(100, 125, 5), sample_nodes=4, workers=1):
     """The restated CPU reference (oracle, numpy/scipy, 1 thread) on a bounded sample of the
     same workload: same per-node size (15625 poses per robot node, slab-shaped), same loss
     and algorithm; setup (matrix assembly, factorisations) excluded as in dist_pgo."""
@@ -175,17 +175,28 @@ def cpu_baseline_run(args, steps, warmup, sample_grid=(100, 125, 5), sample_node
     timing = {}
     iters = max(1, steps)
     t0 = time.perf_counter()
-    odist.run(meas, g.num_poses, sample_nodes, opts, X0, iters, args.algorithm, log_global=False,
-              timing=timing)
+    workers = max(1, min(workers, sample_nodes)) if args.algorithm == "star" else 1
+    try:
+        odist.run(meas, g.num_poses, sample_nodes, opts, X0, iters, args.algorithm, log_global=False,
+                  timing=timing, workers=workers)
+    except Exception as e:                     # the multi-process runner must never cost the run: serial fallback
+        if workers == 1:
+            raise
+        print("parallel oracle failed (%r), serial fallback" % (e,), file=sys.stderr)
+        workers, timing = 1, {}
+        t0 = time.perf_counter()
+        odist.run(meas, g.num_poses, sample_nodes, opts, X0, iters, args.algorithm, log_global=False, timing=timing)
     wall = time.perf_counter() - t0
     secs = timing["seconds"]
+    how = ("" if workers == 1 else "; per-node work in %d forked worker processes, global objective and restart "
+           "decisions on the master (oracle/parallel.py)" % workers)
     return {
-        "value": g.num_edges * iters / secs, "unit": UNIT, "cores": 1, "kind": "port",
+        "value": g.num_edges * iters / secs, "unit": UNIT, "cores": workers, "kind": "port",
         "sample": "%dx%dx%d SE(3) grid slab (%d poses / %d edges, %d robot nodes of %d poses = the "
                   "per-node size of the full workload), %d iterations, %.1f s in iterate+update+"
-                  "communicate (setup %.1f s excluded)" % (
+                  "communicate (setup %.1f s excluded)%s" % (
                       sample_grid + (g.num_poses, g.num_edges, sample_nodes, g.num_poses // sample_nodes,
-                                     iters, secs, wall - secs)),
+                                     iters, secs, wall - secs, how)),
     }, secs, iters
 
 
@@ -196,7 +207,10 @@ def run_reference(args):
     nx, ny, nz = (int(v) for v in args.grid.split(","))
     N, E = nx * ny * nz, 4 * nx * ny * nz
     steps = max(1, min(args.steps, 3))
-    cb, secs, iters = cpu_baseline_run(args, steps, 0)
+    # all the host threads the restated reference can use: one worker process per robot node of the sample
+    # (this arm runs in a process without CUDA or torch threads, so forking is safe here; the in-process
+    # cpu_baseline of the CUDA arm stays single-threaded)
+    cb, secs, iters = cpu_baseline_run(args, steps, 0, workers=min(4, os.cpu_count() or 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / iters,

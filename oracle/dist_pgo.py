@@ -68,10 +68,11 @@ def odometry_initialization(num_poses, meas):
 
 
 def run(meas, num_poses, num_nodes, opts, X0, iters, algorithm="hash",
-        log_global=True, timing=None):
+        log_global=True, timing=None, workers=1):
     """Returns dict(trace=[(2F, 2|grad|)...], X=global X, per-node scalars).
     `timing`, if a dict, receives seconds spent in iterate/update/communicate
-    (what dist_pgo.cpp:496-521 times, plus communicate)."""
+    (what dist_pgo.cpp:496-521 times, plus communicate).  `workers` > 1 (AMM-PGO* only) spreads the
+    per-node work over forked processes (oracle/parallel.py; same iterates, CPU-baseline timing)."""
     per_node, g_index, part = g2o.partition(num_poses, num_nodes, meas)
     d = meas.d
     gobj = dpgo.GlobalObjective(num_poses, num_nodes, meas, part, opts)
@@ -111,7 +112,11 @@ def run(meas, num_poses, num_nodes, opts, X0, iters, algorithm="hash",
         out["weights"] = [getattr(h.problem, "last_weights", None) for h in hashes]
         out["hashes"] = hashes
     elif algorithm == "star":
-        star = dpgo.DPGOStar(num_nodes, per_node, g_index, num_poses, gobj, opts)
+        if workers > 1:
+            from . import parallel
+            star = parallel.ParallelDPGOStar(num_nodes, per_node, g_index, num_poses, gobj, opts, workers=workers)
+        else:
+            star = dpgo.DPGOStar(num_nodes, per_node, g_index, num_poses, gobj, opts)
         star.initialize(X0)
         X = X0
         for it in range(iters + 1):
@@ -129,7 +134,9 @@ def run(meas, num_poses, num_nodes, opts, X0, iters, algorithm="hash",
             star.communicate()
             t_acc += time.perf_counter() - t0
             out["refined"].append([st.last_refined for st in star.results])
-        X = star.Xk
+        X = np.array(star.Xk)
+        if workers > 1:
+            star.close()
         out["tcg"] = [st.tcg_iters for st in star.results]
         out["restarts"] = star.n_global_restarts if hasattr(star, "n_global_restarts") else 0
         out["weights"] = [getattr(p, "last_weights", None) for p in star.problems]

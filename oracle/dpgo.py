@@ -704,10 +704,16 @@ class DPGOStar:
 
     # DPGOStar.cpp:315-390
     def update(self):
-        for a, p in enumerate(self.problems):
+        for a in range(self.num_nodes):
+            self._update_n(a)
+        return 0
+
+    def _update_n(self, a):
+        p = self.problems[a]
+        if True:
             st = self.results[a]
             if st.updated:
-                continue
+                return
             it = st.iters
             X_it = st.Xk.copy()
             if p.quadratic:
@@ -730,7 +736,6 @@ class DPGOStar:
                 st.gamma = (s0 - 1) / st.s[it + 1]
             st.Fk = [fobj, fobj]
             st.updated = True
-        return 0
 
     # DPGOStar.cpp:392-550
     def _amm_pgo_n(self, a):
@@ -779,6 +784,24 @@ class DPGOStar:
         st.Xakh = p.proximal(st.Xk, st.Dfobj_cur)
         self._put(self.Xkh, a, st.Xakh)
 
+    def _restart_n(self, a):
+        st = self.results[a]
+        self._mm_pgo_n(a)
+        st.s[st.iters + 1] = max(0.5 * st.s[st.iters + 1], 1.0)
+
+    def _safeguard_n(self, a):
+        st, p = self.results[a], self.problems[a]
+        n0 = p.n[0]
+        st.Xak[n0:] = st.Xakh[n0:]
+        st.Xak[:n0] = p.recover_translations(st.Xak[n0:], st.g_cur)
+        self._put(self.Xkp, a, st.Xak)
+
+    def _finish_n(self, a):
+        st, p = self.results[a], self.problems[a]
+        st.iters += 1
+        st.Xk[:p.size0] = st.Xak
+        st.updated = False
+
     # DPGOStar.cpp:126-213
     def iterate(self):
         o = self.opts
@@ -794,23 +817,14 @@ class DPGOStar:
         if fobj > self.F - o.psi * float(np.sum(np.square(self.Xkp - self.Xk))):
             self.n_global_restarts += 1
             for a in range(self.num_nodes):
-                st = self.results[a]
-                self._mm_pgo_n(a)
-                st.s[st.iters + 1] = max(0.5 * st.s[st.iters + 1], 1.0)
+                self._restart_n(a)
             fobj = self.gobj.evaluate_f(self.Xkp)
         if self.F - fobj < o.phi * (self.F - fobjh):
             for a in range(self.num_nodes):
-                st, p = self.results[a], self.problems[a]
-                n0 = p.n[0]
-                st.Xak[n0:] = st.Xakh[n0:]
-                st.Xak[:n0] = p.recover_translations(st.Xak[n0:], st.g_cur)
-                self._put(self.Xkp, a, st.Xak)
+                self._safeguard_n(a)
             fobj = self.gobj.evaluate_f(self.Xkp)
         for a in range(self.num_nodes):
-            st, p = self.results[a], self.problems[a]
-            st.iters += 1
-            st.Xk[:p.size0] = st.Xak
-            st.updated = False
+            self._finish_n(a)
         self.Xk, self.Xkp = self.Xkp, self.Xk
         self.fobj = fobj
         self.F = self.F * (1 - o.eta[0]) + fobj * o.eta[0]
@@ -824,3 +838,13 @@ class DPGOStar:
             st.Xk[p.size0:] = Zs[a][p.size0:]
             st.updated = False
         return 0
+
+    def _communicate_n(self, a):
+        """communicate() for one node (same values; used by the multi-process runner)."""
+        p, st, d, N = self.problems[a], self.results[a], self.d, self.num_poses
+        n0, n1 = p.n
+        ng = p.nbr_gid
+        base = (d + 1) * n0
+        st.Xk[base:base + n1] = self.Xk[ng]
+        st.Xk[base + n1:] = self.Xk[(N + d * ng[:, None] + np.arange(d)).ravel()]
+        st.updated = False
