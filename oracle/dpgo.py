@@ -710,32 +710,31 @@ class DPGOStar:
 
     def _update_n(self, a):
         p = self.problems[a]
-        if True:
-            st = self.results[a]
-            if st.updated:
-                return
-            it = st.iters
-            X_it = st.Xk.copy()
-            if p.quadratic:
-                g, f = p.evaluate_none_g_and_f0(X_it)
-                fobj = p.evaluate_G(st.Xak, g, f)
-                Dfobj = g + p.G @ st.Xak
-            else:
-                g, f, Dfobj, fobj, st.DfobjE, st.fobjE = p.evaluate_g_and_f0(X_it)
-            st.Gk = fobj
-            st.gradF = p.full_tangent_space_projection(st.Xak, Dfobj)
-            st.gradFnorm = float(np.linalg.norm(st.gradF))
-            if it > 0:
-                st.X_prev, st.g_prev, st.Dfobj_prev = st.X_cur, st.g_cur, st.Dfobj_cur
-            st.X_cur, st.g_cur, st.Dfobj_cur, st.fobj_cur, st.f_cur = X_it, g, Dfobj, fobj, f
-            if self.opts.scheme == "AMM":
-                if it == 0:
-                    st.s[0] = 1.0
-                s0 = st.s[it]
-                st.s[it + 1] = 0.5 + 0.5 * math.sqrt(4.0 * s0 * s0 + 1.0)
-                st.gamma = (s0 - 1) / st.s[it + 1]
-            st.Fk = [fobj, fobj]
-            st.updated = True
+        st = self.results[a]
+        if st.updated:
+            return
+        it = st.iters
+        X_it = st.Xk.copy()
+        if p.quadratic:
+            g, f = p.evaluate_none_g_and_f0(X_it)
+            fobj = p.evaluate_G(st.Xak, g, f)
+            Dfobj = g + p.G @ st.Xak
+        else:
+            g, f, Dfobj, fobj, st.DfobjE, st.fobjE = p.evaluate_g_and_f0(X_it)
+        st.Gk = fobj
+        st.gradF = p.full_tangent_space_projection(st.Xak, Dfobj)
+        st.gradFnorm = float(np.linalg.norm(st.gradF))
+        if it > 0:
+            st.X_prev, st.g_prev, st.Dfobj_prev = st.X_cur, st.g_cur, st.Dfobj_cur
+        st.X_cur, st.g_cur, st.Dfobj_cur, st.fobj_cur, st.f_cur = X_it, g, Dfobj, fobj, f
+        if self.opts.scheme == "AMM":
+            if it == 0:
+                st.s[0] = 1.0
+            s0 = st.s[it]
+            st.s[it + 1] = 0.5 + 0.5 * math.sqrt(4.0 * s0 * s0 + 1.0)
+            st.gamma = (s0 - 1) / st.s[it + 1]
+        st.Fk = [fobj, fobj]
+        st.updated = True
 
     # DPGOStar.cpp:392-550
     def _amm_pgo_n(self, a):
