@@ -66,6 +66,7 @@ static int reduce_to_host(Handle *h, const double **out) {
   launch_reduce(h->A, h->d_node_tb, h->d_node_te, h->d_partials, h->d_node_scal, h->stream);
   h->ctr.launches++;
   CK(cudaMemcpyAsync(h->h_pinned, h->d_node_scal, sizeof(double) * h->A * NS, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   *out = h->h_pinned;
   return 0;
@@ -83,6 +84,7 @@ static int reduce_async(Handle *h, int slot) {
 }
 static const double *slot_host(Handle *h, int slot) { return h->h_slot + (size_t)slot * h->A * NS; }
 static int host_sync(Handle *h) {
+  CK(cudaGetLastError());             // a failed launch configuration of any kernel enqueued since the last check
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -591,6 +593,13 @@ template <int D> struct Drv {
     Mask m(A, 0);
     for (int n = 0; n < A; ++n) m[n] = !h->st[n].updated;
     if (!any(m)) return 0;
+    // all nodes of a handle advance in lock step (one batched launch per operation): batch-wide
+    // decisions below (first update, history terms) are taken once for the whole handle
+    for (int n = 0; n < A; ++n)
+      if (!m[n] || h->st[n].iters != h->st[0].iters) {
+        set_error("update(): the nodes of a handle must share the iteration count and the updated state");
+        return MMPGO_ERR_STATE;
+      }
     const bool star = o.algorithm == MMPGO_ALG_STAR;
     const bool trivial = o.loss == MMPGO_LOSS_NONE;
     // rotate history: the "current" slot becomes "previous"
@@ -982,15 +991,22 @@ template <int D> struct Drv {
     else if (h->opt.scheme == MMPGO_SCHEME_AMM) RC(hash_amm(h));
     else RC(hash_mm(h));
     for (int n = 0; n < h->A; ++n) { h->st[n].iters++; h->st[n].updated = false; }
+    // publish X^{k+1}: the reference copies Xak into the head of Xk at the end of iterate()
+    // (DPGOHash.cpp:612-616, DPGOStar.cpp:194-208); on the device the three pose buffers rotate.
+    // The neighbour copies stay those of iteration k until communicate() refreshes them, as in
+    // the reference, so communicate() may be repeated or (for a graph without remote
+    // neighbours) skipped.
+    const int old_km1 = h->ikm1;
+    h->ikm1 = h->ik; h->ik = h->iak; h->iak = old_km1;
+    if (h->NH > 0 && !h->next_halo_current)
+      CK(cudaMemcpyAsync(h->X[h->ik] + (size_t)h->NO * PB, h->X[h->ikm1] + (size_t)h->NO * PB,
+                         sizeof(double) * (size_t)h->NH * PB, cudaMemcpyDeviceToDevice, h->stream));
     return 0;
   }
 
-  // publish X^{k+1}: the reference copies Xak into the head of Xk at the end of iterate()
-  // (DPGOHash.cpp:612-616) and neighbours pick it up in communicate(); on the device the
-  // three pose buffers rotate instead.
+  // DPGOHash::communicate (DPGOHash.h:28-86) / DPGOStar::communicate (DPGOStar.cpp:215-223): refresh
+  // the copies of the remote neighbours.  Neighbours on the same GPU are read in place.
   static int communicate(Handle *h) {
-    const int old_km1 = h->ikm1;
-    h->ikm1 = h->ik; h->ik = h->iak; h->iak = old_km1;
     if (h->next_halo_current) { h->next_halo_current = false; return 0; }
     return halo_exchange(h, h->X[h->ik]);
   }

@@ -32,8 +32,8 @@ CASES = [
     # name, file, nodes, loss, algorithm, iters, outlier fraction
     ("tinyGrid3D_n2_trivial_hash", "tinyGrid3D.g2o", 2, "trivial", "hash", 30, 0.0),
     ("smallGrid3D_n4_huber_star", "smallGrid3D.g2o", 4, "huber", "star", 30, 0.0),
-    ("sphere2500_n4_trivial_hash", "sphere2500.g2o", 4, "trivial", "hash", 50, 0.0),
-    ("city10000_n16_gm_hash", "city10000.g2o", 16, "gm", "hash", 20, 0.1),
+    ("sphere2500_n4_trivial_hash", "sphere2500.g2o", 4, "trivial", "hash", 1000, 0.0),
+    ("city10000_n16_gm_hash", "city10000.g2o", 16, "gm", "hash", 50, 0.1),
 ]
 
 

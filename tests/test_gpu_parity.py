@@ -330,3 +330,74 @@ def test_set_graph_rejects_bad_input():
     iso = D.PoseGraph(3, 64, iso.i[keep], iso.j[keep], g.R[keep], g.t[keep], g.kappa[keep], g.tau[keep])
     with pytest.raises(D.MmpgoError):
         D.DPGOHash(iso, 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: parity at the benchmarked node size, several handles per run, driver call order
+# ---------------------------------------------------------------------------------------------
+def test_config3_node_size_slab():
+    """BASELINE.json configs[3] per-node size: a 100 x 125 x 5 slab of the benchmark's grid generator =
+    4 robot nodes of 15 625 poses each (the 1 M-pose workload has 64 of them), AMM-PGO*, trivial loss,
+    sparse translation solve (no dense G00 inverse at this size), against the oracle."""
+    g, _, X0 = D.grid3d(100, 125, 5)
+    out = parity.run_both(g, 4, X0, 4, loss="trivial", algorithm="star", dense_solve_max_n=0)
+    _check(out, 3)
+    assert [out["drv"].node_scalars(a).n0 for a in range(4)] == [15625] * 4
+
+
+def test_config2_fifty_iterations():
+    """configs[1] stand-in (see test_config2_grid3d_standin) over the 50 iterations north_star names."""
+    g, _, X0 = D.grid3d(20, 20, 20, seed=2)
+    _check(parity.run_both(g, 8, X0, 50, loss="huber", algorithm="star"), 3, iters_checked=50)
+
+
+@pytest.mark.parametrize("alg,loss,dense", [("hash", "trivial", 2048), ("hash", "huber", 0), ("star", "trivial", 0),
+                                            ("star", "welsch", 2048)])
+@pytest.mark.parametrize("W", [2, 3])
+def test_sharded_handles_reproduce_single_handle(alg, loss, dense, W):
+    """W handles (one per rank of a W-GPU run) driven in lock step through the transport callbacks of
+    mmpgo_set_sharding reproduce the single-handle run: same exchange plan, packing kernels and halo
+    rows as the NCCL run, served in-process (tests/inproc_world.py) so that it runs on one GPU.
+    AMM-PGO# has no scalar collective: bit-identical.  AMM-PGO* sums its four global scalars in a
+    different association (per-rank partial sums), hence the tolerance."""
+    from inproc_world import InProcWorld
+    g, _, X0 = D.grid3d(12, 12, 12, seed=4)
+    nodes, iters = 6, 10
+    ref, tr = D.run_dist_pgo(g, nodes, X0, iters, D.Options(loss=loss, dense_solve_max_n=dense), alg)
+    tr = np.array([t[0] / 2 for t in tr])
+    world = InProcWorld(g, nodes, W, alg, loss=loss, dense_solve_max_n=dense)
+    trace, X = world.run(X0, iters)
+    assert all(rk.exchanges > 0 for rk in world.ranks)
+    if alg == "hash":
+        assert np.array_equal(X, ref.X()), np.abs(X - ref.X()).max()
+        assert np.abs(trace - tr).max() <= 1e-13 * np.abs(tr).max()
+    else:
+        assert all(rk.allreduces > 0 for rk in world.ranks)
+        assert np.abs(trace - tr).max() <= 1e-9 * np.abs(tr).max()
+        assert np.abs(X - ref.X()).max() < 1e-7
+
+
+def test_communicate_may_be_repeated_or_skipped(grid):
+    """The reference's iterate() publishes X^{k+1} itself (DPGOHash.cpp:612-616); communicate() only
+    refreshes neighbour copies and may be called twice, or not at all when every neighbour lives in
+    the same handle."""
+    g, _, X0 = grid
+    def run(pattern):
+        drv = D.DPGOHash(g, 4, D.Options(loss="huber"))
+        assert drv.initialize(X0) == 0 and drv.update() == 0
+        assert drv.communicate() == 0                         # before the first iterate: harmless
+        for _ in range(5):
+            assert drv.iterate() == 0
+            for _ in range(pattern):
+                assert drv.communicate() == 0
+            assert drv.update() == 0
+        return drv.X(), drv.objective()[0]
+    X1, f1 = run(1)
+    for pattern in (0, 2):
+        X, f = run(pattern)
+        assert f == f1 and np.array_equal(X, X1)
+    # results().Xk right after iterate() is the new iterate
+    drv = D.DPGOHash(g, 4)
+    assert drv.initialize(X0) == 0 and drv.update() == 0 and drv.iterate() == 0
+    assert np.abs(drv.X() - X0).max() > 1e-3
+    assert drv.iterate() == -3                                # MMPGO_ERR_STATE: update() first
