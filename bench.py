@@ -321,6 +321,11 @@ def run_ours(args):
     # write p, Ap; phase B: read x, p, Ap, z, write x, z  (11 vector streams of 8 d bytes)
     sell_bytes_per_pose = 12.0 * 2 * E_intra / max(NO, 1)
     b_iter = sell_bytes_per_pose + 16 + 8 * d * 11
+    sinfo = drv.solver_info()
+    direct = sinfo["solver"] == "direct"
+    # sparse direct solve (SURVEY.md section 8d solve model): both triangular sweeps read the factor once
+    # (8 B per entry of L each; the blocks are dense, no indices) + right-hand side in, solution out
+    direct_bytes = 16.0 * sinfo["factor_nnz"] + 2 * 8 * d * NO
     alg_bytes = {
         "k2_eval": 120 * E_intra + 192 * NO, "k2_grad": 120 * E_intra + 192 * NO,
         "k2_hv": 120 * E_intra + 192 * NO,
@@ -329,7 +334,7 @@ def run_ours(args):
         "k2_g01": (4 + 8 * (d + 1)) * 2 * E_intra + (8 * d * d + 16 * d + 8 * (d + 1)) * NO,
         "k1_inter": 120 * HE + 192 * NO, "k3_prox": 680 * NO,
         "edge_objective": 120 * sizes["owned_edges"] + 96 * NO,
-        "g00_solve": b_iter * solve_pose_iters,
+        "g00_solve": direct_bytes if direct else b_iter * solve_pose_iters,
     }
     # every translation solve is preceded by one G01 pass; the other K2 passes are full block-CSR passes
     n_g01 = min(per_step["g00_solves"], per_step["k2"])
@@ -337,7 +342,7 @@ def run_ours(args):
     share = {
         "k2 block-CSR pass": (per_step["k2"] - n_g01) * k2_full + n_g01 * k_ms["k2_g01"],
         "k2b translation solve": per_step["g00_solves"] * k_ms["g00_solve"] *
-                                 (pose_iters / solve_calls) / max(solve_pose_iters, 1.0),
+                                 (1.0 if direct else (pose_iters / solve_calls) / max(solve_pose_iters, 1.0)),
         "k1 inter-edge pass": per_step["k1_inter"] * k_ms["k1_inter"],
         "k3 fused proximal": per_step["k3_prox"] * k_ms["k3_prox"],
     }
@@ -345,12 +350,13 @@ def run_ours(args):
     # whole-step figure: algorithmic bytes of everything launched in one step / measured step time
     n_eobj = 2.0 if args.algorithm == "star" else 0.0
     step_bytes = ((per_step["k2"] - n_g01) * alg_bytes["k2_eval"] + n_g01 * alg_bytes["k2_g01"] +
-                  b_iter * pose_iters / args.steps +
+                  (direct_bytes * per_step["g00_solves"] if direct else b_iter * pose_iters / args.steps) +
                   (per_step["k1_inter"] - n_eobj) * alg_bytes["k1_inter"] + n_eobj * alg_bytes["edge_objective"] +
                   per_step["k3_prox"] * alg_bytes["k3_prox"] + ctr.vector_passes / args.steps * 96.0 * 2 * NO)
     lite = int(ctr.reserved[1]) > 0
-    names = {"k2b translation solve": ("g00_solve", ("k_tsolve_lite<3,7> (K2b persistent Jacobi-PCG translation solve, "
-                                                     "small-shard kernel)") if lite else
+    names = {"k2b translation solve": ("g00_solve", "k_mf_solve<3> (K2b sparse Cholesky sweeps, one persistent launch per solve)"
+                                       if direct else ("k_tsolve_lite<3,7> (K2b persistent Jacobi-PCG translation solve, "
+                                                       "small-shard kernel)") if lite else
                                        "k_tsolve<3> + resumed tail in k_tsolve_lite<3,7> (K2b persistent Jacobi-PCG translation solve)"),
              "k2 block-CSR pass": ("k2_eval", "k_gpass<3,G_EVAL> (K2 block-CSR connection-Laplacian pass)"),
              "k1 inter-edge pass": ("k1_inter", "k_inter<3> (K1 inter-node edge pass)"),
@@ -437,6 +443,7 @@ def run_ours(args):
                        "l2": "working set (graph %.0f MB + iterates) is larger than the 126 MB L2" % (
                            (sizes["bsr_entries"] * 132 + HE * 128) / 1e6),
                        "preconditioner": "BlockJacobi", "nodes_per_gpu": args.nodes // world,
+                       "translation_solver": sinfo,
                        "final_2F": 2 * F, "final_2gradnorm": 2 * gn},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_cost": ttc,
             "gpu_launches": int(ctr.launches), "clocks": clk.summary(),

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "mmpgo_driver.cuh"
+#include "mmpgo_mf.cuh"
 
 namespace mmpgo {
 static thread_local std::string g_err;
@@ -59,12 +60,14 @@ void mmpgo_default_options(mmpgo_options *o) {
   o->translation_solve_tol = 1e-12;
   o->translation_solve_max_iters = 4000;
   o->device = 0;
+  o->translation_solver = MMPGO_TSOLVE_AUTO;
 }
 
 int mmpgo_create(const mmpgo_options *opts, mmpgo_handle *out) {
   if (!opts || !out) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
   if (opts->loss < 0 || opts->loss > 3 || opts->preconditioner < 0 || opts->preconditioner > 2 ||
-      opts->algorithm < 0 || opts->algorithm > 1 || opts->scheme < 0 || opts->scheme > 1) {
+      opts->algorithm < 0 || opts->algorithm > 1 || opts->scheme < 0 || opts->scheme > 1 ||
+      opts->translation_solver < 0 || opts->translation_solver > 4) {
     mmpgo::set_error("invalid enum value in options");
     return MMPGO_ERR_ARG;
   }
@@ -177,6 +180,12 @@ int mmpgo_evaluate_grad(mmpgo_handle hh, const double *X, int64_t ldx, double *G
   GUARDED(mmpgo::driver_evaluate_grad(h, X, ldx, G, ldg));
 }
 
+int mmpgo_translation_solve(mmpgo_handle hh, const double *rhs, double *t) {
+  H_OR_FAIL(hh);
+  if (!rhs || !t) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::driver_translation_solve(h, rhs, t));
+}
+
 int mmpgo_current_objective(mmpgo_handle hh, double *fobj, double *grad_sqnorm) {
   H_OR_FAIL(hh);
   if (!fobj || !grad_sqnorm) { mmpgo::set_error("null output"); return MMPGO_ERR_ARG; }
@@ -263,6 +272,37 @@ int mmpgo_graph_sizes(mmpgo_handle hh, int64_t *sizes /* [8] */) {
   return MMPGO_OK;
 }
 
+int mmpgo_solver_info(mmpgo_handle hh, int64_t *info /* [8] */) {
+  H_OR_FAIL(hh);
+  if (!info || !h->graph_set) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
+  info[0] = !h->any_pcg ? 0 : h->use_direct ? MMPGO_TSOLVE_DIRECT
+            : h->ts_force_kernel == 1 ? MMPGO_TSOLVE_PCG_RING : h->ts_force_kernel == 2 ? MMPGO_TSOLVE_PCG_LITE : MMPGO_TSOLVE_PCG;
+  info[1] = h->mf_nnz; info[2] = h->mf_entries; info[3] = h->mf_height; info[4] = h->mf_supernodes;
+  info[5] = h->mf_tasks; info[6] = h->mf_grid; info[7] = h->dense_poses;
+  return MMPGO_OK;
+}
+
+int mmpgo_solver_stage_times(mmpgo_handle hh, double *us, int32_t *warp_jobs, int32_t *cta_jobs, int32_t capacity, int32_t *count) {
+  H_OR_FAIL(hh);
+  if (!count) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
+  const int n = h->use_direct ? (int)h->mf_stage_jobs.size() / 2 : 0;
+  *count = n;
+  if (!us || n == 0) return MMPGO_OK;
+  if (capacity < n) { mmpgo::set_error("buffer too small"); return MMPGO_ERR_ARG; }
+  std::vector<unsigned long long> t((size_t)n + 1);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess ||
+      cudaMemcpy(t.data(), h->mf.stage_ns, sizeof(unsigned long long) * (n + 1), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    mmpgo::set_error("stage time read-back failed");
+    return MMPGO_ERR_CUDA;
+  }
+  for (int i = 0; i < n; ++i) {
+    us[i] = 1e-3 * (double)(t[i + 1] - t[i]);
+    if (warp_jobs) warp_jobs[i] = h->mf_stage_jobs[2 * i];
+    if (cta_jobs) cta_jobs[i] = h->mf_stage_jobs[2 * i + 1];
+  }
+  return MMPGO_OK;
+}
+
 int mmpgo_project_to_sodn(int32_t d, int64_t n, const double *A, double *U, int32_t device) {
   if ((d != 2 && d != 3) || n < 0 || !A || !U) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
   if (n == 0) return MMPGO_OK;
@@ -284,6 +324,33 @@ int mmpgo_project_to_sodn(int32_t d, int64_t n, const double *A, double *U, int3
   if (rc) mmpgo::set_error(std::string("project_to_SOdn: ") + cudaGetErrorString(cudaGetLastError()));
   cudaFree(dA); cudaFree(dU);
   return rc;
+}
+
+int mmpgo_mf_host_solve(int32_t n, const int32_t *ptr, const int32_t *col, const double *val, int32_t block,
+                        int32_t leaf, int32_t nrhs, const double *rhs, double *x, int64_t *stats) {
+  if (n <= 0 || !ptr || !col || !val || block < 1 || n % block || nrhs < 1 || nrhs > 8 || !rhs || !x) {
+    mmpgo::set_error("bad argument");
+    return MMPGO_ERR_ARG;
+  }
+  try {
+    mmpgo::MfMatrix A;
+    A.n = n; A.ptr = ptr; A.col = col; A.val = val;
+    mmpgo::MfFactor F;
+    if (mmpgo::mf_factor({A}, block, leaf, false, &F) != 0) {
+      mmpgo::set_error("matrix is not positive definite");
+      return MMPGO_ERR_ARG;
+    }
+    mmpgo::mf_host_solve(F, nrhs, rhs, x);
+    if (stats) {
+      stats[0] = F.nnz; stats[1] = F.height; stats[2] = (int64_t)F.sn.size(); stats[3] = (int64_t)F.flops;
+      stats[4] = (int64_t)(F.wjobs[0].size() + F.cjobs[0].size()); stats[5] = (int64_t)(F.wjobs[1].size() + F.cjobs[1].size());
+      stats[6] = F.max_R_big; stats[7] = F.urows;
+    }
+    return MMPGO_OK;
+  } catch (const std::exception &e) {
+    mmpgo::set_error(e.what());
+    return MMPGO_ERR_ARG;
+  }
 }
 
 }  // extern "C"

@@ -181,6 +181,7 @@ template <int D> struct Drv {
     std::memset(&a, 0, sizeof(a));
     a.rowptr = h->d_rowptr; a.col = h->d_col; a.blk = h->d_blk; a.blk0 = h->d_blk0;
     a.diag = diag ? diag : h->d_gdiag; a.partials = h->d_partials;
+    a.out_perm = h->use_direct ? h->d_mf_perm : nullptr;      // G_RHS_T feeds the sparse direct solve in its elimination order
     return a;
   }
 
@@ -206,6 +207,22 @@ template <int D> struct Drv {
       launch_dense_solve<D>(h->A, h->d_node_off, h->d_dense_off, h->d_active2, h->d_ginv, h->rhs_t, xio,
                             h->max_dense_n0, h->stream);
       h->ctr.launches++;
+    }
+    if (any(mp) && h->use_direct) {
+      // sparse Cholesky factor of G00 (host, at upload) applied by one persistent launch of the
+      // level-scheduled supernodal sweeps (mmpgo_mfsolve.cu): exact like the reference's L_.solve
+      MfSolveArgs ma;
+      ma.f = h->mf;
+      if (all(mp)) ma.active = nullptr;
+      else {
+        CK(cudaMemcpyAsync(h->d_active2, mp.data(), sizeof(int) * mp.size(), cudaMemcpyHostToDevice, h->stream));
+        ma.active = h->d_active2;
+      }
+      ma.rhs = h->rhs_t; ma.out = xio; ma.out_stride = PB; ma.sign = -1.0;
+      CK((cudaError_t)launch_mf_solve<D>(ma, h->mf_grid, h->stream));
+      h->ctr.launches++;
+      h->ctr.reserved[2]++;                                   // solves served by the sparse direct kernel
+      return 0;
     }
     if (any(mp)) {
       // one persistent launch: per-node Jacobi-PCG to `translation_solve_tol` (mmpgo_tsolve.cu)
@@ -1167,6 +1184,33 @@ template <int D> static int evaluate_grad_t(Handle *h, const double *X, int64_t 
 int driver_evaluate_grad(Handle *h, const double *X, int64_t ldx, double *G, int64_t ldg) {
   if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
   return h->d == 2 ? evaluate_grad_t<2>(h, X, ldx, G, ldg) : evaluate_grad_t<3>(h, X, ldx, G, ldg);
+}
+
+// t = -G00^{-1} rhs for every local node through the solve path of the handle (dense inverse, sparse
+// Cholesky sweeps or PCG): the core of recover_translations (DPGOProblem.h:275-294), on caller data.
+template <int D> static int translation_solve_t(Handle *h, const double *rhs, double *t) {
+  typedef Drv<D> Dr;
+  constexpr int PB = (D + 1) * D;
+  const Mask allm(h->A, 1);
+  std::vector<double> prhs;
+  if (h->use_direct) {       // the sparse direct solve takes its right-hand side in elimination order
+    prhs.resize((size_t)h->NO * D);
+    for (int p = 0; p < h->NO; ++p)
+      for (int c = 0; c < D; ++c) prhs[(size_t)h->h_mf_perm[p] * D + c] = rhs[(size_t)p * D + c];
+    rhs = prhs.data();
+  }
+  CK(cudaMemcpyAsync(h->rhs_t, rhs, sizeof(double) * (size_t)h->NO * D, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->xeval, 0, sizeof(double) * (size_t)h->NO * PB, h->stream));
+  RC(Dr::solve_t(h, h->xeval, allm, false));
+  CK(cudaMemcpy2DAsync(t, sizeof(double) * D, h->xeval, sizeof(double) * PB, sizeof(double) * D, (size_t)h->NO,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int driver_translation_solve(Handle *h, const double *rhs, double *t) {
+  if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
+  return h->d == 2 ? translation_solve_t<2>(h, rhs, t) : translation_solve_t<3>(h, rhs, t);
 }
 
 // Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA

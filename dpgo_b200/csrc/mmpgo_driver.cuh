@@ -8,6 +8,7 @@
 
 #include "../../include/mmpgo.h"
 #include "mmpgo_kernels.cuh"
+#include "mmpgo_mf.cuh"
 
 namespace mmpgo {
 
@@ -109,9 +110,17 @@ struct Handle {
   int ts_plan_grid = -1, ts_plan_chunk = -1, ts_plan_max = 0;
   std::vector<int> ts_plan_stage;
   int ts_lite_max_tiles = 16;    // use k_tsolve_lite when a CTA gets at most this many CTA tiles
-  // development knobs of the translation solve, read ONCE per handle (set_graph) from the environment:
-  // MMPGO_TS_KERNEL=ring|lite, MMPGO_TS_CHUNK, MMPGO_TS_LITE_MAX_TILES, MMPGO_TS_NORES, MMPGO_TS_HANDOFF
-  int ts_force_kernel = 0;       // 0 automatic, 1 copy-ring kernel, 2 small-shard kernel
+  // sparse direct translation solve (mmpgo_mf.cuh): factor of G00 of every node above dense_solve_max_n
+  bool use_direct = false;
+  MfDevice mf;
+  int *d_mf_perm = nullptr;            // original own pose -> row of the permuted right-hand side (identity for dense nodes)
+  std::vector<int> h_mf_perm;
+  std::vector<int> mf_stage_jobs;      // per stage (forward stages, then backward): warp jobs, CTA jobs
+  int mf_grid = 0;
+  int64_t mf_nnz = 0, mf_entries = 0, mf_tasks = 0;
+  int mf_height = 0, mf_supernodes = 0;
+  int64_t dense_poses = 0;
+  int ts_force_kernel = 0;       // PCG path: 0 automatic, 1 copy-ring kernel, 2 small-shard kernel (options.translation_solver)
   int ts_chunk = 8;              // consecutive CTA tiles dealt to one CTA at a time (ring kernel)
   bool ts_nores = false;         // small-shard kernel without shared-memory residency
   int ts_handoff = -1;           // nodes still iterating at which the ring kernel hands off (-1: max(2, nodes/16))
@@ -167,6 +176,7 @@ void plan_halo_pair(int world, const int64_t *send_poses, const int64_t *recv_po
 int driver_evaluate_f(Handle *h, const double *X, int64_t ldx, double *f);
 int driver_evaluate_grad(Handle *h, const double *X, int64_t ldx, double *G, int64_t ldg);
 int driver_current_objective(Handle *h, double *f, double *g2);
+int driver_translation_solve(Handle *h, const double *rhs, double *t);
 int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg);
 int driver_sync_counters(Handle *h);
 int driver_reset_solve_stats(Handle *h);

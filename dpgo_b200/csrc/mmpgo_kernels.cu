@@ -151,7 +151,7 @@ k_gpass(Tiles tl, GPassArgs a) {
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         const double gv = a.g ? a.g[(size_t)p * PB + c] : 0.0;
-        a.out[(size_t)p * D + c] = gv + acc[c];
+        a.out[(size_t)(a.out_perm ? a.out_perm[p] : p) * D + c] = gv + acc[c];
       }
     }
     return;
@@ -309,10 +309,11 @@ __global__ void __launch_bounds__(TILE) k_g01(Tiles tl, GPassArgs a) {
 #pragma unroll
     for (int c = 0; c < D; ++c) acc[c] = fma(dv, xp[(k - 1) * D + c], acc[c]);
   }
+  const size_t orow = a.out_perm ? (size_t)a.out_perm[p] : (size_t)p;
 #pragma unroll
   for (int c = 0; c < D; ++c) {
     const double gv = a.g ? a.g[(size_t)p * PB + c] : 0.0;
-    a.out[(size_t)p * D + c] = gv + acc[c];
+    a.out[orow * D + c] = gv + acc[c];
   }
 }
 

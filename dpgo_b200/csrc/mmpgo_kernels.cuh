@@ -51,6 +51,7 @@ struct GPassArgs {
   const double *xref;     // G_HV: the point Y (pose blocks); others unused
   const double *nab;      // G_HV: Euclidean gradient rows
   double *out;            // vector output (pose blocks or compact t rows for G_RHS_T)
+  const int *out_perm;    // G_RHS_T: row of pose p in `out` (sparse direct solve: its elimination order); null = p
   double *out2;           // G_REDGRAD: grad
   double *partials;       // [n_tiles][NS]
 };

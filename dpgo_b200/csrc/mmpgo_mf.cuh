@@ -1,0 +1,116 @@
+// Sparse direct solve of the per-node SPD systems (K2b, direct path): nested-dissection
+// multifrontal Cholesky on the host at graph upload, level-scheduled supernodal sweeps on the
+// device per solve.
+//
+// Replaces the reference's CHOLMOD factor `L_ = chol(G00)` (C++/DPGO/src/DPGOProblem.cpp:93) and
+// its `L_.solve` call sites: recover_translations (include/DPGO/DPGOProblem.h:275-294), retract
+// (DPGOProblem.cpp:127-143), the inner solve of the reduced Hessian-vector product (:552-577).
+// The same machinery factors G11 + lambda I for the reference's default preconditioner
+// (RegularizedCholesky, DPGOProblem.cpp:101-124, applied at :592).
+//
+// Data model.  The matrix of one robot node is ordered by nested dissection (separators from
+// breadth-first level structures); every node of the separator tree is one SUPERNODE s with k_s
+// columns (its vertices, contiguous in the new numbering) and a boundary of m_s rows in its
+// ancestors (R_s = k_s + m_s rows in all).  With the front's Cholesky panel [L11; L21] the device
+// keeps ONE dense block per supernode
+//        M_s = [ inv(L11) ; L21 inv(L11) ]        (R_s x k_s)
+// so that both sweeps are plain dense products without a triangular dependency inside a supernode:
+//   forward   [ y_s ; -du ] = M_s f1,  f1 = b_s + (children's update rows),  u_s = f2 - L21 y_s
+//   backward  x_s = M_s^T [ y_s ; -x_boundary ]
+// M_s is stored twice, column-major (forward: one row per thread, coalesced over rows) and
+// row-major (backward: one column per thread, coalesced over columns).  Supernodes of equal
+// height (forward) / depth (backward) are independent: one grid-wide barrier per level.
+// Every sum has a fixed order: results do not depend on scheduling or on which nodes share a GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace mmpgo {
+
+struct MfSn {             // one supernode, 48 bytes
+  int node;               // local robot node
+  int c0;                 // first column, handle-wide permuted numbering (node offset included)
+  int k, R;               // columns, rows
+  long long moff;         // M_s: column-major copy (leading dimension R) in M, row-major copy (leading dimension k) in MT
+  int rowoff;             // its R rows in pull0 / pull1
+  int boff;               // its m = R - k boundary rows in bidx
+  int uoff;               // first row of its update vector in the u buffer
+  int nchild;             // 0 for the leaves of the separator tree (no update rows to pull)
+  int pad[2];
+};
+static_assert(sizeof(MfSn) == 48, "MfSn must be 48 bytes");
+
+// forward: rows [r0, r0 + span) of supernode sn; backward: columns [r0, r0 + span).  Warp jobs (fronts of at
+// most MF_RW rows) have span 32, CTA jobs span MF_SPAN.
+struct MfJob { int sn, r0; };
+
+constexpr int MF_THREADS = 1024;   // one persistent CTA per SM
+constexpr int MF_WARPS = MF_THREADS / 32;
+constexpr int MF_RW = 128;         // supernodes with R <= MF_RW are served by single warps
+constexpr int MF_Q = 4;            // CTA jobs: every output row / column is summed in MF_Q contiguous slices by MF_Q threads
+constexpr int MF_SPAN = MF_THREADS / MF_Q;   // rows (forward) / columns (backward) of one CTA job
+
+// Host-side factor of all local nodes of a handle (or of one matrix in the host-only tests).
+struct MfFactor {
+  int nrows = 0;                       // total scalar rows (sum over nodes)
+  int block = 1;                       // scalar rows per graph vertex (1: G00, d: G11)
+  std::vector<MfSn> sn;
+  std::vector<double> M, MT;
+  std::vector<int> pull0, pull1;       // per supernode row: row of a child's update vector in u, or -1
+  std::vector<int> bidx;               // per boundary row: position in the permuted numbering
+  std::vector<int> iperm, perm;        // permuted position -> original row (handle-wide) and its inverse
+  // per sweep (0 forward, 1 backward): warp jobs and CTA jobs, with their ranges per stage
+  std::vector<MfJob> wjobs[2], cjobs[2];
+  std::vector<int> wstage[2], cstage[2];   // [stage[s], stage[s+1])
+  int urows = 0;                       // rows of the u buffer
+  int max_R_big = 0;                   // largest R among supernodes served by whole CTAs
+  int64_t nnz = 0;                     // sum k(k+1)/2 + k m  (entries of L)
+  double flops = 0.0;
+  int height = 0;
+};
+
+// One SPD matrix per node, CSR over scalar rows local to the node (full symmetric pattern incl.
+// the diagonal; duplicate entries are summed).  `block` consecutive rows form one graph vertex.
+struct MfMatrix {
+  int n = 0;
+  const int *ptr = nullptr, *col = nullptr;
+  const double *val = nullptr;
+  bool skip = false;      // rows are numbered but not factored (node served by another solve path)
+};
+
+// Symbolic pass only: fills nnz / flops / height estimates (no values).  Returns 0.
+// Full factorisation: returns 0, or -1 when a pivot is not positive (matrix not SPD).
+int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbolic_only, MfFactor *out);
+// Host restatement of the device sweeps (same blocks, same order of every sum): x = A^{-1} rhs,
+// rhs / x are [nrows][nrhs] in the ORIGINAL numbering.
+void mf_host_solve(const MfFactor &F, int nrhs, const double *rhs, double *x);
+
+// ---- device side ---------------------------------------------------------------------------
+struct MfDevice {
+  const MfSn *sn = nullptr;
+  const double *M = nullptr, *MT = nullptr;
+  const int *pull0 = nullptr, *pull1 = nullptr, *bidx = nullptr, *iperm = nullptr;
+  const MfJob *wjobs[2] = {nullptr, nullptr}, *cjobs[2] = {nullptr, nullptr};
+  const int *wstage[2] = {nullptr, nullptr}, *cstage[2] = {nullptr, nullptr};
+  int n_stage[2] = {0, 0};
+  double *y = nullptr, *xp = nullptr, *u = nullptr;     // [nrows][D] permuted, [urows][D]
+  unsigned *barrier = nullptr;                          // grid barrier counter (zeroed before launch)
+  unsigned long long *stage_ns = nullptr;               // [n_stage[0] + n_stage[1] + 1] globaltimer of CTA 0 at every stage boundary
+  int smem_bytes = 0;
+  int part_off = 0;                                     // doubles: slice sums of the CTA jobs behind the front buffer
+  int max_ctas = 0;                                     // CTAs the fullest stage can use (grid sizing)
+};
+struct MfSolveArgs {
+  MfDevice f;
+  const int *active;        // per-node mask or nullptr
+  const double *rhs;        // [rows][D] in the PERMUTED numbering (row perm[p] holds the entry of original row p)
+  double *out;              // out[row * out_stride + c] = sign * x
+  int out_stride;
+  double sign;
+};
+template <int D> int launch_mf_solve(const MfSolveArgs &a, int grid, cudaStream_t s);
+template <int D> int mf_solve_max_grid(int device, int smem_bytes);
+
+}  // namespace mmpgo

@@ -360,15 +360,8 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   h->n_ctiles = (int)ct_node.size();
   h->h_node_ctb = node_ctb; h->h_node_cte = node_cte;
   h->ts_plan_grid = -1;
-  {
-    const char *e;
-    h->ts_force_kernel = 0;
-    if ((e = getenv("MMPGO_TS_KERNEL"))) h->ts_force_kernel = !strcmp(e, "ring") ? 1 : !strcmp(e, "lite") ? 2 : 0;
-    if ((e = getenv("MMPGO_TS_CHUNK"))) h->ts_chunk = std::max(1, atoi(e));
-    if ((e = getenv("MMPGO_TS_LITE_MAX_TILES"))) h->ts_lite_max_tiles = atoi(e);
-    h->ts_nores = getenv("MMPGO_TS_NORES") != nullptr;
-    if ((e = getenv("MMPGO_TS_HANDOFF"))) h->ts_handoff = atoi(e);
-  }
+  h->ts_force_kernel = h->opt.translation_solver == MMPGO_TSOLVE_PCG_RING ? 1
+                       : h->opt.translation_solver == MMPGO_TSOLVE_PCG_LITE ? 2 : 0;
   const int n_sl = TS_WPT * h->n_ctiles;
   std::vector<int> sell_ptr((size_t)n_sl + 1, 0), slot_of(NO, 0);
   for (int c = 0; c < h->n_ctiles; ++c)
@@ -426,15 +419,109 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
       if (!dense_spd_inverse(n0, M)) { set_error("G00 is not positive definite"); return MMPGO_ERR_ARG; }
       dense_off[a] = (long long)ginv.size();
       ginv.insert(ginv.end(), M.begin(), M.end());
-      h->info[a].dense = true; h->dense_mask[a] = 1; h->any_dense = true;
+      h->info[a].dense = true; h->dense_mask[a] = 1; h->any_dense = true; h->dense_poses += n0;
       h->max_dense_n0 = std::max(h->max_dense_n0, n0);
     } else {
       h->pcg_mask[a] = 1; h->any_pcg = true;
     }
   }
 
-  // ---- upload
+  // ---- sparse Cholesky of G00 for the nodes above dense_solve_max_n (the reference factors every
+  // node's G00 with CHOLMOD, DPGOProblem.cpp:93): host factorisation now, device sweeps per solve
   int rc = 0;
+  if (h->any_pcg && (h->opt.translation_solver == MMPGO_TSOLVE_AUTO || h->opt.translation_solver == MMPGO_TSOLVE_DIRECT)) {
+    // scalar CSR of every node's G00 (local column indices, diagonal included)
+    std::vector<int> mptr((size_t)NO + A, 0), mcol;
+    std::vector<double> mval;
+    std::vector<MfMatrix> mats(A);
+    mcol.reserve((size_t)nnz + NO); mval.reserve((size_t)nnz + NO);
+    std::vector<size_t> ptr_off(A);
+    size_t po = 0;
+    for (int a = 0; a < A; ++a) {
+      const int off = h->node_off[a], n0 = h->info[a].n0;
+      ptr_off[a] = po;
+      for (int p = 0; p < n0; ++p) {
+        mptr[po + p] = (int)mcol.size();
+        if (!h->pcg_mask[a]) continue;
+        mcol.push_back(p); mval.push_back(d00[off + p]);
+        for (int s2 = rowptr[off + p]; s2 < rowptr[off + p + 1]; ++s2) { mcol.push_back(col[s2] - off); mval.push_back(a00[s2]); }
+      }
+      mptr[po + n0] = (int)mcol.size();
+      po += (size_t)n0 + 1;
+    }
+    for (int a = 0; a < A; ++a) {
+      // row pointers are absolute offsets into mcol / mval: rebase the column / value pointers per node
+      mats[a].n = h->info[a].n0; mats[a].ptr = &mptr[ptr_off[a]]; mats[a].col = mcol.data(); mats[a].val = mval.data();
+      mats[a].skip = !h->pcg_mask[a];
+    }
+    const int leaf = 16;
+    MfFactor F;
+    mf_factor(mats, 1, leaf, true, &F);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const double bytes = 16.0 * (double)F.nnz * 1.35;          // both copies; the stored blocks carry the zero triangle of inv(L11)
+    const bool fits = bytes <= 0.3 * (double)free_b && F.flops <= 1.5e12;
+    if (!fits && h->opt.translation_solver == MMPGO_TSOLVE_DIRECT) {
+      set_error("translation_solver = DIRECT: the sparse factor of G00 exceeds the memory / setup budget");
+      return MMPGO_ERR_UNSUPPORTED;
+    }
+    if (fits) {
+      if (mf_factor(mats, 1, leaf, false, &F) != 0) { set_error("G00 is not positive definite"); return MMPGO_ERR_ARG; }
+      // shared memory: per-warp front buffers of the warp jobs, or one front buffer + the slice sums of a CTA job
+      const int part_off = d * std::max(MF_WARPS * MF_RW, F.max_R_big);
+      const int smem = (int)sizeof(double) * (part_off + MF_Q * MF_SPAN * d);
+      if (smem <= 200 * 1024) {
+        MfDevice &m = h->mf;
+        MfSn *sn_d; double *M_d, *MT_d; int *p0, *p1, *bi, *ip;
+        if ((rc = upload(h, &sn_d, F.sn))) return rc;
+        if ((rc = upload(h, &M_d, F.M))) return rc;
+        if ((rc = upload(h, &MT_d, F.MT))) return rc;
+        if ((rc = upload(h, &p0, F.pull0))) return rc;
+        if ((rc = upload(h, &p1, F.pull1))) return rc;
+        if ((rc = upload(h, &bi, F.bidx))) return rc;
+        if ((rc = upload(h, &ip, F.iperm))) return rc;
+        if ((rc = upload(h, &h->d_mf_perm, F.perm))) return rc;
+        h->h_mf_perm = F.perm;
+        m.sn = sn_d; m.M = M_d; m.MT = MT_d; m.pull0 = p0; m.pull1 = p1; m.bidx = bi; m.iperm = ip;
+        for (int dir = 0; dir < 2; ++dir) {
+          MfJob *wj, *cj; int *ws, *cs;
+          if ((rc = upload(h, &wj, F.wjobs[dir]))) return rc;
+          if ((rc = upload(h, &cj, F.cjobs[dir]))) return rc;
+          if ((rc = upload(h, &ws, F.wstage[dir]))) return rc;
+          if ((rc = upload(h, &cs, F.cstage[dir]))) return rc;
+          m.wjobs[dir] = wj; m.cjobs[dir] = cj; m.wstage[dir] = ws; m.cstage[dir] = cs;
+          m.n_stage[dir] = (int)F.wstage[dir].size() - 1;
+          for (int st = 0; st < m.n_stage[dir]; ++st)
+            m.max_ctas = std::max(m.max_ctas, (F.wstage[dir][st + 1] - F.wstage[dir][st] + MF_WARPS - 1) / MF_WARPS +
+                                                  F.cstage[dir][st + 1] - F.cstage[dir][st]);
+          h->mf_tasks += (int64_t)(F.wjobs[dir].size() + F.cjobs[dir].size());
+        }
+        if ((rc = dalloc(h, &m.y, (size_t)NO * d))) return rc;
+        if ((rc = dalloc(h, &m.xp, (size_t)NO * d))) return rc;
+        if ((rc = dalloc(h, &m.u, (size_t)std::max(F.urows, 1) * d))) return rc;
+        if ((rc = dalloc(h, &m.barrier, (size_t)4))) return rc;
+        if ((rc = dalloc(h, &m.stage_ns, (size_t)(F.wstage[0].size() + F.wstage[1].size() + 2)))) return rc;
+        h->mf_stage_jobs.clear();
+        for (int dir = 0; dir < 2; ++dir)
+          for (size_t st = 0; st + 1 < F.wstage[dir].size(); ++st) {
+            h->mf_stage_jobs.push_back(F.wstage[dir][st + 1] - F.wstage[dir][st]);
+            h->mf_stage_jobs.push_back(F.cstage[dir][st + 1] - F.cstage[dir][st]);
+          }
+        m.smem_bytes = smem; m.part_off = part_off;
+        const int mg = d == 2 ? mf_solve_max_grid<2>(h->opt.device, smem) : mf_solve_max_grid<3>(h->opt.device, smem);
+        if (mg <= 0) { set_error("occupancy query for the sparse direct solve failed"); return MMPGO_ERR_CUDA; }
+        h->mf_grid = std::max(1, std::min(mg, m.max_ctas));
+        h->use_direct = true;
+        h->mf_nnz = F.nnz; h->mf_entries = 2 * (int64_t)F.M.size(); h->mf_height = F.height;
+        h->mf_supernodes = (int)F.sn.size();
+      } else if (h->opt.translation_solver == MMPGO_TSOLVE_DIRECT) {
+        set_error("translation_solver = DIRECT: a front of the sparse factor does not fit shared memory");
+        return MMPGO_ERR_UNSUPPORTED;
+      }
+    }
+  }
+
+  // ---- upload
   {
     std::vector<int64_t> pg(h->own_gid);
     pg.insert(pg.end(), h->halo_gid.begin(), h->halo_gid.end());

@@ -39,7 +39,7 @@ class Options(C.Structure):
         ("dense_solve_max_n", C.c_int32),
         ("translation_solve_tol", C.c_double),
         ("translation_solve_max_iters", C.c_int32), ("device", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("translation_solver", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -73,6 +73,7 @@ LOSS = {"trivial": 0, "none": 0, "huber": 1, "gm": 2, "geman-mcclure": 2, "welsc
 PRECON = {"None": 0, "Jacobi": 1, "BlockJacobi": 2}
 ALGORITHM = {"hash": 0, "star": 1}
 SCHEME = {"MM": 0, "AMM": 1}
+TSOLVER = {"auto": 0, "pcg": 1, "pcg_ring": 2, "pcg_lite": 3, "direct": 4}
 
 # every symbol include/mmpgo.h declares, with its signature
 _P = C.c_void_p
@@ -106,14 +107,18 @@ SIGNATURES = {
     "mmpgo_evaluate_f": (C.c_int, [_P, _dp, C.c_int64, _dp]),
     "mmpgo_evaluate_grad": (C.c_int, [_P, _dp, C.c_int64, _dp, C.c_int64]),
     "mmpgo_current_objective": (C.c_int, [_P, _dp, _dp]),
+    "mmpgo_translation_solve": (C.c_int, [_P, _dp, _dp]),
     "mmpgo_star_objective": (C.c_int, [_P, _dp, _dp, _ip]),
     "mmpgo_graph_sizes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "mmpgo_solver_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "mmpgo_solver_stage_times": (C.c_int, [_P, _dp, _ip, _ip, C.c_int32, _ip]),
     "mmpgo_profile_pass": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "mmpgo_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "mmpgo_reset_counters": (C.c_int, [_P]),
     "mmpgo_synchronize": (C.c_int, [_P]),
     "mmpgo_stream": (C.c_void_p, [_P]),
     "mmpgo_project_to_sodn": (C.c_int, [C.c_int32, C.c_int64, _dp, _dp, C.c_int32]),
+    "mmpgo_mf_host_solve": (C.c_int, [C.c_int32, _ip, _ip, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _lp]),
 }
 
 _lib = None

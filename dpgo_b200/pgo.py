@@ -36,6 +36,8 @@ class Options:
                 self.c.algorithm = L.ALGORITHM[v]
             elif k == "scheme":
                 self.c.scheme = L.SCHEME[v]
+            elif k == "translation_solver":
+                self.c.translation_solver = L.TSOLVER[v]
             elif k in ("eta", "max_soft_restart_hits"):
                 arr = getattr(self.c, k)
                 arr[0], arr[1] = v
@@ -159,6 +161,33 @@ class _Driver:
         keys = ("own_poses", "halo_poses", "bsr_entries", "inter_half_edges",
                 "owned_edges", "tiles", "local_nodes", "d")
         return dict(zip(keys, list(s)))
+
+    def translation_solve(self, rhs):
+        """t = -G00^{-1} rhs for every local node (the L_.solve of recover_translations,
+        DPGOProblem.h:291); rhs: (own poses, d)."""
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        t = np.zeros_like(rhs)
+        L.check(self.lib.mmpgo_translation_solve(self._h, L.dptr(rhs), L.dptr(t)))
+        return t
+
+    def solver_info(self):
+        s = (C.c_int64 * 8)()
+        L.check(self.lib.mmpgo_solver_info(self._h, s))
+        keys = ("solver", "factor_nnz", "factor_entries", "tree_height", "supernodes", "tasks_per_solve",
+                "persistent_ctas", "dense_poses")
+        out = dict(zip(keys, list(s)))
+        out["solver"] = {v: k for k, v in L.TSOLVER.items()}[out["solver"]] if out["solver"] else "dense"
+        return out
+
+    def solver_stage_times(self):
+        """[(microseconds, warp jobs, CTA jobs)] per stage of the last sparse direct solve."""
+        n = C.c_int32()
+        L.check(self.lib.mmpgo_solver_stage_times(self._h, None, None, None, 0, C.byref(n)))
+        if n.value == 0:
+            return []
+        us, wj, cj = np.zeros(n.value), np.zeros(n.value, dtype=np.int32), np.zeros(n.value, dtype=np.int32)
+        L.check(self.lib.mmpgo_solver_stage_times(self._h, L.dptr(us), L.iptr(wj), L.iptr(cj), n.value, C.byref(n)))
+        return list(zip(us.tolist(), wj.tolist(), cj.tolist()))
 
     KERNEL_KINDS = {"k2_eval": 0, "k2_grad": 1, "k1_inter": 2, "k3_prox": 3, "edge_objective": 4,
                     "k2_hv": 6, "k2_g01": 7, "g00_solve": 8}

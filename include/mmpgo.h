@@ -42,6 +42,14 @@ enum mmpgo_scheme { MMPGO_SCHEME_MM = 0, MMPGO_SCHEME_AMM = 1 };
  * block-Jacobi preconditioner of the device path. */
 enum mmpgo_preconditioner { MMPGO_PRECON_NONE = 0, MMPGO_PRECON_JACOBI = 1,
                             MMPGO_PRECON_BLOCK_JACOBI = 2 };
+/* How G00 u = rhs is solved for nodes with more than dense_solve_max_n poses (the reference
+ * keeps a CHOLMOD factor of G00, DPGOProblem.cpp:93).  DIRECT: sparse Cholesky (nested dissection,
+ * multifrontal, factored at mmpgo_set_graph) applied by level-scheduled supernodal sweeps -- exact
+ * like the reference's.  PCG: Jacobi-preconditioned CG to translation_solve_tol; _RING / _LITE pin
+ * one of its two kernels (tests).  AUTO: DIRECT unless the factor would exceed the memory / setup
+ * budget (thick 3-D nodes), then PCG. */
+enum mmpgo_translation_solver { MMPGO_TSOLVE_AUTO = 0, MMPGO_TSOLVE_PCG = 1, MMPGO_TSOLVE_PCG_RING = 2,
+                                MMPGO_TSOLVE_PCG_LITE = 3, MMPGO_TSOLVE_DIRECT = 4 };
 /* Which driver class the handle emulates. */
 enum mmpgo_algorithm { MMPGO_ALG_HASH = 0,   /* DPGOHash: AMM-PGO# / MM-PGO */
                        MMPGO_ALG_STAR = 1 }; /* DPGOStar: AMM-PGO*          */
@@ -74,7 +82,8 @@ typedef struct mmpgo_options {
   double translation_solve_tol;  /* relative residual of the G00 PCG, 1e-12 */
   int32_t translation_solve_max_iters;
   int32_t device;                /* CUDA device ordinal */
-  int32_t reserved[7];
+  int32_t translation_solver;    /* mmpgo_translation_solver; nodes above dense_solve_max_n */
+  int32_t reserved[6];
 } mmpgo_options;
 
 /* DPGOResult scalars a caller of results() reads (DPGO_types.h:204-322). */
@@ -95,7 +104,8 @@ typedef struct mmpgo_counters {
   int64_t solve_calls, solve_iters;   /* K2b G00 solves / PCG iterations */
   int64_t tcg_iterations, tnt_iterations;
   int64_t vector_passes;
-  int64_t reserved[7];            /* [0] pose-iterations of the G00 PCG, [1] solves served by the small-shard kernel */
+  int64_t reserved[7];            /* [0] pose-iterations of the G00 PCG, [1] solves served by the small-shard PCG kernel,
+                                     [2] solves served by the sparse direct kernel */
 } mmpgo_counters;
 
 const char *mmpgo_version(void);
@@ -150,6 +160,11 @@ int mmpgo_evaluate_f(mmpgo_handle h, const double *X, int64_t ldx, double *fobj)
  * (column-major ((d+1)N) x d, leading dimension ldg); only the rows of the poses owned by the
  * local nodes are written (all rows for a single handle).  Does not touch the solver state. */
 int mmpgo_evaluate_grad(mmpgo_handle h, const double *X, int64_t ldx, double *G, int64_t ldg);
+/* The linear solve inside DPGOProblem::recover_translations (DPGOProblem.h:275-294, L_.solve):
+ * t = -G00^{-1} rhs for every local node, through the handle's solve path (dense inverse, sparse
+ * Cholesky sweeps or PCG, see mmpgo_translation_solver).  rhs, t: [own poses][d] row-major, own poses
+ * of the local nodes in ascending global id.  Needs mmpgo_set_graph only; uses scratch. */
+int mmpgo_translation_solve(mmpgo_handle h, const double *rhs, double *t);
 /* Objective of the CURRENT device iterate, no host<->device pose traffic
  * (what dist_pgo logs each iteration, dist_pgo.cpp:523-530). */
 int mmpgo_current_objective(mmpgo_handle h, double *fobj, double *grad_sqnorm);
@@ -205,12 +220,32 @@ int mmpgo_star_objective(mmpgo_handle h, double *F, double *fobj, int32_t *resta
 /* sizes[8] = {own poses, halo poses, block-CSR entries, inter half-edges,
  * owned edges, tiles, local nodes, d} */
 int mmpgo_graph_sizes(mmpgo_handle h, int64_t *sizes);
+/* info[8] = {translation solver in use for the large nodes (mmpgo_translation_solver; 0 = every node
+ * is dense), nnz(L) of the sparse factor, stored factor entries (both copies), separator-tree height,
+ * supernodes, jobs per solve, persistent CTAs, poses solved by the dense inverse} */
+int mmpgo_solver_info(mmpgo_handle h, int64_t *info);
+/* Sparse direct solve, measurement: duration in microseconds of every stage of the LAST solve (forward
+ * stages by height, then backward stages by depth; device timer of CTA 0 at the grid barriers) with the
+ * warp jobs and CTA jobs of the stage.  *count receives the number of stages (0 without a sparse factor);
+ * us may be NULL to query it. */
+int mmpgo_solver_stage_times(mmpgo_handle h, double *us, int32_t *warp_jobs, int32_t *cta_jobs, int32_t capacity,
+                             int32_t *count);
 
 /* project_to_SO3n / project_to_SO2n (C++/DPGO/include/DPGO/DPGO_utils.h:515-565; kernels
  * C++/DPGO/src/internal/project_to_SOd.cpp:27-33,121-196): the polar projection of n row-major
  * d x d host blocks onto SO(d), on `device`; the operation the fused proximal kernel applies to
  * every pose.  Needs no handle. */
 int mmpgo_project_to_sodn(int32_t d, int64_t n, const double *A, double *U, int32_t device);
+
+/* Host-only (no CUDA): the sparse direct solver behind the translation solve (the reference's
+ * CHOLMOD factor L_ = chol(G00), DPGOProblem.cpp:93, and its L_.solve call sites) on one SPD
+ * matrix given as CSR (full symmetric pattern incl. the diagonal; `block` consecutive rows form
+ * one graph vertex): nested-dissection multifrontal Cholesky, then the host restatement of the
+ * device sweeps (same blocks, same order of every sum).  rhs, x: [n][nrhs] row-major.  stats[8]
+ * (may be NULL) = {nnz(L), tree height, supernodes, factor flops, forward jobs, backward jobs,
+ * largest CTA-served front, update rows}.  Used by the CPU tests of the factorisation. */
+int mmpgo_mf_host_solve(int32_t n, const int32_t *ptr, const int32_t *col, const double *val, int32_t block,
+                        int32_t leaf, int32_t nrhs, const double *rhs, double *x, int64_t *stats);
 
 /* Measurement hook: average device time (CUDA events on the handle's stream) of
  * `reps` back-to-back launches of one hot kernel on the current iterate.

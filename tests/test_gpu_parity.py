@@ -52,10 +52,13 @@ def test_no_refinement(grid):
     _check(parity.run_both(g, 4, X0, 8, max_iterations=0), 3)
 
 
-def test_pcg_translation_solve(grid):
-    # nodes too large for a dense G00^{-1} use the Jacobi-PCG solve
+@pytest.mark.parametrize("solver", ["direct", "pcg"])
+def test_sparse_translation_solve(grid, solver):
+    # nodes too large for a dense G00^{-1}: sparse Cholesky sweeps (default) or the Jacobi-PCG solve
     g, _, X0 = grid
-    _check(parity.run_both(g, 4, X0, 8, dense_solve_max_n=0), 3)
+    out = parity.run_both(g, 4, X0, 8, dense_solve_max_n=0, translation_solver=solver)
+    _check(out, 3)
+    assert out["drv"].solver_info()["solver"] == solver
 
 
 @pytest.mark.parametrize("loss", ["trivial", "gm"])
@@ -129,7 +132,10 @@ def test_golden_fixture(name):
         assert drv.iterate() == 0 and drv.communicate() == 0 and drv.update() == 0
         f.append(sum(drv.node_scalars(a).fobj for a in range(nn)))
     want = z["fobj_nodes"].sum(axis=1)
-    assert np.abs(np.array(f) - want).max() <= F_TOL * np.abs(want).max()
+    err = np.abs(np.array(f) - want) / np.abs(want)
+    # north_star: 1e-8 relative over the first 50 iterations; rounding differences then accumulate slowly
+    # (sphere2500 runs its full 1000 iterations: 1.2e-8 at the end)
+    assert err[:51].max() <= F_TOL and err.max() <= 1e-6, (err[:51].max(), err.max())
     X = drv.X()
     assert np.abs(X - z["X_final"]).max() < POSE_TOL
     if loss != "trivial":
@@ -191,7 +197,7 @@ def test_full_size_properties():
     (i) sum of per-node objectives equals the edge-parallel global objective,
     (ii) MM-PGO is monotone, (iii) rotations stay on SO(3)."""
     g, _, X0 = D.grid3d(40, 40, 25, seed=11)     # 40k poses, ~160k edges, PCG solve path
-    drv = D.DPGOHash(g, 8, D.Options(scheme="MM", dense_solve_max_n=0))
+    drv = D.DPGOHash(g, 8, D.Options(scheme="MM", dense_solve_max_n=0, translation_solver="pcg"))
     assert drv.initialize(X0) == 0 and drv.update() == 0
     prev = None
     for _ in range(5):
@@ -225,36 +231,34 @@ def test_projection_bitwise_vs_reference_avx2(d):
         assert np.array_equal(ref.project(A, nofma=True), want)
 
 
-TS_KERNELS = ["ring", "lite"]    # copy-ring kernel (large shards) / rendezvous-lean kernel (small shards)
+# sparse Cholesky sweeps (default) / PCG copy-ring kernel (large shards) / PCG rendezvous-lean kernel (small shards)
+TS_KERNELS = ["direct", "pcg_ring", "pcg_lite"]
 
 
 @pytest.mark.parametrize("kernel", TS_KERNELS)
 @pytest.mark.parametrize("alg,loss", [("hash", "trivial"), ("star", "huber")])
-def test_persistent_solve_multi_tile_nodes(alg, loss, kernel, monkeypatch):
+def test_persistent_solve_multi_tile_nodes(alg, loss, kernel):
     """Nodes spanning many CTA tiles and several chunks of the persistent translation solve
     (1600 poses per node, ragged last tile), masked sub-sets of nodes in the restart paths."""
-    monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
     g, _, X0 = D.grid3d(20, 20, 12, seed=8)
-    _check(parity.run_both(g, 3, X0, 6, loss=loss, algorithm=alg, dense_solve_max_n=0), 3)
+    _check(parity.run_both(g, 3, X0, 6, loss=loss, algorithm=alg, dense_solve_max_n=0, translation_solver=kernel), 3)
 
 
 @pytest.mark.parametrize("kernel", TS_KERNELS)
-def test_persistent_solve_se2(kernel, monkeypatch):
-    monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
+def test_persistent_solve_se2(kernel):
     g, _, X0 = D.city2d(40, 30, seed=6)
-    _check(parity.run_both(g, 5, X0, 6, loss="gm", dense_solve_max_n=0), 2)
+    _check(parity.run_both(g, 5, X0, 6, loss="gm", dense_solve_max_n=0, translation_solver=kernel), 2)
 
 
 @pytest.mark.parametrize("kernel", TS_KERNELS)
-def test_persistent_solve_many_small_nodes(kernel, monkeypatch):
+def test_persistent_solve_many_small_nodes(kernel):
     # more nodes than a CTA has segments to spare: 40 nodes of 45 poses, one tile each
-    monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
     g, _, X0 = D.grid3d(15, 12, 10, seed=12)
-    _check(parity.run_both(g, 40, X0, 5, dense_solve_max_n=0), 3)
+    _check(parity.run_both(g, 40, X0, 5, dense_solve_max_n=0, translation_solver=kernel), 3)
 
 
-def _run_star(g, X0, nodes, iters):
-    drv = D.DPGOStar(g, nodes, D.Options(loss="trivial", dense_solve_max_n=0))
+def _run_star(g, X0, nodes, iters, solver="pcg"):
+    drv = D.DPGOStar(g, nodes, D.Options(loss="trivial", dense_solve_max_n=0, translation_solver=solver))
     assert drv.initialize(X0) == 0 and drv.update() == 0
     for _ in range(iters):
         assert drv.iterate() == 0, D.load().mmpgo_last_error()
@@ -264,15 +268,14 @@ def _run_star(g, X0, nodes, iters):
 
 
 @pytest.mark.parametrize("dims,nodes", [((30, 30, 30), 5), ((24, 24, 16), 3)])
-def test_tsolve_lite_bitwise_equals_ring(dims, nodes, monkeypatch):
+def test_tsolve_lite_bitwise_equals_ring(dims, nodes):
     """The two translation-solve kernels share the data layout, the per-pose arithmetic and the
     fixed-order reductions: same iterates to the last bit, same iteration counts.  The first case
     gives every lite CTA two CTA tiles, some straddling a node boundary (two segments per CTA)."""
     g, _, X0 = D.grid3d(*dims, seed=21)
     out = {}
-    for kernel in TS_KERNELS:
-        monkeypatch.setenv("MMPGO_TS_KERNEL", kernel)
-        out[kernel] = _run_star(g, X0, nodes, 3)
+    for kernel in ("ring", "lite"):
+        out[kernel] = _run_star(g, X0, nodes, 3, "pcg_" + kernel)
     assert out["ring"][2] == out["lite"][2] and out["ring"][2] > 0
     assert out["ring"][1] == out["lite"][1]
     assert np.array_equal(out["ring"][0], out["lite"][0]), np.abs(out["ring"][0] - out["lite"][0]).max()
@@ -340,8 +343,9 @@ def test_config3_node_size_slab():
     4 robot nodes of 15 625 poses each (the 1 M-pose workload has 64 of them), AMM-PGO*, trivial loss,
     sparse translation solve (no dense G00 inverse at this size), against the oracle."""
     g, _, X0 = D.grid3d(100, 125, 5)
-    out = parity.run_both(g, 4, X0, 4, loss="trivial", algorithm="star", dense_solve_max_n=0)
+    out = parity.run_both(g, 4, X0, 4, loss="trivial", algorithm="star")
     _check(out, 3)
+    assert out["drv"].solver_info()["solver"] == "direct"
     assert [out["drv"].node_scalars(a).n0 for a in range(4)] == [15625] * 4
 
 
@@ -401,3 +405,71 @@ def test_communicate_may_be_repeated_or_skipped(grid):
     assert drv.initialize(X0) == 0 and drv.update() == 0 and drv.iterate() == 0
     assert np.abs(drv.X() - X0).max() > 1e-3
     assert drv.iterate() == -3                                # MMPGO_ERR_STATE: update() first
+
+
+def _g00(g, nodes, xi=1e-11):
+    """G00 of every node (DPGO_utils.cpp:2212-2243), block diagonal over nodes, scipy CSR."""
+    import scipy.sparse as sp
+    N = g.num_poses
+    node = np.minimum(np.arange(N) // (N // nodes), nodes - 1) if N % nodes == 0 else None
+    assert node is not None
+    ii, jj = g.i.astype(np.int64), g.j.astype(np.int64)
+    intra = node[ii] == node[jj]
+    A = sp.coo_matrix((np.concatenate([-g.tau[intra]] * 2), (np.concatenate([ii[intra], jj[intra]]),
+                                                             np.concatenate([jj[intra], ii[intra]]))), shape=(N, N)).tocsr()
+    diag = np.full(N, xi)
+    np.add.at(diag, ii[intra], g.tau[intra])
+    np.add.at(diag, jj[intra], g.tau[intra])
+    np.add.at(diag, ii[~intra], 2 * g.tau[~intra])
+    np.add.at(diag, jj[~intra], 2 * g.tau[~intra])
+    return (A + sp.diags(diag)).tocsr()
+
+
+@pytest.mark.parametrize("solver,tol", [("direct", 1e-12), ("pcg", 1e-10)])
+@pytest.mark.parametrize("case", ["grid", "slab", "rings", "se2"])
+def test_translation_solve_against_scipy(solver, tol, case):
+    """The linear solve of recover_translations (L_.solve, DPGOProblem.h:291) on random right-hand sides,
+    every solve path against scipy's sparse LU: grid nodes of a few CTA tiles, the 15 625-pose slabs of the
+    benchmark (fronts served by whole CTAs), ring-shaped robots (separators of two poses), SE(2)."""
+    import scipy.sparse.linalg as spla
+    if case == "grid":
+        (g, _, _), nodes = D.grid3d(20, 20, 12, seed=8), 3
+    elif case == "slab":
+        (g, _, _), nodes = D.grid3d(100, 125, 5), 4
+    elif case == "rings":
+        (g, _, _), nodes = D.sphere_rings(6, 3000, seed=3), 6
+    else:
+        (g, _, _), nodes = D.city2d(60, 50, seed=6), 5
+    drv = D.DPGOHash(g, nodes, D.Options(dense_solve_max_n=0, translation_solver=solver))
+    assert drv.solver_info()["solver"] == solver
+    A = _g00(g, nodes)
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal((g.num_poses, g.d)) * 100.0
+    t = drv.translation_solve(b)
+    want = -spla.splu(A.tocsc()).solve(b)
+    assert np.abs(t - want).max() <= tol * np.abs(want).max()
+    # deterministic: a second solve returns the same bits
+    assert np.array_equal(t, drv.translation_solve(b))
+
+
+def test_direct_solve_bitwise_equals_host_restatement():
+    """The device sweeps accumulate in the order of mf_host_solve (mmpgo_factor.cu) with fused multiply-adds:
+    same bits as the host restatement of the same factor."""
+    import ctypes as C
+    import scipy.sparse as sp
+    from dpgo_b200 import lib as L
+    g, _, _ = D.grid3d(24, 24, 16, seed=21)
+    nodes = 1
+    drv = D.DPGOHash(g, nodes, D.Options(dense_solve_max_n=0, translation_solver="direct", regularizer=1e-3))
+    A = sp.csr_matrix(_g00(g, nodes, xi=1e-3))
+    A.sort_indices()
+    # the ordering depends on the graph only and every (row, column) pair occurs once in this grid, so the
+    # library's factor of G00 and the one built here from scipy's CSR hold the same numbers
+    rng = np.random.default_rng(6)
+    b = rng.standard_normal((g.num_poses, 3))
+    x = np.zeros_like(b)
+    ptr, col = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    L.check(L.load().mmpgo_mf_host_solve(A.shape[0], L.iptr(ptr), L.iptr(col), L.dptr(np.ascontiguousarray(A.data)), 1, 16, 3,
+                                         L.dptr(b), L.dptr(x), None))
+    t = drv.translation_solve(b)
+    assert np.array_equal(t, -x), np.abs(t + x).max()
