@@ -160,68 +160,134 @@ def ncu_traffic(kernel_key):
 
 
 # ---------------------------------------------------------------------------
-def cpu_baseline_run(args, steps, warmup, sample_grid=(100, 125, 5), sample_nodes=4, workers=1):
-    """The restated CPU reference (oracle, numpy/scipy, 1 thread) on a bounded sample of the
-    same workload: same per-node size (15625 poses per robot node, slab-shaped), same loss
-    and algorithm; setup (matrix assembly, factorisations) excluded as in dist_pgo."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def make_graph(args, dims=None):
     import dpgo_b200 as D
+    if args.workload == "sphere":
+        return D.sphere_rings(args.nodes, args.poses_per_robot)
+    nx, ny, nz = dims or tuple(int(v) for v in args.grid.split(","))
+    return D.grid3d(nx, ny, nz)
+
+
+def cpu_reference_driver(args, g, nodes, workers, threads):
+    """The restated CPU reference on graph g: the C++/OpenMP restatement (oracle/cpu_dpgo.cpp, built into
+    oracle/_ref/libcpu_dpgo.so together with the reference's own AVX2 projection kernels) when the prebuilt
+    library travelled with the repo, else None."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import cpu_ref
+    from oracle import dpgo as odpgo
+    from parity import to_measurements
+    if not cpu_ref.available():
+        return None
+    opts = odpgo.Options(loss=args.loss, preconditioner="BlockJacobi")
+    return cpu_ref.CpuDPGO(to_measurements(g), g.num_poses, nodes, opts, args.algorithm, workers=workers,
+                           threads=threads, mode=0)
+
+
+def cpu_time_steps(drv, X0, steps, warmup, budget_s=None):
+    """initialize + update, `warmup` untimed and up to `steps` timed iterations (iterate, communicate, update:
+    what dist_pgo times, C++/examples/dist_pgo.cpp:496-521, plus communicate).  Stops early when the budget
+    is spent; returns (seconds, timed steps actually run, per-step seconds)."""
+    drv.initialize(X0)
+    drv.update()
+    per = []
+    t_begin = time.perf_counter()
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        drv.iterate()
+        drv.communicate()
+        drv.update()
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            per.append(dt)
+        if budget_s is not None and k + 1 >= warmup + 1 and time.perf_counter() - t_begin + dt > budget_s:
+            break
+    return float(sum(per)), len(per), per
+
+
+def cpu_baseline_sample(args, sample_grid=(100, 125, 5), sample_nodes=4, iters=5):
+    """`cpu_baseline` object of the CUDA arm: the restated CPU reference on a BOUNDED sample of the same
+    workload (a slab of the same grid generator with the per-node size of the full workload), all host
+    threads, nodes looped serially with OpenMP inside the operators like the reference; setup excluded
+    as in dist_pgo.  Runs in the process that holds the CUDA context, so nothing is forked."""
+    g, _, X0 = make_graph(args, sample_grid)
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    drv = cpu_reference_driver(args, g, sample_nodes, workers=1, threads=threads)
+    if drv is None:
+        return numpy_oracle_sample(args, sample_grid, sample_nodes, 2)
+    setup = time.perf_counter() - t0
+    secs, n, _ = cpu_time_steps(drv, X0, iters, 1, budget_s=60.0)
+    drv.close()
+    return {"value": g.num_edges * n / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "C++/OpenMP restatement (oracle/cpu_dpgo.cpp + the reference's AVX2 projections) on a %dx%dx%d "
+                      "SE(3) grid slab: %d poses / %d edges, %d robot nodes of %d poses (the per-node size of the full "
+                      "workload), %d timed iterations after 1 warm-up, %.2f s in iterate+communicate+update (setup "
+                      "%.1f s excluded), %d OpenMP threads, nodes looped serially" % (
+                          sample_grid + (g.num_poses, g.num_edges, sample_nodes, g.num_poses // sample_nodes, n, secs,
+                                         setup, threads))}
+
+
+def numpy_oracle_sample(args, sample_grid, sample_nodes, iters):
+    """Fallback when oracle/_ref/libcpu_dpgo.so is absent: the numpy/scipy oracle, one thread."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import dist_pgo as odist
     from oracle import dpgo as odpgo
     from parity import to_measurements
-    g, _, X0 = D.grid3d(*sample_grid)
-    opts = odpgo.Options(loss=args.loss, preconditioner="BlockJacobi")
-    meas = to_measurements(g)
+    g, _, X0 = make_graph(args, sample_grid)
     timing = {}
-    iters = max(1, steps)
-    t0 = time.perf_counter()
-    workers = max(1, min(workers, sample_nodes)) if args.algorithm == "star" else 1
-    try:
-        odist.run(meas, g.num_poses, sample_nodes, opts, X0, iters, args.algorithm, log_global=False,
-                  timing=timing, workers=workers)
-    except Exception as e:                     # the multi-process runner must never cost the run: serial fallback
-        if workers == 1:
-            raise
-        print("parallel oracle failed (%r), serial fallback" % (e,), file=sys.stderr)
-        workers, timing = 1, {}
-        t0 = time.perf_counter()
-        odist.run(meas, g.num_poses, sample_nodes, opts, X0, iters, args.algorithm, log_global=False, timing=timing)
-    wall = time.perf_counter() - t0
-    secs = timing["seconds"]
-    how = ("" if workers == 1 else "; per-node work in %d forked worker processes, global objective and restart "
-           "decisions on the master (oracle/parallel.py)" % workers)
-    return {
-        "value": g.num_edges * iters / secs, "unit": UNIT, "cores": workers, "kind": "port",
-        "sample": "%dx%dx%d SE(3) grid slab (%d poses / %d edges, %d robot nodes of %d poses = the "
-                  "per-node size of the full workload), %d iterations, %.1f s in iterate+update+"
-                  "communicate (setup %.1f s excluded)%s" % (
-                      sample_grid + (g.num_poses, g.num_edges, sample_nodes, g.num_poses // sample_nodes,
-                                     iters, secs, wall - secs, how)),
-    }, secs, iters
+    odist.run(to_measurements(g), g.num_poses, sample_nodes, odpgo.Options(loss=args.loss, preconditioner="BlockJacobi"),
+              X0, iters, args.algorithm, log_global=False, timing=timing)
+    return {"value": g.num_edges * iters / timing["seconds"], "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "numpy/scipy oracle (libcpu_dpgo.so not built) on a %dx%dx%d slab, %d robot nodes, %d iterations"
+                      % (sample_grid + (sample_nodes, iters))}
 
 
 def run_reference(args):
+    """Reference arm: the restated CPU reference on the FULL workload of the CUDA arm (same generator, seed,
+    node count, loss, algorithm, initial iterate), all host threads, `--warmup` untimed and `--steps` timed
+    iterations (fewer only if a 4-minute budget runs out; the line carries the count actually timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nx, ny, nz = (int(v) for v in args.grid.split(","))
-    N, E = nx * ny * nz, 4 * nx * ny * nz
-    steps = max(1, min(args.steps, 3))
-    # all the host threads the restated reference can use: one worker process per robot node of the sample
-    # (this arm runs in a process without CUDA or torch threads, so forking is safe here; the in-process
-    # cpu_baseline of the CUDA arm stays single-threaded)
-    cb, secs, iters = cpu_baseline_run(args, steps, 0, workers=min(4, os.cpu_count() or 1))
+    g, _, X0 = make_graph(args)
+    N, E = g.num_poses, g.num_edges
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    drv = cpu_reference_driver(args, g, args.nodes, workers=min(threads, 16), threads=threads)
+    if drv is None:
+        cb = numpy_oracle_sample(args, (100, 125, 5), 4, 2)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 2,
+                "warmup": 0, "ms_per_step": 1e3 * 250000 / cb["value"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args, N, E), "note": "bounded sample only: " + cb["sample"]},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+    setup = time.perf_counter() - t0
+    secs, n, per = cpu_time_steps(drv, X0, args.steps, args.warmup, budget_s=240.0)
+    value = E * n / secs
+    fobj = float(drv.node_scalars()[:, 0].sum())
+    cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+          "sample": "the full workload: %d timed iterations after %d warm-up, %.1f s in iterate+communicate+update "
+                    "(setup %.1f s excluded: matrix assembly by oracle/data_matrix.py, sparse Cholesky of G00), %d OpenMP "
+                    "threads inside the operators, robot nodes looped serially (C++/examples/dist_pgo.cpp:497-520)"
+                    % (n, args.warmup, secs, setup, threads)}
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / iters,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": workload_name(args, N, E),
-                                        "note": "upstream dist_pgo cannot be built here (no Eigen/SuiteSparse/"
-                                                "glog/Boost); this arm times the restated CPU reference "
-                                                "(oracle/, numpy+scipy) on a bounded sample, %d timed "
-                                                "iterations" % iters},
+        "impl": "reference", "metric": METRIC if args.workload == "grid" else "AMM-PGO%s edge-updates/s on a multi-robot SE(3) sphere" % (
+            "*" if args.algorithm == "star" else "#"),
+        "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": n, "warmup": args.warmup, "ms_per_step": 1e3 * secs / n, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, N, E), "preconditioner": "BlockJacobi",
+                   "final_2F": 2 * fobj, "step_seconds": per,
+                   "note": "upstream dist_pgo cannot be built here (no Eigen / SuiteSparse / glog / Boost); this arm times the "
+                           "restated reference algorithm in C++17 + OpenMP (oracle/cpu_dpgo.cpp: the reference's scalar CSR "
+                           "operators, an up-looking sparse Cholesky in place of CHOLMOD, the reference's own AVX2 SO(3) "
+                           "projection compiled from its sources) on the same graph, partition, initial iterate and options "
+                           "as the CUDA arm; `steps` is the number of iterations actually timed"},
         "cpu_baseline": cb,
-        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -245,11 +311,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    if args.workload == "sphere":
-        g, _, X0 = D.sphere_rings(args.nodes, args.poses_per_robot)
-    else:
-        nx, ny, nz = (int(v) for v in args.grid.split(","))
-        g, _, X0 = D.grid3d(nx, ny, nz)
+    g, _, X0 = make_graph(args)
     N, E, d = g.num_poses, g.num_edges, g.d
     opts = D.Options(loss=args.loss, device=local_rank)
     drv = multi.make_driver(g, args.nodes, opts, args.algorithm, rank, world)
@@ -266,9 +328,16 @@ def run_ours(args):
 
     assert drv.initialize(X0) == 0
     D.lib.check(drv.update())
-    for _ in range(args.warmup):
-        step()
     stream = torch.cuda.ExternalStream(drv.stream())
+    # per-iteration trace from iteration 0: an event behind every step (no synchronisation of its own) and the
+    # rank-local objective (host scalars of update(), no device traffic)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.warmup + args.steps + 1)]
+    f_trace = [drv.objective()[0]]
+    ev[0].record(stream)
+    for k in range(args.warmup):
+        step()
+        ev[k + 1].record(stream)
+        f_trace.append(drv.objective()[0])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     drv.reset_counters()
     barrier()
@@ -281,12 +350,25 @@ def run_ours(args):
     gc.disable()                     # no collector pause inside the timed region
     with ClockSampler(local_rank, dev_uuid) as clk:
         e0.record(stream)
-        for _ in range(args.steps):
+        for k in range(args.steps):
             step()
+            ev[args.warmup + k + 1].record(stream)
+            f_trace.append(drv.objective()[0])
         e1.record(stream)
         barrier()
     gc.enable()
     ms = e0.elapsed_time(e1)
+    # (the first timed interval starts at the barrier, not at the previous step's event)
+    iter_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.warmup)] + \
+              [e0.elapsed_time(ev[args.warmup + 1])] + \
+              [ev[k].elapsed_time(ev[k + 1]) for k in range(args.warmup + 1, args.warmup + args.steps)]
+    f_trace = np.array(f_trace)
+    if world > 1:
+        t = torch.tensor(f_trace, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        f_trace = t.cpu().numpy()
+    import hashlib
+    trace_digest = hashlib.sha256(" ".join("%.11e" % (2 * v) for v in f_trace).encode()).hexdigest()[:16]
     ctr = drv.counters()
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -377,33 +459,7 @@ def run_ours(args):
     }
 
     # ---- e2e: reference-facing call sequence with host matrices inside the timed region
-    e2e = None
-    if world == 1:
-        # host buffers of the caller: pinned, in the reference's layout (column-major ((d+1)N) x d)
-        pin_in = torch.empty((d, (d + 1) * N), dtype=torch.float64).pin_memory()
-        pin_out = torch.empty((d, (d + 1) * N), dtype=torch.float64).pin_memory()
-        Xh, Xo = pin_in.numpy().T, pin_out.numpy().T
-        Xh[:] = X0
-        torch.cuda.synchronize()
-        assert drv.initialize(Xh) == 0 and drv.update() == 0      # warm the path once
-        drv.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            assert drv.initialize(Xh) == 0                        # H2D of the step's input
-            D.lib.check(drv.update())
-            D.lib.check(drv.iterate())
-            D.lib.check(drv.communicate())
-            drv.X(out=Xo)                                         # D2H of the step's result
-            Xh, Xo = Xo, Xh                                       # the result is the next step's input
-        drv.synchronize()
-        dt = time.perf_counter() - t0
-        nbytes = (d + 1) * N * d * 8
-        e2e = {"value": E * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": nbytes, "steps": args.e2e_steps,
-               "call_sequence": "initialize(X_host); update(); iterate(); communicate(); X(out=X_host)",
-               "host_buffers": "pinned"}
-    else:
-        e2e = multi.e2e_multi(drv, X0, args.e2e_steps, E, d, N)
+    e2e = multi.e2e_loop(drv, X0, args.e2e_steps, E, d, N)
 
     # ---- time-to-cost: the reference cost is this implementation's own cost after
     # ITERS iterations; the CPU oracle cannot run 1000 iterations of 4M edges within a bench run
@@ -430,7 +486,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "grid":
-        cpu, _, _ = cpu_baseline_run(args, 2, 0)
+        cpu = cpu_baseline_sample(args)
 
     if rank == 0:
         line = {
@@ -444,7 +500,13 @@ def run_ours(args):
                            (sizes["bsr_entries"] * 132 + HE * 128) / 1e6),
                        "preconditioner": "BlockJacobi", "nodes_per_gpu": args.nodes // world,
                        "translation_solver": sinfo,
-                       "final_2F": 2 * F, "final_2gradnorm": 2 * gn},
+                       "final_2F": 2 * F, "final_2gradnorm": 2 * gn,
+                       "objective_trace": {"digest": trace_digest, "first_2F": 2 * float(f_trace[0]), "last_2F": 2 * float(f_trace[-1]),
+                                           "note": "sha256 over the 2F values of every iteration from 0 (warm-up included), 12 "
+                                                   "significant digits: equal digests at 1/2/4/8 GPUs = the same trajectory"},
+                       "iter_ms": [round(v, 4) for v in iter_ms],
+                       "init": "seeded perturbation of the ground truth (sigma_t 0.2, sigma_R 0.1 rad), iteration 0 is the first "
+                               "entry of iter_ms; the reference's dist_pgo starts from a chordal initialisation"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_cost": ttc,
             "gpu_launches": int(ctr.launches), "clocks": clk.summary(),
             "counters_per_step": {"launches": ctr.launches / args.steps, "k2_passes": per_step["k2"],

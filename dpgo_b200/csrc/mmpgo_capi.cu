@@ -303,6 +303,13 @@ int mmpgo_solver_stage_times(mmpgo_handle hh, double *us, int32_t *warp_jobs, in
   return MMPGO_OK;
 }
 
+int mmpgo_stage_range(mmpgo_handle hh, int64_t *lo, int64_t *hi) {
+  H_OR_FAIL(hh);
+  if (!lo || !hi || !h->graph_set) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
+  *lo = h->stage_lo; *hi = h->stage_hi;
+  return MMPGO_OK;
+}
+
 int mmpgo_project_to_sodn(int32_t d, int64_t n, const double *A, double *U, int32_t device) {
   if ((d != 2 && d != 3) || n < 0 || !A || !U) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
   if (n == 0) return MMPGO_OK;

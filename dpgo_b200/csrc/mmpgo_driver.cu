@@ -1044,9 +1044,13 @@ static int stage_alloc(Handle *h) {
 }
 static int stage_upload(Handle *h, const double *X, int64_t ldx) {
   RC(stage_alloc(h));
-  const size_t rows = (size_t)(h->d + 1) * h->N;
-  CK(cudaMemcpy2DAsync(h->d_xstage, rows * sizeof(double), X, (size_t)ldx * sizeof(double), rows * sizeof(double),
-                       h->d, cudaMemcpyHostToDevice, h->stream));
+  // only the rows the handle reads travel: translation rows [lo, hi) and rotation rows [N + d lo, N + d hi)
+  const size_t ld = (size_t)(h->d + 1) * h->N;
+  const size_t lo = (size_t)h->stage_lo, n = (size_t)(h->stage_hi - h->stage_lo), d = (size_t)h->d;
+  CK(cudaMemcpy2DAsync(h->d_xstage + lo, ld * sizeof(double), X + lo, (size_t)ldx * sizeof(double), n * sizeof(double),
+                       d, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(h->d_xstage + h->N + d * lo, ld * sizeof(double), X + h->N + d * lo, (size_t)ldx * sizeof(double),
+                       d * n * sizeof(double), d, cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
 static void pack_dev(Handle *h, double *d0, double *d1, double *d2, double *d3, double *d4) {

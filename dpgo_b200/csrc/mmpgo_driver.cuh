@@ -57,6 +57,7 @@ struct Handle {
   std::vector<int64_t> halo_gid;      // [NH] global id of halo pose
   std::vector<int> halo_owner;        // [NH] owning node
   int NO = 0, NH = 0, NP = 0;
+  int64_t stage_lo = 0, stage_hi = 0;  // id range covering own + halo poses: the rows of a host iterate that travel
   std::vector<NodeInfo> info;
   std::vector<NodeState> st;
   int64_t n_intra_entries = 0, n_inter_he = 0, n_edges_owned = 0;

@@ -228,6 +228,9 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     dev_index[halo[k]] = NO + k;
   }
 
+  h->stage_lo = h->own_gid.front(); h->stage_hi = h->own_gid.back() + 1;
+  if (h->NH > 0) { h->stage_lo = std::min(h->stage_lo, halo.front()); h->stage_hi = std::max(h->stage_hi, halo.back() + 1); }
+
   // ---- count rows
   std::vector<int> rowcnt(NO, 0), xrowcnt(NO, 0);
   int64_t n_owned = 0;

@@ -111,6 +111,7 @@ SIGNATURES = {
     "mmpgo_star_objective": (C.c_int, [_P, _dp, _dp, _ip]),
     "mmpgo_graph_sizes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "mmpgo_solver_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "mmpgo_stage_range": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mmpgo_solver_stage_times": (C.c_int, [_P, _dp, _ip, _ip, C.c_int32, _ip]),
     "mmpgo_profile_pass": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "mmpgo_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),

@@ -161,6 +161,9 @@ class ShardedDriver:
     def solve_kernels_per_iter(self):
         return 3.0
 
+    def stage_range(self):
+        return self.drv.stage_range()
+
     def halo_counts(self):
         sc = np.zeros(self.world, dtype=np.int64)
         rc = np.zeros(self.world, dtype=np.int64)
@@ -173,33 +176,57 @@ def make_driver(graph, num_nodes, options, algorithm="star", rank=0, world=1):
     return ShardedDriver(graph, num_nodes, options or Options(), algorithm, rank, world)
 
 
-def e2e_multi(drv, X0, steps, E, d, N):
-    """End-to-end arm at N > 1: every step uploads the full host iterate from pinned memory
-    (initialize), runs update/iterate/communicate and downloads this rank's rows."""
+def e2e_loop(drv, X0, steps, E, d, N):
+    """End-to-end arm: the loop of dist_pgo with HOST matrices (C++/examples/dist_pgo.cpp:497-530), steady state.
+    Per iteration: iterate(); results().Xk of the local nodes into the caller's pinned global X (device -> host,
+    :502-511); communicate(); update(); evaluate_f(X_host), the logging call dist_pgo makes on the host iterate
+    (:523-524; host -> device: the rows of the local nodes and of their remote neighbours).  The solver state is
+    not reset between steps.  At N > 1 every rank holds its own host matrix: its rows are current, the rows of
+    remote neighbours are those of the start (the value of the logging call is not used, its traffic is)."""
     import time
-    torch, dist = drv.torch, drv.dist
-    pin_in = torch.empty((d, (d + 1) * N), dtype=torch.float64).pin_memory()
-    pin_out = torch.empty((d, (d + 1) * N), dtype=torch.float64).pin_memory()
-    Xh, Xo = pin_in.numpy().T, pin_out.numpy().T
+    torch = drv.torch
+    dist = drv.dist if drv.world > 1 else None
+    pin = torch.empty((d, (d + 1) * N), dtype=torch.float64).pin_memory()
+    Xh = pin.numpy().T
     Xh[:] = X0
-    Xo[:] = X0
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
     assert drv.initialize(Xh) == 0 and drv.update() == 0
-    dist.barrier(); torch.cuda.synchronize()
+    for _ in range(3):                                   # reach the steady state of the Nesterov sequence
+        L.check(drv.iterate()); L.check(drv.communicate()); L.check(drv.update())
+    drv.X(out=Xh)
+    if dist is not None:                                 # every rank starts from the assembled iterate
+        t = torch.from_numpy(np.ascontiguousarray(Xh)).cuda()
+        t[:] = 0
+        own = drv.X()
+        t += torch.from_numpy(np.ascontiguousarray(own)).cuda()
+        dist.all_reduce(t)
+        Xh[:] = t.cpu().numpy()
+    drv.evaluate_f(Xh)
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
-        assert drv.initialize(Xh) == 0
-        L.check(drv.update())
         L.check(drv.iterate())
+        drv.X(out=Xh)
         L.check(drv.communicate())
-        drv.X(out=Xo)
+        L.check(drv.update())
+        drv.evaluate_f(Xh)
     drv.synchronize()
-    dist.barrier(); torch.cuda.synchronize()
+    sync()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    nbytes = (d + 1) * N * d * 8
-    return {"value": E * steps / float(t.item()), "unit": "edge-updates/s",
-            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes // drv.world, "steps": steps,
-            "call_sequence": "initialize(X_host); update(); iterate(); communicate(); X(out=X_host)",
-            "host_buffers": "pinned",
-            "note": "each step restarts from the same host iterate on every rank"}
+    lo, hi = drv.stage_range()
+    up = np.array([float((hi - lo) * (d + 1) * d * 8), float(drv.sizes()["own_poses"] * (d + 1) * d * 8), dt])
+    if dist is not None:
+        t = torch.tensor(up, dtype=torch.float64, device="cuda")
+        tm = t.clone()
+        dist.all_reduce(t)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        up = np.array([float(t[0]), float(t[1]), float(tm[2])])
+    return {"value": E * steps / up[2], "unit": "edge-updates/s", "h2d_bytes_per_step": int(up[0]),
+            "d2h_bytes_per_step": int(up[1]), "steps": steps,
+            "call_sequence": "iterate(); X(out=X_host); communicate(); update(); evaluate_f(X_host)  "
+                             "[dist_pgo.cpp:497-530, steady state, solver state kept]",
+            "host_buffers": "pinned", "bytes": "summed over ranks"}

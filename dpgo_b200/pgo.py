@@ -170,6 +170,13 @@ class _Driver:
         L.check(self.lib.mmpgo_translation_solve(self._h, L.dptr(rhs), L.dptr(t)))
         return t
 
+    def stage_range(self):
+        """[lo, hi): the global pose ids whose rows initialize / evaluate_f / evaluate_grad copy to the device
+        (the local nodes' own poses and their remote neighbours)."""
+        lo, hi = C.c_int64(), C.c_int64()
+        L.check(self.lib.mmpgo_stage_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def solver_info(self):
         s = (C.c_int64 * 8)()
         L.check(self.lib.mmpgo_solver_info(self._h, s))

@@ -224,6 +224,9 @@ int mmpgo_graph_sizes(mmpgo_handle h, int64_t *sizes);
  * is dense), nnz(L) of the sparse factor, stored factor entries (both copies), separator-tree height,
  * supernodes, jobs per solve, persistent CTAs, poses solved by the dense inverse} */
 int mmpgo_solver_info(mmpgo_handle h, int64_t *info);
+/* [lo, hi): the global pose ids whose rows of a host iterate are copied to the device by mmpgo_initialize /
+ * mmpgo_evaluate_f / mmpgo_evaluate_grad: the own poses of the local nodes and their remote neighbours. */
+int mmpgo_stage_range(mmpgo_handle h, int64_t *lo, int64_t *hi);
 /* Sparse direct solve, measurement: duration in microseconds of every stage of the LAST solve (forward
  * stages by height, then backward stages by depth; device timer of CTA 0 at the grid barriers) with the
  * warp jobs and CTA jobs of the stage.  *count receives the number of stages (0 without a sparse factor);
