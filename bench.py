@@ -384,7 +384,7 @@ def run_ours(args):
     NO = sizes["own_poses"]
     HE = sizes["inter_half_edges"]
     kinds = [k for k in drv.KERNEL_KINDS if k != "g00_spmv"]
-    k_ms = {k: drv.profile_pass(k, 20) for k in kinds if k != "g00_solve"}
+    k_ms = {k: drv.profile_pass(k, 20) for k in kinds if not k.startswith("g00_solve")}
     # the persistent translation solve is timed over the solves of the timed steps themselves
     # (bytes = pose-iterations x bytes per pose-iteration); one extra cold solve gives its duration
     solve_calls = max(int(ctr.solve_calls), 1)

@@ -350,8 +350,8 @@ int mmpgo_mf_host_solve(int32_t n, const int32_t *ptr, const int32_t *col, const
     mmpgo::mf_host_solve(F, nrhs, rhs, x);
     if (stats) {
       stats[0] = F.nnz; stats[1] = F.height; stats[2] = (int64_t)F.sn.size(); stats[3] = (int64_t)F.flops;
-      stats[4] = (int64_t)(F.wjobs[0].size() + F.cjobs[0].size()); stats[5] = (int64_t)(F.wjobs[1].size() + F.cjobs[1].size());
-      stats[6] = F.max_R_big; stats[7] = F.urows;
+      stats[4] = (int64_t)F.wjobs[0].size(); stats[5] = (int64_t)F.wjobs[1].size();
+      stats[6] = F.max_R; stats[7] = F.urows;
     }
     return MMPGO_OK;
   } catch (const std::exception &e) {

@@ -148,7 +148,7 @@ struct NodeFactor {
   std::vector<int> sperm, siperm;                 // scalar permutation (local)
   std::vector<int> c0, k, m, child0, child1, height, depth;
   std::vector<std::vector<int>> bnd;              // boundary, scalar permuted indices (local)
-  std::vector<size_t> moff;
+  std::vector<size_t> moff, mtoff;                // column-major copy (k columns of Rp) / row-major copy (R rows of kp)
   std::vector<double> M, MT;
   int64_t nnz = 0;
   double flops = 0.0;
@@ -161,7 +161,7 @@ void factor_node(const MfMatrix &A, int block, int leaf, bool symbolic_only, Nod
   if (A.skip) {
     nf.siperm.resize(n);
     std::iota(nf.siperm.begin(), nf.siperm.end(), 0);
-    nf.moff.assign(1, 0);
+    nf.moff.assign(1, 0); nf.mtoff.assign(1, 0);
     return;
   }
   // vertex graph
@@ -224,14 +224,16 @@ void factor_node(const MfMatrix &A, int block, int leaf, bool symbolic_only, Nod
   }
   for (int s = ns - 1; s >= 0; --s)
     for (int c : {nf.child0[s], nf.child1[s]}) if (c >= 0) nf.depth[c] = nf.depth[s] + 1;
-  nf.moff.resize(ns + 1);
-  nf.moff[0] = 0;
-  for (int s = 0; s < ns; ++s) nf.moff[s + 1] = nf.moff[s] + (size_t)nf.k[s] * (nf.k[s] + nf.m[s]);
+  nf.moff.assign(ns + 1, 0); nf.mtoff.assign(ns + 1, 0);
+  for (int s = 0; s < ns; ++s) {
+    nf.moff[s + 1] = nf.moff[s] + (size_t)nf.k[s] * mf_even(nf.k[s] + nf.m[s]);
+    nf.mtoff[s + 1] = nf.mtoff[s] + (size_t)(nf.k[s] + nf.m[s]) * mf_even(nf.k[s]);
+  }
   if (symbolic_only) return;
 
   // numeric: multifrontal Cholesky, dense fronts (column-major, lower triangle)
   nf.M.assign(nf.moff[ns], 0.0);
-  nf.MT.assign(nf.moff[ns], 0.0);
+  nf.MT.assign(nf.mtoff[ns], 0.0);
   std::vector<int> fpos(n, -1);
   std::vector<std::vector<double>> upd(ns);
   std::vector<double> F, X;
@@ -286,18 +288,19 @@ void factor_node(const MfMatrix &A, int block, int leaf, bool symbolic_only, Nod
         X[(size_t)i + (size_t)c * k] = -sum / F[(size_t)i + (size_t)i * R];
       }
     }
-    double *Ms = &nf.M[nf.moff[s]], *Mt = &nf.MT[nf.moff[s]];
+    double *Ms = &nf.M[nf.moff[s]], *Mt = &nf.MT[nf.mtoff[s]];
+    const size_t Rp = (size_t)mf_even(R), kp = (size_t)mf_even(k);
     for (int c = 0; c < k; ++c) {
-      for (int i = c; i < k; ++i) Ms[(size_t)i + (size_t)c * R] = X[(size_t)i + (size_t)c * k];
+      for (int i = c; i < k; ++i) Ms[(size_t)i + (size_t)c * Rp] = X[(size_t)i + (size_t)c * k];
       for (int i = 0; i < m; ++i) {
         // W = L21 inv(L11):  W[i][c] = sum_{t >= c} L21[i][t] X[t][c]
         double sum = 0.0;
         for (int t = c; t < k; ++t) sum += F[(size_t)(k + i) + (size_t)t * R] * X[(size_t)t + (size_t)c * k];
-        Ms[(size_t)(k + i) + (size_t)c * R] = sum;
+        Ms[(size_t)(k + i) + (size_t)c * Rp] = sum;
       }
     }
     for (int i = 0; i < R; ++i)
-      for (int c = 0; c < k; ++c) Mt[(size_t)i * k + c] = Ms[(size_t)i + (size_t)c * R];
+      for (int c = 0; c < k; ++c) Mt[(size_t)i * kp + c] = Ms[(size_t)i + (size_t)c * Rp];
     if (m > 0) {
       std::vector<double> &U = upd[s];
       U.resize((size_t)m * m);
@@ -317,12 +320,12 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
   MfFactor &F = *out;
   F = MfFactor();
   F.block = block;
-  size_t tot_m = 0, tot_rows = 0, tot_b = 0;
+  size_t tot_m = 0, tot_mt = 0, tot_rows = 0, tot_b = 0;
   int row_off = 0;
   for (int a = 0; a < A; ++a) {
     if (!nfs[a].ok) return -1;
     F.nnz += nfs[a].nnz; F.flops += nfs[a].flops;
-    tot_m += nfs[a].moff.back();
+    tot_m += nfs[a].moff.back(); tot_mt += nfs[a].mtoff.back();
     for (size_t s = 0; s < nfs[a].k.size(); ++s) { tot_rows += nfs[a].k[s] + nfs[a].m[s]; tot_b += nfs[a].m[s]; }
     row_off += nfs[a].n;
   }
@@ -332,12 +335,12 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
       for (size_t s = 0; s < nfs[a].k.size(); ++s) F.height = std::max(F.height, nfs[a].height[s]);
     return 0;
   }
-  F.M.resize(tot_m); F.MT.resize(tot_m);
+  F.M.resize(tot_m); F.MT.resize(tot_mt);
   F.pull0.assign(tot_rows, -1); F.pull1.assign(tot_rows, -1);
   F.bidx.resize(tot_b);
   F.iperm.resize(F.nrows);
   std::vector<std::vector<int>> fw, bw;        // supernodes per forward / backward stage
-  size_t mo = 0, ro = 0, bo = 0;
+  size_t mo = 0, mto = 0, ro = 0, bo = 0;
   int uo = 0;
   row_off = 0;
   for (int a = 0; a < A; ++a) {
@@ -345,7 +348,7 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
     const int ns = (int)nf.k.size(), base = (int)F.sn.size();
     if (!nf.M.empty()) {
       std::memcpy(&F.M[mo], nf.M.data(), nf.M.size() * sizeof(double));
-      std::memcpy(&F.MT[mo], nf.MT.data(), nf.MT.size() * sizeof(double));
+      std::memcpy(&F.MT[mto], nf.MT.data(), nf.MT.size() * sizeof(double));
     }
     for (int p = 0; p < nf.n; ++p) F.iperm[row_off + p] = row_off + nf.siperm[p];
     std::vector<int> uoff(ns);
@@ -354,7 +357,7 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
       std::memset(&sn, 0, sizeof(sn));
       const int k = nf.k[s], m = nf.m[s], R = k + m;
       sn.node = a; sn.c0 = row_off + nf.c0[s]; sn.k = k; sn.R = R;
-      sn.moff = (long long)(mo + nf.moff[s]);
+      sn.moff = (long long)(mo + nf.moff[s]); sn.mtoff = (long long)(mto + nf.mtoff[s]);
       sn.rowoff = (int)ro; sn.boff = (int)bo; sn.uoff = uo;
       sn.nchild = (nf.child0[s] >= 0) + (nf.child1[s] >= 0);
       uoff[s] = uo;
@@ -382,31 +385,33 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
       F.height = std::max(F.height, nf.height[s]);
       ro += R; bo += m; uo += m;
     }
-    mo += nf.M.size();
+    mo += nf.M.size(); mto += nf.MT.size();
     row_off += nf.n;
     nf = NodeFactor();     // release the node's copy
   }
   F.urows = uo;
   F.perm.resize(F.nrows);
   for (int p = 0; p < F.nrows; ++p) F.perm[F.iperm[p]] = p;
-  // job lists: supernodes with R <= MF_RW are cut into warp jobs of 32 rows (forward) / 32 columns
-  // (backward), larger ones into CTA jobs of MF_SPAN
+  // warp jobs.  Forward: fronts with at most MF_KS columns are cut into jobs of 64 rows (whole front if it has at
+  // most 128), wider ones into jobs of 2 MF_SROWS rows summed in slices.  Backward: fronts with at most MF_RS rows
+  // are one job, taller ones are cut into jobs of 2 MF_SROWS columns summed in slices.
   for (int dir = 0; dir < 2; ++dir) {
     const std::vector<std::vector<int>> &stages = dir == 0 ? fw : bw;
-    F.wstage[dir].assign(1, 0); F.cstage[dir].assign(1, 0);
+    F.wstage[dir].assign(1, 0);
     for (const auto &st : stages) {
       for (int s : st) {
         const MfSn &sn = F.sn[s];
-        const int span = dir == 0 ? sn.R : sn.k;
-        if (sn.R <= MF_RW) {
-          for (int r0 = 0; r0 < span; r0 += 32) F.wjobs[dir].push_back({s, r0});
+        F.max_R = std::max(F.max_R, sn.R);
+        if (dir == 0) {
+          if (sn.k > MF_KS) for (int r0 = 0; r0 < sn.R; r0 += 2 * MF_SROWS) F.wjobs[0].push_back({s, r0, std::min(2 * MF_SROWS, sn.R - r0), 0});
+          else if (sn.R <= 128) F.wjobs[0].push_back({s, 0, sn.R, 0});
+          else for (int r0 = 0; r0 < sn.R; r0 += 64) F.wjobs[0].push_back({s, r0, std::min(64, sn.R - r0), 0});
         } else {
-          F.max_R_big = std::max(F.max_R_big, sn.R);
-          for (int r0 = 0; r0 < span; r0 += MF_SPAN) F.cjobs[dir].push_back({s, r0});
+          if (sn.R > MF_RS) for (int c0 = 0; c0 < sn.k; c0 += 2 * MF_SROWS) F.wjobs[1].push_back({s, c0, std::min(2 * MF_SROWS, sn.k - c0), 0});
+          else F.wjobs[1].push_back({s, 0, sn.k, 0});
         }
       }
       F.wstage[dir].push_back((int)F.wjobs[dir].size());
-      F.cstage[dir].push_back((int)F.cjobs[dir].size());
     }
   }
   return 0;
@@ -428,64 +433,60 @@ void mf_host_solve(const MfFactor &F, int nrhs, const double *rhs, double *x) {
       if (p1 >= 0) val[c] += u[(size_t)p1 * D + c];
     }
   };
-  // sum_{j in [b, e)} M[j] * f[j] per right-hand side: one chain, or MF_Q contiguous slices
-  auto dot = [&](bool big, int b, int e, const double *Mp, size_t stride, const double *fv, double *acc) {
-    const int nq = big ? MF_Q : 1, per = (e - b + nq - 1) / nq;
-    for (int c = 0; c < D; ++c) acc[c] = 0.0;
-    for (int q = 0; q < nq; ++q) {
-      double part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int j = b + q * per; j < std::min(e, b + (q + 1) * per); ++j)
-        for (int c = 0; c < D; ++c) part[c] = std::fma(Mp[(size_t)j * stride], fv[(size_t)j * D + c], part[c]);
-      for (int c = 0; c < D; ++c) acc[c] = q == 0 ? part[c] : acc[c] + part[c];
+  // sum_{j in [b, e)} Mp[j] * fv[j] per right-hand side, fused multiply-adds in ascending order: one chain, or
+  // (sliced fronts) MF_Q chains -- term j belongs to slice ((j - base) % MF_BLK) / MF_QW -- added in slice order
+  auto dot = [&](bool sliced, int base, int b, int e, const double *Mp, const double *fv, double *acc) {
+    double part[MF_Q][8];
+    for (int q = 0; q < MF_Q; ++q) for (int c = 0; c < D; ++c) part[q][c] = 0.0;
+    for (int j = b; j < e; ++j) {
+      const int q = sliced ? ((j - base) % MF_BLK) / MF_QW : 0;
+      for (int c = 0; c < D; ++c) part[q][c] = std::fma(Mp[j], fv[(size_t)j * D + c], part[q][c]);
+    }
+    for (int c = 0; c < D; ++c) {
+      acc[c] = part[0][c];
+      if (sliced) for (int q = 1; q < MF_Q; ++q) acc[c] += part[q][c];
     }
   };
   for (size_t st = 0; st + 1 < F.wstage[0].size(); ++st)
-    for (int big = 1; big >= 0; --big) {
-      const std::vector<MfJob> &jobs = big ? F.cjobs[0] : F.wjobs[0];
-      const std::vector<int> &ptr = big ? F.cstage[0] : F.wstage[0];
-      for (int t = ptr[st]; t < ptr[st + 1]; ++t) {
-        const MfJob &jb = jobs[t];
-        const MfSn &sn = F.sn[jb.sn];
-        const int span = big ? MF_SPAN : 32;
-        const int k = sn.k, R = sn.R;
-        f.resize((size_t)k * D);
-        for (int j = 0; j < k; ++j) stage_rows(sn, j, &f[(size_t)j * D]);
-        const int jend = jb.r0 < k ? std::min(k, jb.r0 + span) : k;
-        const double *Ms = &F.M[sn.moff];
-        for (int i = jb.r0; i < std::min(R, jb.r0 + span); ++i) {
-          double acc[8];
-          dot(big != 0, 0, jend, Ms + i, (size_t)R, f.data(), acc);
-          if (i < k) {
-            for (int c = 0; c < D; ++c) y[(size_t)(sn.c0 + i) * D + c] = acc[c];
-          } else {
-            double f2[8];
-            stage_rows(sn, i, f2);
-            for (int c = 0; c < D; ++c) u[(size_t)(sn.uoff + i - k) * D + c] = f2[c] - acc[c];
-          }
+    for (int t = F.wstage[0][st]; t < F.wstage[0][st + 1]; ++t) {
+      const MfJob &jb = F.wjobs[0][t];
+      const MfSn &sn = F.sn[jb.sn];
+      const int k = sn.k, kp = mf_even(k);
+      f.assign((size_t)kp * D, 0.0);
+      for (int j = 0; j < k; ++j) stage_rows(sn, j, &f[(size_t)j * D]);
+      const double *Mt = &F.MT[sn.mtoff];
+      for (int i = jb.r0; i < jb.r0 + jb.n; ++i) {
+        const int len = i < k ? i + 1 : k;                            // inv(L11) is lower triangular
+        double acc[8];
+        dot(k > MF_KS, 0, 0, len, Mt + (size_t)i * kp, f.data(), acc);
+        if (i < k) {
+          for (int c = 0; c < D; ++c) y[(size_t)(sn.c0 + i) * D + c] = acc[c];
+        } else {
+          double f2[8];
+          stage_rows(sn, i, f2);
+          for (int c = 0; c < D; ++c) u[(size_t)(sn.uoff + i - k) * D + c] = f2[c] - acc[c];
         }
       }
     }
   for (size_t st = 0; st + 1 < F.wstage[1].size(); ++st)
-    for (int big = 1; big >= 0; --big) {
-      const std::vector<MfJob> &jobs = big ? F.cjobs[1] : F.wjobs[1];
-      const std::vector<int> &ptr = big ? F.cstage[1] : F.wstage[1];
-      for (int t = ptr[st]; t < ptr[st + 1]; ++t) {
-        const MfJob &jb = jobs[t];
-        const MfSn &sn = F.sn[jb.sn];
-        const int span = big ? MF_SPAN : 32;
-        const int k = sn.k, R = sn.R;
-        f.resize((size_t)R * D);
-        for (int i = 0; i < R; ++i)
-          for (int c = 0; c < D; ++c)
-            f[(size_t)i * D + c] = i < k ? y[(size_t)(sn.c0 + i) * D + c] : -xp[(size_t)F.bidx[sn.boff + i - k] * D + c];
-        const double *Mt = &F.MT[sn.moff];
-        for (int j = jb.r0; j < std::min(k, jb.r0 + span); ++j) {
-          double acc[8];
-          dot(big != 0, jb.r0, R, Mt + j, (size_t)k, f.data(), acc);
-          for (int c = 0; c < D; ++c) {
-            xp[(size_t)(sn.c0 + j) * D + c] = acc[c];
-            x[(size_t)F.iperm[sn.c0 + j] * D + c] = acc[c];
-          }
+    for (int t = F.wstage[1][st]; t < F.wstage[1][st + 1]; ++t) {
+      const MfJob &jb = F.wjobs[1][t];
+      const MfSn &sn = F.sn[jb.sn];
+      const int k = sn.k, R = sn.R, Rp = mf_even(R);
+      f.assign((size_t)Rp * D, 0.0);
+      for (int i = 0; i < R; ++i)
+        for (int c = 0; c < D; ++c)
+          f[(size_t)i * D + c] = i < k ? y[(size_t)(sn.c0 + i) * D + c] : -xp[(size_t)F.bidx[sn.boff + i - k] * D + c];
+      const double *Ms = &F.M[sn.moff];
+      const bool sliced = R > MF_RS;
+      for (int j = jb.r0; j < jb.r0 + jb.n; ++j) {
+        // rows before the job's (pass's) first column multiply zeros of M_s^T; sliced jobs start their blocks there
+        const int b = sliced ? jb.r0 : ((j - jb.r0) / 64) * 64 + jb.r0;
+        double acc[8];
+        dot(sliced, b, b, R, Ms + (size_t)j * Rp, f.data(), acc);
+        for (int c = 0; c < D; ++c) {
+          xp[(size_t)(sn.c0 + j) * D + c] = acc[c];
+          x[(size_t)F.iperm[sn.c0 + j] * D + c] = acc[c];
         }
       }
     }

@@ -17,9 +17,10 @@
 // so that both sweeps are plain dense products without a triangular dependency inside a supernode:
 //   forward   [ y_s ; -du ] = M_s f1,  f1 = b_s + (children's update rows),  u_s = f2 - L21 y_s
 //   backward  x_s = M_s^T [ y_s ; -x_boundary ]
-// M_s is stored twice, column-major (forward: one row per thread, coalesced over rows) and
-// row-major (backward: one column per thread, coalesced over columns).  Supernodes of equal
-// height (forward) / depth (backward) are independent: one grid-wide barrier per level.
+// M_s is stored twice: row-major (forward: a lane owns one output row, or a quarter of it, and
+// streams it with 128-bit loads) and column-major (backward: the same for output columns), rows /
+// columns zero-padded to an even length.  Supernodes of equal height (forward) / depth (backward)
+// are independent: one grid-wide barrier per level.
 // Every sum has a fixed order: results do not depend on scheduling or on which nodes share a GPU.
 #pragma once
 #include <cuda_runtime.h>
@@ -33,24 +34,30 @@ struct MfSn {             // one supernode, 48 bytes
   int node;               // local robot node
   int c0;                 // first column, handle-wide permuted numbering (node offset included)
   int k, R;               // columns, rows
-  long long moff;         // M_s: column-major copy (leading dimension R) in M, row-major copy (leading dimension k) in MT
+  long long moff;         // column-major copy in M: column j at moff + j * Rp, Rp = R rounded up to even   (backward sweep)
+  long long mtoff;        // row-major copy in MT: row i at mtoff + i * kp, kp = k rounded up to even        (forward sweep)
   int rowoff;             // its R rows in pull0 / pull1
   int boff;               // its m = R - k boundary rows in bidx
   int uoff;               // first row of its update vector in the u buffer
   int nchild;             // 0 for the leaves of the separator tree (no update rows to pull)
-  int pad[2];
 };
 static_assert(sizeof(MfSn) == 48, "MfSn must be 48 bytes");
 
-// forward: rows [r0, r0 + span) of supernode sn; backward: columns [r0, r0 + span).  Warp jobs (fronts of at
-// most MF_RW rows) have span 32, CTA jobs span MF_SPAN.
-struct MfJob { int sn, r0; };
+// One warp job: rows [r0, r0 + n) of supernode sn in the forward sweep, columns [r0, r0 + n) in the backward sweep.
+struct MfJob { int sn, r0, n, pad; };
 
-constexpr int MF_THREADS = 1024;   // one persistent CTA per SM
+constexpr int MF_THREADS = 512;    // one persistent CTA per SM: 16 warps with up to 128 registers each (measured per solve on the
+                                   // 1 M-pose grid: 256 threads 1.29, 384: 1.10, 512: 0.97, 768: 1.16, 1024 (spills): 1.62 ms)
 constexpr int MF_WARPS = MF_THREADS / 32;
-constexpr int MF_RW = 128;         // supernodes with R <= MF_RW are served by single warps
-constexpr int MF_Q = 4;            // CTA jobs: every output row / column is summed in MF_Q contiguous slices by MF_Q threads
-constexpr int MF_SPAN = MF_THREADS / MF_Q;   // rows (forward) / columns (backward) of one CTA job
+constexpr int MF_BLK = 128;        // rows of a front's right-hand side a warp stages at a time
+constexpr int MF_BUF = MF_BLK + 8; // its shared-memory buffer (the dot loops may overrun a range by < 8 zero terms)
+constexpr int MF_KS = 64;          // forward: fronts with more columns are summed in MF_Q slices by MF_Q lanes per row
+constexpr int MF_RS = 128;         // backward: fronts with more rows are summed in MF_Q slices by MF_Q lanes per column
+constexpr int MF_Q = 4;            // slices: term j of a block of MF_BLK belongs to slice (j % MF_BLK) / (MF_BLK / MF_Q)
+constexpr int MF_QW = MF_BLK / MF_Q;
+constexpr int MF_SROWS = 32 / MF_Q;   // rows (columns) per sliced job
+
+inline int mf_even(int x) { return (x + 1) & ~1; }
 
 // Host-side factor of all local nodes of a handle (or of one matrix in the host-only tests).
 struct MfFactor {
@@ -61,11 +68,11 @@ struct MfFactor {
   std::vector<int> pull0, pull1;       // per supernode row: row of a child's update vector in u, or -1
   std::vector<int> bidx;               // per boundary row: position in the permuted numbering
   std::vector<int> iperm, perm;        // permuted position -> original row (handle-wide) and its inverse
-  // per sweep (0 forward, 1 backward): warp jobs and CTA jobs, with their ranges per stage
-  std::vector<MfJob> wjobs[2], cjobs[2];
-  std::vector<int> wstage[2], cstage[2];   // [stage[s], stage[s+1])
+  // per sweep (0 forward, 1 backward): the warp jobs with their ranges per stage
+  std::vector<MfJob> wjobs[2];
+  std::vector<int> wstage[2];              // [stage[s], stage[s+1])
   int urows = 0;                       // rows of the u buffer
-  int max_R_big = 0;                   // largest R among supernodes served by whole CTAs
+  int max_R = 0;                       // largest front
   int64_t nnz = 0;                     // sum k(k+1)/2 + k m  (entries of L)
   double flops = 0.0;
   int height = 0;
@@ -92,14 +99,13 @@ struct MfDevice {
   const MfSn *sn = nullptr;
   const double *M = nullptr, *MT = nullptr;
   const int *pull0 = nullptr, *pull1 = nullptr, *bidx = nullptr, *iperm = nullptr;
-  const MfJob *wjobs[2] = {nullptr, nullptr}, *cjobs[2] = {nullptr, nullptr};
-  const int *wstage[2] = {nullptr, nullptr}, *cstage[2] = {nullptr, nullptr};
+  const MfJob *wjobs[2] = {nullptr, nullptr};
+  const int *wstage[2] = {nullptr, nullptr};
   int n_stage[2] = {0, 0};
   double *y = nullptr, *xp = nullptr, *u = nullptr;     // [nrows][D] permuted, [urows][D]
   unsigned *barrier = nullptr;                          // grid barrier counter (zeroed before launch)
   unsigned long long *stage_ns = nullptr;               // [n_stage[0] + n_stage[1] + 1] globaltimer of CTA 0 at every stage boundary
   int smem_bytes = 0;
-  int part_off = 0;                                     // doubles: slice sums of the CTA jobs behind the front buffer
   int max_ctas = 0;                                     // CTAs the fullest stage can use (grid sizing)
 };
 struct MfSolveArgs {
@@ -109,6 +115,7 @@ struct MfSolveArgs {
   double *out;              // out[row * out_stride + c] = sign * x
   int out_stride;
   double sign;
+  int dry;                  // measurement: walk the stages and barriers without executing the jobs
 };
 template <int D> int launch_mf_solve(const MfSolveArgs &a, int grid, cudaStream_t s);
 template <int D> int mf_solve_max_grid(int device, int smem_bytes);

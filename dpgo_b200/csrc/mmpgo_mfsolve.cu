@@ -7,13 +7,15 @@
 // Execution model.  A stage = all supernodes of equal height (forward) or depth (backward) of
 // every active robot node; its tasks are dealt round-robin to the persistent CTAs, stages are
 // separated by a grid barrier (2 H + 1 barriers per solve, H = tree height, 14 on the 15 625-pose
-// slabs of the 1 M-pose grid), one 1024-thread CTA per SM.  Supernodes with at most MF_RW rows are
-// served by single warps (32 independent warp jobs per task: 32 rows forward / 32 columns backward
-// each, the front's right-hand side staged in the warp's slice of shared memory); larger ones by
-// whole CTAs, MF_SPAN rows / columns per job, each summed in MF_Q contiguous slices by MF_Q threads.
-// Sums run in ascending order with fused multiply-adds, slice sums are added in slice order:
-// deterministic, bit-identical to mf_host_solve.  The factor is read exactly once per sweep, so the
-// loops batch their loads (MF_BATCH in flight per thread) instead of counting on reuse.
+// slabs of the 1 M-pose grid), one 1024-thread CTA per SM.  All work is cut into WARP JOBS: a run of
+// rows (forward) or columns (backward) of one supernode, whose right-hand side the warp stages in its
+// slice of shared memory (in blocks of MF_BLK rows for large fronts).  A lane owns two adjacent
+// output rows / columns, so every term is one 128-bit load and a warp reads 512 contiguous bytes.
+// Narrow fronts: one lane per output pair, passes of 64.  Wide fronts: MF_Q lanes per pair, each
+// summing a quarter of every block, so that the dependent chain of a job stays short.  The kernel
+// is bound by the latency of dependent instructions and loads per job, not by bandwidth.  Sums run
+// in ascending order with fused multiply-adds, slice sums are added in slice order: deterministic,
+// bit-identical to mf_host_solve.
 // HBM traffic per solve = both copies of the factor once (2 x 8 B x nnz(M)) + O(rows) vectors:
 // the roofline model of SURVEY.md section 8(d) for the solve.
 #include "mmpgo_mf.cuh"
@@ -66,194 +68,252 @@ __device__ __forceinline__ void front_rhs(const MfSolveArgs &a, const MfSn &sn, 
   }
 }
 
-// The factor is read exactly once per sweep: latency, not reuse, has to be covered, so the loads of MF_BATCH
-// consecutive terms are issued together and the first batch is issued BEFORE the front's right-hand side is
-// staged (its addresses depend on the supernode record only).
-constexpr int MF_BATCH = 8;
-__device__ __forceinline__ void load_batch(const double *__restrict__ Mp, size_t stride, int j, int e, double (&mv)[MF_BATCH]) {
-#pragma unroll
-  for (int t = 0; t < MF_BATCH; ++t) mv[t] = j + t < e ? __ldg(Mp + (size_t)(j + t) * stride) : 0.0;
-}
-// acc[c] = sum_{j in [b, e)} Mp[j * stride] * fv[j * D + c], ascending j, fused multiply-adds; mv = the batch
-// loaded at j = b
+// The factor is read exactly once per sweep: latency, not reuse, has to be covered.  A lane owns TWO adjacent
+// output rows (forward, column-major copy) or columns (backward, row-major copy), so that one 128-bit load per
+// term serves both and the 32 lanes of a warp read 512 contiguous bytes; MF_G terms are in flight per lane.  The
+// front's right-hand side comes from shared memory (broadcast reads).
+constexpr int MF_G = 8;
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+// a0[c] += sum_{j in [b, e)} P[j * ld].x * fv[j * D + c], a1 likewise with .y; ascending j, fused multiply-adds.
+// The loop runs to the warp-uniform bound emax >= e; terms beyond e are taken as zeros (the buffer behind fv only
+// ever holds finite numbers, up to 8 rows past any range).
 template <int D>
-__device__ __forceinline__ void dot_range(const double *__restrict__ Mp, size_t stride, const double *fv, int b, int e,
-                                          double (&mv)[MF_BATCH], double (&acc)[D]) {
+__device__ __forceinline__ void dot_pair(const double *__restrict__ P, size_t ld, const double *fv, int b, int e, int emax,
+                                         double (&a0)[D], double (&a1)[D]) {
+  for (int j = b; j < emax; j += MF_G) {
+    double2 mv[MF_G];
 #pragma unroll
-  for (int c = 0; c < D; ++c) acc[c] = 0.0;
-  for (int j = b; j < e; j += MF_BATCH) {
-    if (j > b) load_batch(Mp, stride, j, e, mv);
+    for (int t = 0; t < MF_G; ++t) mv[t] = j + t < e ? ldg2(P + (size_t)(j + t) * ld) : make_double2(0.0, 0.0);
 #pragma unroll
-    for (int t = 0; t < MF_BATCH; ++t) {
-      if (j + t < e) {
+    for (int t = 0; t < MF_G; ++t) {
+      const double *fp = fv + (j + t) * D;
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] = fma(mv[t], fv[(j + t) * D + c], acc[c]);
+      for (int c = 0; c < D; ++c) {
+        const double fc = fp[c];
+        a0[c] = fma(mv[t].x, fc, a0[c]);
+        a1[c] = fma(mv[t].y, fc, a1[c]);
       }
     }
   }
 }
+// slice sums of the MF_Q lanes of an output pair, added in slice order; valid in the lane with q == 0
+template <int D> __device__ __forceinline__ void slice_sum(double (&acc)[D], int lane) {
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    double s = acc[c];
+#pragma unroll
+    for (int q = 1; q < MF_Q; ++q) s += __shfl_sync(0xffffffffu, acc[c], (lane & ~(MF_Q - 1)) + q);
+    acc[c] = s;
+  }
+}
 
-// ---- warp jobs (fronts of at most MF_RW rows) ------------------------------------------------
-// forward: rows [r0, r0 + 32) of the supernode; `buf` holds k x D doubles
+// rows [j0, j0 + cnt) of the front's forward right-hand side -> buf[0 .. cnt), zero beyond k.  cnt <= MF_BLK: the
+// (at most four) rows of a lane are fetched together -- first every index, then every value -- instead of one
+// dependent chain after the other.
 template <int D>
-__device__ __forceinline__ void forward_warp(const MfSolveArgs &a, const MfSn &sn, int r0, double *buf, int lane) {
+__device__ __forceinline__ void stage_forward(const MfSolveArgs &a, const MfSn &sn, int j0, int cnt, double *buf, int lane) {
+  const MfDevice &f = a.f;
+  constexpr int U = MF_BLK / 32;
+  int p0[U], p1[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = j0 + lane + 32 * u;
+    p0[u] = -1; p1[u] = -1;
+    if (sn.nchild && lane + 32 * u < cnt && j < sn.k) { p0[u] = __ldg(f.pull0 + sn.rowoff + j); p1[u] = __ldg(f.pull1 + sn.rowoff + j); }
+  }
+  double v[U][D];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = j0 + lane + 32 * u;
+    const bool on = lane + 32 * u < cnt && j < sn.k;
+#pragma unroll
+    for (int c = 0; c < D; ++c) v[u][c] = on ? a.rhs[(size_t)(sn.c0 + j) * D + c] : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (p0[u] >= 0) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) v[u][c] += __ldcg(f.u + (size_t)p0[u] * D + c);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (p1[u] >= 0) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) v[u][c] += __ldcg(f.u + (size_t)p1[u] * D + c);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (lane + 32 * u < cnt) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) buf[(lane + 32 * u) * D + c] = v[u][c];
+    }
+  }
+}
+// rows [i0, i0 + cnt) of [y_s; -x_boundary] -> buf[0 .. cnt), zero beyond R; cnt <= MF_BLK, fetched like stage_forward
+template <int D>
+__device__ __forceinline__ void stage_backward(const MfSolveArgs &a, const MfSn &sn, int i0, int cnt, double *buf, int lane) {
+  const MfDevice &f = a.f;
+  constexpr int U = MF_BLK / 32;
+  const double *src[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = i0 + lane + 32 * u;
+    src[u] = nullptr;
+    if (lane + 32 * u < cnt && i < sn.R)
+      src[u] = i < sn.k ? f.y + (size_t)(sn.c0 + i) * D : f.xp + (size_t)__ldg(f.bidx + sn.boff + i - sn.k) * D;
+  }
+  double v[U][D];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double sg = i0 + lane + 32 * u < sn.k ? 1.0 : -1.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) v[u][c] = src[u] ? sg * __ldcg(src[u] + c) : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (lane + 32 * u < cnt) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) buf[(lane + 32 * u) * D + c] = v[u][c];
+    }
+  }
+}
+
+// forward: one output row of [y_s; -du] = M_s f1; f2 = the children's update rows of a boundary row (fetched
+// before the dot product, see forward_job)
+template <int D>
+__device__ __forceinline__ void forward_store(const MfSolveArgs &a, const MfSn &sn, int i, const double (&acc)[D], const double (&f2)[D]) {
+  const MfDevice &f = a.f;
+  if (i < sn.k) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) f.y[(size_t)(sn.c0 + i) * D + c] = acc[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) f.u[(size_t)(sn.uoff + i - sn.k) * D + c] = f2[c] - acc[c];
+  }
+}
+// update rows pulled by the boundary rows i, i + 1 of a front (zero for columns and for rows beyond `end`)
+template <int D>
+__device__ __forceinline__ void pull_pair(const MfSolveArgs &a, const MfSn &sn, int i, int end, bool on, double (&g0)[D], double (&g1)[D]) {
+#pragma unroll
+  for (int c = 0; c < D; ++c) { g0[c] = 0.0; g1[c] = 0.0; }
+  if (on && sn.nchild) {
+    if (i >= sn.k && i < end) front_rhs<D>(a, sn, i, g0);
+    if (i + 1 >= sn.k && i + 1 < end) front_rhs<D>(a, sn, i + 1, g1);
+  }
+}
+// backward: one entry of x_s
+template <int D>
+__device__ __forceinline__ void backward_store(const MfSolveArgs &a, const MfSn &sn, int j, const double (&acc)[D]) {
+  const MfDevice &f = a.f;
+  double *o = a.out + (size_t)__ldg(f.iperm + sn.c0 + j) * a.out_stride;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    f.xp[(size_t)(sn.c0 + j) * D + c] = acc[c];
+    o[c] = a.sign * acc[c];
+  }
+}
+
+// forward job: [y_s; -du] = M_s f1 for rows [r0, r0 + n)
+template <int D>
+__device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn, int r0, int n, double *buf, int lane) {
   const MfDevice &f = a.f;
   if (a.active && !a.active[sn.node]) return;
-  const int k = sn.k, R = sn.R;
-  const int i = r0 + lane;
-  // rows above the diagonal of inv(L11) are zero: columns beyond the chunk's last row add nothing
-  const int jend = i < R ? (r0 < k ? min(k, r0 + 32) : k) : 0;
-  const double *Mi = f.M + sn.moff + i;
-  double mv[MF_BATCH];
-  load_batch(Mi, (size_t)R, 0, jend, mv);
-  for (int j = lane; j < k; j += 32) {
-    double v[D];
-    front_rhs<D>(a, sn, j, v);
+  const int k = sn.k, kp = (k + 1) & ~1, Rp = (sn.R + 1) & ~1;
+  const double *Mc = f.M + sn.moff;                       // column-major, leading dimension Rp
+  double a0[D], a1[D];
+  if (k <= MF_KS) {
+    // one lane per pair of rows, passes of 64 rows; the whole right-hand side fits the buffer
+    stage_forward<D>(a, sn, 0, kp, buf, lane);
+    __syncwarp();
+    for (int p0 = r0; p0 < r0 + n; p0 += 64) {
+      const int i = p0 + 2 * lane;
+      const bool mine = i < r0 + n;
+      // inv(L11) is lower triangular: rows below p0 + 64 never reach beyond column p0 + 63
+      const int emax = p0 < k ? min(k, p0 + 64) : k;
 #pragma unroll
-    for (int c = 0; c < D; ++c) buf[j * D + c] = v[c];
-  }
-  double f2[D];
-  if (i >= k && i < R) front_rhs<D>(a, sn, i, f2);
-  __syncwarp();
-  if (i < R) {
-    double acc[D];
-    dot_range<D>(Mi, (size_t)R, buf, 0, jend, mv, acc);
-    if (i < k) {
+      for (int c = 0; c < D; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
+      double g0[D], g1[D];
+      pull_pair<D>(a, sn, i, r0 + n, mine, g0, g1);
+      dot_pair<D>(Mc + i, (size_t)Rp, buf, 0, mine ? emax : 0, emax, a0, a1);
+      if (mine) {
+        forward_store<D>(a, sn, i, a0, g0);
+        if (i + 1 < r0 + n) forward_store<D>(a, sn, i + 1, a1, g1);
+      }
+    }
+  } else {
+    // MF_Q lanes per pair of rows (n <= 2 MF_SROWS rows), the right-hand side staged in blocks of MF_BLK columns;
+    // lane q of a pair sums the q-th quarter of every block
+    const int ri = lane / MF_Q, q = lane % MF_Q;
+    const int i = r0 + 2 * ri;
+    const bool mine = 2 * ri < n;
+    const int emax = r0 < k ? min(k, r0 + 2 * MF_SROWS) : k;
 #pragma unroll
-      for (int c = 0; c < D; ++c) f.y[(size_t)(sn.c0 + i) * D + c] = acc[c];
-    } else {
-#pragma unroll
-      for (int c = 0; c < D; ++c) f.u[(size_t)(sn.uoff + i - k) * D + c] = f2[c] - acc[c];
+    for (int c = 0; c < D; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
+    double g0[D], g1[D];
+    pull_pair<D>(a, sn, i, r0 + n, mine && q == 0, g0, g1);
+    for (int cb = 0; cb < emax; cb += MF_BLK) {
+      __syncwarp();
+      stage_forward<D>(a, sn, cb, min(MF_BLK, kp - cb), buf, lane);
+      __syncwarp();
+      const int b = cb + q * MF_QW, em = min(emax, b + MF_QW);
+      dot_pair<D>(Mc + i, (size_t)Rp, buf - cb * D, b, mine ? em : b, em, a0, a1);
+    }
+    slice_sum<D>(a0, lane);
+    slice_sum<D>(a1, lane);
+    if (mine && q == 0) {
+      forward_store<D>(a, sn, i, a0, g0);
+      if (2 * ri + 1 < n) forward_store<D>(a, sn, i + 1, a1, g1);
     }
   }
   __syncwarp();
 }
 
-// backward: columns [r0, r0 + 32); `buf` holds R x D doubles
+// backward job: x_s = M_s^T [y_s; -x_boundary] for columns [c0, c0 + n)
 template <int D>
-__device__ __forceinline__ void backward_warp(const MfSolveArgs &a, const MfSn &sn, int r0, double *buf, int lane) {
+__device__ __forceinline__ void backward_job(const MfSolveArgs &a, const MfSn &sn, int c0, int n, double *buf, int lane) {
   const MfDevice &f = a.f;
   if (a.active && !a.active[sn.node]) return;
-  const int k = sn.k, R = sn.R;
-  const int j = r0 + lane;
-  const int e = j < k ? R : r0;
-  const double *Mj = f.MT + sn.moff + j;
-  double mv[MF_BATCH];
-  load_batch(Mj, (size_t)k, r0, e, mv);
-  const int orow = j < k ? __ldg(f.iperm + sn.c0 + j) : 0;
-  for (int i = r0 + lane; i < R; i += 32) {      // rows before r0 multiply zeros of every column of the chunk
-    const double *src = i < k ? f.y + (size_t)(sn.c0 + i) * D : f.xp + (size_t)__ldg(f.bidx + sn.boff + i - k) * D;
-    const double sg = i < k ? 1.0 : -1.0;
+  const int R = sn.R, Rp = (R + 1) & ~1, kp = (sn.k + 1) & ~1;
+  const double *Mr = f.MT + sn.mtoff;                     // row-major, leading dimension kp
+  double a0[D], a1[D];
+  if (R <= MF_RS) {
+    stage_backward<D>(a, sn, 0, Rp, buf, lane);
+    __syncwarp();
+    for (int p0 = c0; p0 < c0 + n; p0 += 64) {            // rows before p0 multiply zeros of every column of the pass
+      const int j = p0 + 2 * lane;
+      const bool mine = j < c0 + n;
 #pragma unroll
-    for (int c = 0; c < D; ++c) buf[i * D + c] = sg * __ldcg(src + c);
-  }
-  __syncwarp();
-  if (j < k) {
-    double acc[D];
-    dot_range<D>(Mj, (size_t)k, buf, r0, R, mv, acc);
-    double *o = a.out + (size_t)orow * a.out_stride;
+      for (int c = 0; c < D; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
+      dot_pair<D>(Mr + j, (size_t)kp, buf, p0, mine ? R : p0, R, a0, a1);
+      if (mine) {
+        backward_store<D>(a, sn, j, a0);
+        if (j + 1 < c0 + n) backward_store<D>(a, sn, j + 1, a1);
+      }
+    }
+  } else {
+    const int lj = lane / MF_Q, q = lane % MF_Q;
+    const int j = c0 + 2 * lj;
+    const bool mine = 2 * lj < n;
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-      f.xp[(size_t)(sn.c0 + j) * D + c] = acc[c];
-      o[c] = a.sign * acc[c];
+    for (int c = 0; c < D; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
+    for (int rb = c0; rb < R; rb += MF_BLK) {             // rows before c0 multiply zeros of the job's columns
+      __syncwarp();
+      stage_backward<D>(a, sn, rb, min(MF_BLK, Rp - rb), buf, lane);
+      __syncwarp();
+      const int b = rb + q * MF_QW, em = min(R, b + MF_QW);
+      dot_pair<D>(Mr + j, (size_t)kp, buf - rb * D, b, mine ? em : b, em, a0, a1);
+    }
+    slice_sum<D>(a0, lane);
+    slice_sum<D>(a1, lane);
+    if (mine && q == 0) {
+      backward_store<D>(a, sn, j, a0);
+      if (2 * lj + 1 < n) backward_store<D>(a, sn, j + 1, a1);
     }
   }
   __syncwarp();
-}
-
-// ---- CTA jobs (larger fronts): MF_SPAN rows / columns, each summed in MF_Q contiguous slices by MF_Q
-// threads; the slice sums are added in slice order.  `buf`: front right-hand side, `part`: [MF_Q][MF_SPAN][D]
-template <int D>
-__device__ __forceinline__ void forward_cta(const MfSolveArgs &a, const MfJob job, double *buf, double *part) {
-  const MfDevice &f = a.f;
-  const MfSn sn = f.sn[job.sn];
-  const bool on = !a.active || a.active[sn.node];
-  const int k = sn.k, R = sn.R;
-  const int li = threadIdx.x % MF_SPAN, q = threadIdx.x / MF_SPAN;
-  const int i = job.r0 + li;
-  const int jend = job.r0 < k ? min(k, job.r0 + MF_SPAN) : k;
-  const int per = (jend + MF_Q - 1) / MF_Q;
-  const int jb = q * per, je = (on && i < R) ? min(jend, (q + 1) * per) : jb;
-  const double *Mi = f.M + sn.moff + i;
-  double mv[MF_BATCH];
-  load_batch(Mi, (size_t)R, jb, je, mv);
-  if (on) {
-    for (int j = threadIdx.x; j < k; j += MF_THREADS) {
-      double v[D];
-      front_rhs<D>(a, sn, j, v);
-#pragma unroll
-      for (int c = 0; c < D; ++c) buf[j * D + c] = v[c];
-    }
-  }
-  double f2[D];
-  if (on && q == 0 && i >= k && i < R) front_rhs<D>(a, sn, i, f2);
-  __syncthreads();
-  if (on && i < R) {
-    double acc[D];
-    dot_range<D>(Mi, (size_t)R, buf, jb, je, mv, acc);
-#pragma unroll
-    for (int c = 0; c < D; ++c) part[(q * MF_SPAN + li) * D + c] = acc[c];
-  }
-  __syncthreads();
-  if (on && i < R && q == 0) {
-    double acc[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      acc[c] = part[li * D + c];
-#pragma unroll
-      for (int qq = 1; qq < MF_Q; ++qq) acc[c] += part[(qq * MF_SPAN + li) * D + c];
-    }
-    if (i < k) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) f.y[(size_t)(sn.c0 + i) * D + c] = acc[c];
-    } else {
-#pragma unroll
-      for (int c = 0; c < D; ++c) f.u[(size_t)(sn.uoff + i - k) * D + c] = f2[c] - acc[c];
-    }
-  }
-}
-
-template <int D>
-__device__ __forceinline__ void backward_cta(const MfSolveArgs &a, const MfJob job, double *buf, double *part) {
-  const MfDevice &f = a.f;
-  const MfSn sn = f.sn[job.sn];
-  const bool on = !a.active || a.active[sn.node];
-  const int k = sn.k, R = sn.R;
-  const int lj = threadIdx.x % MF_SPAN, q = threadIdx.x / MF_SPAN;
-  const int j = job.r0 + lj;
-  const int per = (R - job.r0 + MF_Q - 1) / MF_Q;
-  const int ib = job.r0 + q * per, ie = (on && j < k) ? min(R, job.r0 + (q + 1) * per) : ib;
-  const double *Mj = f.MT + sn.moff + j;
-  double mv[MF_BATCH];
-  load_batch(Mj, (size_t)k, ib, ie, mv);
-  const int orow = (on && j < k && q == 0) ? __ldg(f.iperm + sn.c0 + j) : 0;
-  if (on) {
-    for (int i = job.r0 + threadIdx.x; i < R; i += MF_THREADS) {
-      const double *src = i < k ? f.y + (size_t)(sn.c0 + i) * D : f.xp + (size_t)__ldg(f.bidx + sn.boff + i - k) * D;
-      const double sg = i < k ? 1.0 : -1.0;
-#pragma unroll
-      for (int c = 0; c < D; ++c) buf[i * D + c] = sg * __ldcg(src + c);
-    }
-  }
-  __syncthreads();
-  if (on && j < k) {
-    double acc[D];
-    dot_range<D>(Mj, (size_t)k, buf, ib, ie, mv, acc);
-#pragma unroll
-    for (int c = 0; c < D; ++c) part[(q * MF_SPAN + lj) * D + c] = acc[c];
-  }
-  __syncthreads();
-  if (on && j < k && q == 0) {
-    double *o = a.out + (size_t)orow * a.out_stride;
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      double acc = part[lj * D + c];
-#pragma unroll
-      for (int qq = 1; qq < MF_Q; ++qq) acc += part[(qq * MF_SPAN + lj) * D + c];
-      f.xp[(size_t)(sn.c0 + j) * D + c] = acc;
-      o[c] = a.sign * acc;
-    }
-  }
 }
 
 template <int D>
@@ -261,8 +321,12 @@ __global__ void __launch_bounds__(MF_THREADS, 1) k_mf_solve(MfSolveArgs a) {
   extern __shared__ double mf_sm[];
   const MfDevice &f = a.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *part = mf_sm + f.part_off, *wbuf = mf_sm + warp * (MF_RW * D);
+  double *wbuf = mf_sm + warp * (MF_BUF * D);
   const int gw = blockIdx.x * MF_WARPS + warp, nw = gridDim.x * MF_WARPS;
+  // the dot loops run to padded bounds and multiply loaded zeros with whatever the buffer holds there: make sure
+  // it only ever holds finite numbers
+  for (int i = threadIdx.x; i < (MF_WARPS + 1) * MF_BUF * D; i += MF_THREADS) mf_sm[i] = 0.0;
+  __syncthreads();
   unsigned target = 0;
   int stamp = 0;
   auto mark = [&]() {      // stage boundaries as seen by CTA 0 (mmpgo_solver_stage_times)
@@ -276,28 +340,21 @@ __global__ void __launch_bounds__(MF_THREADS, 1) k_mf_solve(MfSolveArgs a) {
   mark();
 #pragma unroll 1
   for (int dir = 0; dir < 2; ++dir) {
-    const MfJob *wj = f.wjobs[dir], *cj = f.cjobs[dir];
+    const MfJob *wj = f.wjobs[dir];
     for (int st = 0; st < f.n_stage[dir]; ++st) {
-      // CTA jobs of the stage first (the long ones), then the warp jobs, every warp striding over the
-      // stage's list with the NEXT job's record already in flight
-      const int c1 = f.cstage[dir][st + 1];
-      for (int t = f.cstage[dir][st] + blockIdx.x; t < c1; t += gridDim.x) {
-        __syncthreads();                                 // the previous job's shared memory is free
-        if (dir == 0) forward_cta<D>(a, cj[t], mf_sm, part); else backward_cta<D>(a, cj[t], mf_sm, part);
-      }
-      __syncthreads();
+      // every warp strides over the stage's job list, the next job record in flight while the current one runs
       const int w1 = f.wstage[dir][st + 1];
       int t = f.wstage[dir][st] + gw;
-      MfJob job = {0, 0};
-      MfSn sn;
-      if (t < w1) { job = wj[t]; sn = f.sn[job.sn]; }
+      MfJob cur = {0, 0, 0, 0};
+      if (t < w1) cur = wj[t];
       while (t < w1) {
         const int tn = t + nw;
-        MfJob jobn = {0, 0};
-        MfSn snn;
-        if (tn < w1) { jobn = wj[tn]; snn = f.sn[jobn.sn]; }
-        if (dir == 0) forward_warp<D>(a, sn, job.r0, wbuf, lane); else backward_warp<D>(a, sn, job.r0, wbuf, lane);
-        t = tn; job = jobn; sn = snn;
+        MfJob nxt = {0, 0, 0, 0};
+        if (tn < w1) nxt = wj[tn];
+        const MfSn sn = f.sn[cur.sn];
+        if (a.dry) { t = tn; cur = nxt; continue; }
+        if (dir == 0) forward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane); else backward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane);
+        t = tn; cur = nxt;
       }
       if (dir == 0 || st + 1 < f.n_stage[1]) grid_barrier(f.barrier, target);
       mark();

@@ -457,7 +457,9 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
       mats[a].n = h->info[a].n0; mats[a].ptr = &mptr[ptr_off[a]]; mats[a].col = mcol.data(); mats[a].val = mval.data();
       mats[a].skip = !h->pcg_mask[a];
     }
-    const int leaf = 16;
+    // dissection stops at 32 poses: smaller leaves mean fewer factor entries (-12 % at 16) but more and shorter
+    // jobs and two more levels; measured on the 1 M-pose grid 16: 1.13, 32: 0.98, 48: 0.95, 64: 0.94 ms per solve
+    const int leaf = 32;
     MfFactor F;
     mf_factor(mats, 1, leaf, true, &F);
     size_t free_b = 0, total_b = 0;
@@ -470,9 +472,8 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     }
     if (fits) {
       if (mf_factor(mats, 1, leaf, false, &F) != 0) { set_error("G00 is not positive definite"); return MMPGO_ERR_ARG; }
-      // shared memory: per-warp front buffers of the warp jobs, or one front buffer + the slice sums of a CTA job
-      const int part_off = d * std::max(MF_WARPS * MF_RW, F.max_R_big);
-      const int smem = (int)sizeof(double) * (part_off + MF_Q * MF_SPAN * d);
+      // shared memory: one front buffer of MF_BUF rows per warp (+ one spare: the last warp's loops may overrun)
+      const int smem = (int)sizeof(double) * (MF_WARPS + 1) * MF_BUF * d;
       if (smem <= 200 * 1024) {
         MfDevice &m = h->mf;
         MfSn *sn_d; double *M_d, *MT_d; int *p0, *p1, *bi, *ip;
@@ -487,17 +488,14 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
         h->h_mf_perm = F.perm;
         m.sn = sn_d; m.M = M_d; m.MT = MT_d; m.pull0 = p0; m.pull1 = p1; m.bidx = bi; m.iperm = ip;
         for (int dir = 0; dir < 2; ++dir) {
-          MfJob *wj, *cj; int *ws, *cs;
+          MfJob *wj; int *ws;
           if ((rc = upload(h, &wj, F.wjobs[dir]))) return rc;
-          if ((rc = upload(h, &cj, F.cjobs[dir]))) return rc;
           if ((rc = upload(h, &ws, F.wstage[dir]))) return rc;
-          if ((rc = upload(h, &cs, F.cstage[dir]))) return rc;
-          m.wjobs[dir] = wj; m.cjobs[dir] = cj; m.wstage[dir] = ws; m.cstage[dir] = cs;
+          m.wjobs[dir] = wj; m.wstage[dir] = ws;
           m.n_stage[dir] = (int)F.wstage[dir].size() - 1;
           for (int st = 0; st < m.n_stage[dir]; ++st)
-            m.max_ctas = std::max(m.max_ctas, (F.wstage[dir][st + 1] - F.wstage[dir][st] + MF_WARPS - 1) / MF_WARPS +
-                                                  F.cstage[dir][st + 1] - F.cstage[dir][st]);
-          h->mf_tasks += (int64_t)(F.wjobs[dir].size() + F.cjobs[dir].size());
+            m.max_ctas = std::max(m.max_ctas, (F.wstage[dir][st + 1] - F.wstage[dir][st] + MF_WARPS - 1) / MF_WARPS);
+          h->mf_tasks += (int64_t)F.wjobs[dir].size();
         }
         if ((rc = dalloc(h, &m.y, (size_t)NO * d))) return rc;
         if ((rc = dalloc(h, &m.xp, (size_t)NO * d))) return rc;
@@ -508,9 +506,9 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
         for (int dir = 0; dir < 2; ++dir)
           for (size_t st = 0; st + 1 < F.wstage[dir].size(); ++st) {
             h->mf_stage_jobs.push_back(F.wstage[dir][st + 1] - F.wstage[dir][st]);
-            h->mf_stage_jobs.push_back(F.cstage[dir][st + 1] - F.cstage[dir][st]);
+            h->mf_stage_jobs.push_back(0);
           }
-        m.smem_bytes = smem; m.part_off = part_off;
+        m.smem_bytes = smem;
         const int mg = d == 2 ? mf_solve_max_grid<2>(h->opt.device, smem) : mf_solve_max_grid<3>(h->opt.device, smem);
         if (mg <= 0) { set_error("occupancy query for the sparse direct solve failed"); return MMPGO_ERR_CUDA; }
         h->mf_grid = std::max(1, std::min(mg, m.max_ctas));

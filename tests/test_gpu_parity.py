@@ -478,7 +478,7 @@ def test_direct_solve_bitwise_equals_host_restatement():
     b = rng.standard_normal((g.num_poses, 3))
     x = np.zeros_like(b)
     ptr, col = A.indptr.astype(np.int32), A.indices.astype(np.int32)
-    L.check(L.load().mmpgo_mf_host_solve(A.shape[0], L.iptr(ptr), L.iptr(col), L.dptr(np.ascontiguousarray(A.data)), 1, 16, 3,
+    L.check(L.load().mmpgo_mf_host_solve(A.shape[0], L.iptr(ptr), L.iptr(col), L.dptr(np.ascontiguousarray(A.data)), 1, 32, 3,
                                          L.dptr(b), L.dptr(x), None))
     t = drv.translation_solve(b)
     assert np.array_equal(t, -x), np.abs(t + x).max()

@@ -14,6 +14,10 @@ t0 = time.time()
 drv = D.DPGOStar(g, nodes, D.Options(dense_solve_max_n=0, translation_solver=solver))
 print("set_graph %.1f s" % (time.time() - t0), drv.solver_info())
 assert drv.initialize(X0) == 0 and drv.update() == 0 and drv.iterate() == 0
+if solver == "direct" and "nodry" not in sys.argv:
+    print("g00_solve dry (stages + barriers only) ms:", drv.profile_pass("g00_solve_dry", reps))
+    for us, wj, cj in drv.solver_stage_times()[:3]:
+        print("dry stage %8.1f us  warp jobs %7d" % (us, wj))
 print("g00_solve ms:", drv.profile_pass("g00_solve", reps))
 for us, wj, cj in drv.solver_stage_times():
     print("stage %8.1f us  warp jobs %7d  cta jobs %5d" % (us, wj, cj))
