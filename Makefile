@@ -2,7 +2,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fopenmp,-O3 -Iinclude
-SRC := dpgo_b200/csrc/mmpgo_kernels.cu dpgo_b200/csrc/mmpgo_tsolve.cu dpgo_b200/csrc/mmpgo_setup.cu dpgo_b200/csrc/mmpgo_factor.cu dpgo_b200/csrc/mmpgo_mfsolve.cu dpgo_b200/csrc/mmpgo_driver.cu dpgo_b200/csrc/mmpgo_capi.cu
+SRC := dpgo_b200/csrc/mmpgo_kernels.cu dpgo_b200/csrc/mmpgo_tsolve.cu dpgo_b200/csrc/mmpgo_setup.cu dpgo_b200/csrc/mmpgo_factor.cu dpgo_b200/csrc/mmpgo_mfsolve.cu dpgo_b200/csrc/mmpgo_driver.cu dpgo_b200/csrc/mmpgo_nccl.cu dpgo_b200/csrc/mmpgo_capi.cu
 OBJ := $(SRC:.cu=.o)
 LIB := dpgo_b200/libmmpgo.so
 
@@ -18,7 +18,7 @@ $(HOSTBIN): host/src/dist_pgo.cpp host/include/mmpgo_host/DPGO.h include/mmpgo.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -Xcompiler -fopenmp -lgomp -cudart shared
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -Xcompiler -fopenmp -lgomp -ldl -cudart shared
 
 clean:
 	rm -f $(OBJ) $(LIB) $(HOSTBIN)

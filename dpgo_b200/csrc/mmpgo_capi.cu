@@ -210,6 +210,16 @@ int mmpgo_set_device_allreduce(mmpgo_handle hh, mmpgo_allreduce_dev_fn fn) {
   h->allreduce_dev_fn = fn;
   return MMPGO_OK;
 }
+int mmpgo_nccl_unique_id(void *id128) {
+  if (!id128) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::nccl_unique_id(id128));
+}
+int mmpgo_nccl_init(mmpgo_handle hh, const void *id128) {
+  H_OR_FAIL(hh);
+  if (!id128) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
+  GUARDED(mmpgo::nccl_init(h, id128));
+}
+
 int mmpgo_halo_counts(mmpgo_handle hh, int64_t *send_poses, int64_t *recv_poses) {
   H_OR_FAIL(hh);
   if (!send_poses || !recv_poses || (int)h->send_poses.size() != h->world) {

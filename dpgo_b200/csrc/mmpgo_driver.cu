@@ -97,7 +97,26 @@ static int upload_coef(Handle *h, const std::vector<double> &c) {
 static int allreduce(Handle *h, double *v, int n) {
   if (h->world <= 1) return 0;
   h->allreduces++;
+  if (h->nccl_comm) {
+    // through the device: pinned staging -> ncclAllReduce on the handle's stream -> back
+    double *hp = h->h_pinned + (size_t)h->A * (2 * NS + 8) + 32;
+    for (int i = 0; i < n; ++i) hp[i] = v[i];
+    CK(cudaMemcpyAsync(h->d_scalar + 4, hp, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    RC(nccl_allreduce(h, h->d_scalar + 4, n));
+    CK(cudaMemcpyAsync(hp, h->d_scalar + 4, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) v[i] = hp[i];
+    return 0;
+  }
+  if (!h->allreduce_fn) { set_error("no transport: call mmpgo_nccl_init or pass callbacks to mmpgo_set_sharding"); return MMPGO_ERR_STATE; }
   if (h->allreduce_fn(h->cb_user, v, n) != 0) { set_error("allreduce callback failed"); return MMPGO_ERR_ARG; }
+  return 0;
+}
+// boundary chunks of `send` -> peers, theirs -> `recv`, ordered on the handle's stream
+static int exchange(Handle *h, const double *send, const std::vector<int64_t> &sc, double *recv, const std::vector<int64_t> &rc) {
+  if (h->nccl_comm) return nccl_exchange(h, send, sc.data(), recv, rc.data());
+  if (!h->exchange_fn) { set_error("no transport: call mmpgo_nccl_init or pass callbacks to mmpgo_set_sharding"); return MMPGO_ERR_STATE; }
+  if (h->exchange_fn(h->cb_user, send, sc.data(), recv, rc.data()) != 0) { set_error("exchange callback failed"); return MMPGO_ERR_ARG; }
   return 0;
 }
 
@@ -152,11 +171,7 @@ template <int D> struct Drv {
     h->ctr.launches++;
     // no host synchronisation: the transport orders itself on the handle's stream (mmpgo.h)
     h->halo_exchanges++;
-    if (h->exchange_fn(h->cb_user, h->d_send, h->send_dbl.data(), x + (size_t)h->NO * PB, h->recv_dbl.data()) != 0) {
-      set_error("exchange callback failed");
-      return MMPGO_ERR_ARG;
-    }
-    return 0;
+    return exchange(h, h->d_send, h->send_dbl, x + (size_t)h->NO * PB, h->recv_dbl);
   }
 
   // the same for two pose arrays in ONE all-to-all (per-peer chunks [a | b])
@@ -166,10 +181,7 @@ template <int D> struct Drv {
     launch_copy_poses<D>(h->n_send, h->d_send_idx, h->d_send2_b, xb, h->d_send2, h->stream);
     h->ctr.launches += 2;
     h->halo_exchanges++;
-    if (h->exchange_fn(h->cb_user, h->d_send2, h->send_dbl2.data(), h->d_recv2, h->recv_dbl2.data()) != 0) {
-      set_error("exchange callback failed");
-      return MMPGO_ERR_ARG;
-    }
+    RC(exchange(h, h->d_send2, h->send_dbl2, h->d_recv2, h->recv_dbl2));
     launch_copy_poses<D>(h->NH, h->d_recv2_a, h->d_halo_row, h->d_recv2, xa, h->stream);
     launch_copy_poses<D>(h->NH, h->d_recv2_b, h->d_halo_row, h->d_recv2, xb, h->stream);
     h->ctr.launches += 2;
@@ -946,13 +958,14 @@ template <int D> struct Drv {
       h->ctr.launches += 2;
       double *hp = h->h_pinned;
       double v[4];
-      if (h->world > 1 && h->allreduce_dev_fn) {
+      if (h->world > 1 && (h->allreduce_dev_fn || h->nccl_comm)) {
         // the four scalars are reduced on the device (stream-ordered), then read back once
         launch_sum_strided(A, h->d_node_scal, NS, h->d_scalar + 2, h->stream);
         launch_sum_strided(A, h->d_node_scal2, NS, h->d_scalar + 3, h->stream);
         h->ctr.launches += 2;
         h->allreduces++;
-        if (h->allreduce_dev_fn(h->cb_user, h->d_scalar, 4) != 0) { set_error("device allreduce callback failed"); return MMPGO_ERR_ARG; }
+        if (h->nccl_comm) RC(nccl_allreduce(h, h->d_scalar, 4));
+        else if (h->allreduce_dev_fn(h->cb_user, h->d_scalar, 4) != 0) { set_error("device allreduce callback failed"); return MMPGO_ERR_ARG; }
         CK(cudaMemcpyAsync(hp, h->d_scalar, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         v[0] = hp[0]; v[2] = hp[1]; v[1] = hp[2]; v[3] = hp[3];

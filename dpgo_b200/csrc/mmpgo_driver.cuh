@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -159,6 +160,7 @@ struct Handle {
   mmpgo_allreduce_fn allreduce_fn = nullptr;
   mmpgo_allreduce_dev_fn allreduce_dev_fn = nullptr;
   void *cb_user = nullptr;
+  void *nccl_comm = nullptr;          // ncclComm_t owned by the handle (mmpgo_nccl_init); replaces the callbacks
   int64_t halo_exchanges = 0, allreduces = 0;
   mmpgo_counters ctr;
   std::vector<void *> allocs;
@@ -189,5 +191,10 @@ int plan_halo(int64_t N, int num_nodes, int64_t E, const int32_t *ei, const int3
               const int32_t *rnb, int rank, int64_t *sc, int64_t *rcn, int64_t *sg, int64_t scap, int64_t *rg,
               int64_t rcap);
 void set_error(const std::string &s);
+int nccl_unique_id(void *id);
+int nccl_init(Handle *h, const void *id);
+void nccl_destroy(Handle *h);
+int nccl_exchange(Handle *h, const double *send, const int64_t *send_counts, double *recv, const int64_t *recv_counts);
+int nccl_allreduce(Handle *h, double *vals_dev, int n);
 
 }  // namespace mmpgo

@@ -48,6 +48,7 @@ template <typename T> static int upload(Handle *h, T **p, const std::vector<T> &
 }
 
 void driver_free(Handle *h) {
+  nccl_destroy(h);
   for (void *p : h->allocs) cudaFree(p);
   h->allocs.clear();
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -613,8 +614,8 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   if ((rc = dalloc(h, &h->d_coef, (size_t)A * MAXC))) return rc;
   if ((rc = dalloc(h, &h->d_gamma, (size_t)A))) return rc;
   if ((rc = dalloc(h, &h->d_block_partials, (size_t)148 * 8 + 8))) return rc;
-  if ((rc = dalloc(h, &h->d_scalar, (size_t)8))) return rc;
-  CK(cudaMallocHost((void **)&h->h_pinned, sizeof(double) * ((size_t)A * (2 * NS + 8) + 64)));
+  if ((rc = dalloc(h, &h->d_scalar, (size_t)40))) return rc;
+  CK(cudaMallocHost((void **)&h->h_pinned, sizeof(double) * ((size_t)A * (2 * NS + 8) + 64)));   // [.. + 32, +64): all-reduce staging
   if ((rc = dalloc(h, &h->d_slot, (size_t)RED_SLOTS * A * NS))) return rc;
   CK(cudaMallocHost((void **)&h->h_slot, sizeof(double) * (size_t)RED_SLOTS * A * NS));
   std::memset(h->h_slot, 0, sizeof(double) * (size_t)RED_SLOTS * A * NS);
@@ -679,7 +680,7 @@ int driver_set_sharding(Handle *h, int rank, int world, const int32_t *rnb, mmpg
     set_error("inconsistent sharding");
     return MMPGO_ERR_ARG;
   }
-  if (world > 1 && (!ex || !ar)) { set_error("collective callbacks required for world_size > 1"); return MMPGO_ERR_ARG; }
+  if (world > 1 && ((ex == nullptr) != (ar == nullptr))) { set_error("pass both collective callbacks, or none and call mmpgo_nccl_init"); return MMPGO_ERR_ARG; }
   h->rank = rank; h->world = world; h->exchange_fn = ex; h->allreduce_fn = ar; h->cb_user = user;
   auto owner = [&](int node) {
     int r = (int)(std::upper_bound(rnb, rnb + world + 1, node) - rnb) - 1;

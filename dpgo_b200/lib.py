@@ -87,6 +87,8 @@ SIGNATURES = {
     "mmpgo_set_sharding": (C.c_int, [_P, C.c_int32, C.c_int32, _ip, EXCHANGE_FN, ALLREDUCE_FN, C.c_void_p]),
     "mmpgo_set_device_allreduce": (C.c_int, [_P, ALLREDUCE_DEV_FN]),
     "mmpgo_halo_counts": (C.c_int, [_P, _lp, _lp]),
+    "mmpgo_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "mmpgo_nccl_init": (C.c_int, [_P, C.c_void_p]),
     "mmpgo_plan_halo": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _ip, _ip, C.c_int32, _ip, C.c_int32,
                                   _lp, _lp, _lp, C.c_int64, _lp, C.c_int64]),
     "mmpgo_plan_halo_pair": (C.c_int, [C.c_int32, _lp, _lp, C.c_int64, _ip, _ip, _ip, _ip, _ip]),

@@ -67,7 +67,7 @@ class _DevArray:
 class ShardedDriver:
     """A DPGOHash / DPGOStar over the nodes of this rank, with the NCCL transport bound."""
 
-    def __init__(self, graph, num_nodes, options, algorithm, rank, world):
+    def __init__(self, graph, num_nodes, options, algorithm, rank, world, native_nccl=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -89,8 +89,20 @@ class ShardedDriver:
         self._ext = torch.cuda.ExternalStream(self.drv.stream()) if world > 1 else None
         self._views = {}
         self._ard = L.ALLREDUCE_DEV_FN(self._allreduce_dev)
+        self.transport = "callbacks"
         if world > 1:
             L.check(self.drv.lib.mmpgo_set_device_allreduce(self.drv._h, self._ard))
+            if dist.get_backend() == "nccl" and native_nccl:
+                # the library drives NCCL itself (grouped send / recv + all-reduce on its own stream, from C++);
+                # torch.distributed only carries the 128-byte communicator id to the ranks
+                idb = (C.c_ubyte * 128)()
+                if rank == 0:
+                    L.check(self.drv.lib.mmpgo_nccl_unique_id(idb))
+                t = torch.tensor(list(idb), dtype=torch.uint8, device="cuda")
+                dist.broadcast(t, 0)
+                idb = (C.c_ubyte * 128)(*t.cpu().tolist())
+                L.check(self.drv.lib.mmpgo_nccl_init(self.drv._h, idb))
+                self.transport = "nccl (C++)"
 
     def _view(self, ptr, n):
         """torch view of n device doubles at ptr (cached: the buffers of a handle are fixed)."""
@@ -172,8 +184,8 @@ class ShardedDriver:
         return sc, rc
 
 
-def make_driver(graph, num_nodes, options, algorithm="star", rank=0, world=1):
-    return ShardedDriver(graph, num_nodes, options or Options(), algorithm, rank, world)
+def make_driver(graph, num_nodes, options, algorithm="star", rank=0, world=1, native_nccl=True):
+    return ShardedDriver(graph, num_nodes, options or Options(), algorithm, rank, world, native_nccl)
 
 
 def e2e_loop(drv, X0, steps, E, d, N):

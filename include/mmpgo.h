@@ -194,6 +194,14 @@ int mmpgo_set_sharding(mmpgo_handle h, int32_t rank, int32_t world_size,
  * (ncclAllReduce).  When set, the AMM-PGO* scalars are reduced on the device and read back once. */
 typedef int (*mmpgo_allreduce_dev_fn)(void *user, void *vals_dev, int32_t n);
 int mmpgo_set_device_allreduce(mmpgo_handle h, mmpgo_allreduce_dev_fn allreduce_dev);
+/* NCCL transport driven by the library itself (what mmpgo_communicate(handle, ncclComm_t) of SURVEY.md section 8b
+ * stands for): rank 0 obtains a 128-byte ncclUniqueId, the caller distributes it to all ranks (MPI, a file,
+ * torch.distributed ...), every rank calls mmpgo_nccl_init after mmpgo_set_sharding (whose callbacks may then
+ * be NULL).  From then on the halo exchange is a grouped ncclSend / ncclRecv with the ranks that share an edge and
+ * the AMM-PGO* scalars are one ncclAllReduce, all enqueued on the handle's stream from C++.  libnccl.so.2 is
+ * resolved with dlopen at the first call; the communicator is destroyed with the handle. */
+int mmpgo_nccl_unique_id(void *id128);
+int mmpgo_nccl_init(mmpgo_handle h, const void *id128);
 /* per-peer number of boundary poses sent / received each exchange (length world_size) */
 int mmpgo_halo_counts(mmpgo_handle h, int64_t *send_poses, int64_t *recv_poses);
 /* Host-only (no CUDA) restatement of the exchange plan for rank `rank`: the global ids

@@ -1,4 +1,5 @@
-"""torchrun script: the sharded run over W ranks reproduces the single-handle run.
+"""torchrun script: the sharded run over W ranks (one process per GPU, NCCL) reproduces the single-handle run,
+with the NCCL transport driven from C++ (mmpgo_nccl_init) and with the torch.distributed callbacks.
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py"""
 import os, sys
 import numpy as np
@@ -11,11 +12,14 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ok_all = True
-for (alg, loss, dims, nodes, iters, dense) in (("hash", "trivial", (8, 8, 8), 8, 12, 2048), ("hash", "huber", (8, 8, 8), 8, 12, 2048),
-                                               ("star", "trivial", (8, 8, 8), 8, 12, 2048), ("star", "welsch", (8, 8, 8), 8, 12, 0),
-                                               ("star", "trivial", (30, 30, 16), 16, 6, 0)):
-    g, _, X0 = D.grid3d(*dims, seed=4)
-    drv = multi.make_driver(g, nodes, D.Options(loss=loss, device=lr, dense_solve_max_n=dense), alg, rank, world)
+CASES = (("hash", "trivial", "grid", (8, 8, 8), 8, 12, 2048, True), ("hash", "huber", "grid", (8, 8, 8), 8, 12, 2048, False),
+         ("star", "trivial", "grid", (8, 8, 8), 8, 12, 2048, True), ("star", "welsch", "grid", (8, 8, 8), 8, 12, 0, True),
+         ("star", "trivial", "grid", (30, 30, 16), 16, 6, 0, True), ("star", "trivial", "grid", (30, 30, 16), 16, 6, 0, False),
+         # BASELINE.json configs[4] in small: multi-robot sphere, Welsch, decentralised AMM-PGO#
+         ("hash", "welsch", "sphere", (16, 600), 16, 10, 0, True))
+for (alg, loss, kind, dims, nodes, iters, dense, native) in CASES:
+    g, _, X0 = D.grid3d(*dims, seed=4) if kind == "grid" else D.sphere_rings(dims[0], dims[1], seed=4)
+    drv = multi.make_driver(g, nodes, D.Options(loss=loss, device=lr, dense_solve_max_n=dense), alg, rank, world, native_nccl=native)
     assert drv.initialize(X0) == 0 and drv.update() == 0
     tr = [drv.global_objective()[0]]
     for _ in range(iters):
@@ -30,10 +34,11 @@ for (alg, loss, dims, nodes, iters, dense) in (("hash", "trivial", (8, 8, 8), 8,
         err = np.abs(np.array(tr) - tr_ref) / np.abs(tr_ref)
         perr = np.abs(Xs.cpu().numpy() - ref.X()).max()
         sc, rc = drv.halo_counts()
-        ok = err.max() < 1e-9 and perr < 1e-7
+        # AMM-PGO# has no scalar collective: the same bits; AMM-PGO* sums its global scalars per rank first
+        ok = (err.max() < 1e-13 and perr == 0.0) if alg == "hash" else (err.max() < 1e-9 and perr < 1e-7)
         ok_all &= ok
-        print("%s %-8s %s nodes=%d world=%d: max rel F err %.2e pose err %.2e exchanges=%d allreduces=%d send=%s %s" % (
-            alg, loss, dims, nodes, world, err.max(), perr, drv.exchanges, drv.allreduces, sc.tolist(), "OK" if ok else "FAIL"))
+        print("%s %-8s %s %s nodes=%d world=%d transport=%s: max rel F err %.2e pose err %.2e send=%s %s" % (
+            alg, loss, kind, dims, nodes, world, drv.transport, err.max(), perr, sc.tolist(), "OK" if ok else "FAIL"))
     dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK", "PASS" if ok_all else "FAIL")
