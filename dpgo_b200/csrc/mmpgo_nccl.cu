@@ -18,6 +18,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -36,7 +37,7 @@ void load_api() {
   }
   if (!g_api.lib) return;
 #define SYM(f) g_api.f = reinterpret_cast<decltype(g_api.f)>(dlsym(g_api.lib, "nccl" #f)); if (!g_api.f) return
-  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(GroupStart); SYM(GroupEnd); SYM(Send); SYM(Recv);
+  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(CommAbort); SYM(GroupStart); SYM(GroupEnd); SYM(Send); SYM(Recv);
   SYM(AllReduce); SYM(GetErrorString);
 #undef SYM
   g_api.ok = true;
@@ -73,8 +74,14 @@ int nccl_init(Handle *h, const void *id) {
   return 0;
 }
 
+// ncclCommDestroy may wait for the peers' communicators; handles are destroyed whenever their owner lets go of
+// them (a garbage collector on the Python side), not in lock step, so the local resources are released with
+// ncclCommAbort once the handle's stream has drained.
 void nccl_destroy(Handle *h) {
-  if (h->nccl_comm && g_api.ok) g_api.CommDestroy(static_cast<ncclComm_t>(h->nccl_comm));
+  if (h->nccl_comm && g_api.ok) {
+    cudaStreamSynchronize(h->stream);
+    g_api.CommAbort(static_cast<ncclComm_t>(h->nccl_comm));
+  }
   h->nccl_comm = nullptr;
 }
 

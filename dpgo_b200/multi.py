@@ -158,6 +158,14 @@ class ShardedDriver:
             return 1
 
     # ---- driver interface ------------------------------------------------------------
+    def close(self):
+        """Release the handle (and its NCCL communicator) now, at a point all ranks reach together, instead of
+        whenever the garbage collector finds the callback cycle."""
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+        self.drv.close()
+
     def __getattr__(self, name):
         return getattr(self.drv, name)
 

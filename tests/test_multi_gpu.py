@@ -27,5 +27,6 @@ def test_sharded_over_nccl_reproduces_single_gpu(world):
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "multi_gpu_check.py")]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    # the script carries its own watchdog (a hang dumps the Python stacks and exits after 240 s per case)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
