@@ -101,7 +101,17 @@ class ShardedDriver:
                 t = torch.tensor(list(idb), dtype=torch.uint8, device="cuda")
                 dist.broadcast(t, 0)
                 idb = (C.c_ubyte * 128)(*t.cpu().tolist())
-                L.check(self.drv.lib.mmpgo_nccl_init(self.drv._h, idb))
+                # NCCL may print its version banner on stdout when a communicator is created: send it to stderr
+                import os, sys
+                sys.stdout.flush()
+                saved = os.dup(1)
+                os.dup2(2, 1)
+                try:
+                    rc = self.drv.lib.mmpgo_nccl_init(self.drv._h, idb)
+                finally:
+                    os.dup2(saved, 1)
+                    os.close(saved)
+                L.check(rc)
                 self.transport = "nccl (C++)"
 
     def _view(self, ptr, n):
