@@ -50,7 +50,7 @@ constexpr int MF_THREADS = 512;    // one persistent CTA per SM: 16 warps with u
                                    // 1 M-pose grid: 256 threads 1.29, 384: 1.10, 512: 0.97, 768: 1.16, 1024 (spills): 1.62 ms)
 constexpr int MF_WARPS = MF_THREADS / 32;
 constexpr int MF_BLK = 128;        // rows of a front's right-hand side a warp stages at a time
-constexpr int MF_BUF = MF_BLK + 8; // its shared-memory buffer (the dot loops may overrun a range by < 8 zero terms)
+constexpr int MF_BUF = MF_BLK + 16; // its shared-memory buffer (the dot loops may overrun a range by < 16 zero terms)
 constexpr int MF_KS = 64;          // forward: fronts with more columns are summed in MF_Q slices by MF_Q lanes per row
 constexpr int MF_RS = 128;         // backward: fronts with more rows are summed in MF_Q slices by MF_Q lanes per column
 constexpr int MF_Q = 4;            // slices: term j of a block of MF_BLK belongs to slice (j % MF_BLK) / (MF_BLK / MF_Q)

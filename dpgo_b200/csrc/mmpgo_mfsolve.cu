@@ -72,7 +72,7 @@ __device__ __forceinline__ void front_rhs(const MfSolveArgs &a, const MfSn &sn, 
 // output rows (forward, column-major copy) or columns (backward, row-major copy), so that one 128-bit load per
 // term serves both and the 32 lanes of a warp read 512 contiguous bytes; MF_G terms are in flight per lane.  The
 // front's right-hand side comes from shared memory (broadcast reads).
-constexpr int MF_G = 8;
+constexpr int MF_G = 16;    // measured per solve on the 1 M-pose grid: 4 in flight 1.31, 8: 0.97, 12: 0.87, 16: 0.84 ms (128 registers)
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 // a0[c] += sum_{j in [b, e)} P[j * ld].x * fv[j * D + c], a1 likewise with .y; ascending j, fused multiply-adds.
