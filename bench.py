@@ -151,11 +151,24 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def build_hash():
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "dpgo_b200", "csrc", "*"))):
+        if not f.endswith(".o"):
+            h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(kernel_key):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture -- only if that capture was
+    taken on THIS build of the kernels (profiles/ncu_traffic.json records the source hash), else None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(kernel_key)
+        t = json.load(open(p))
+        if t.get("build") == build_hash():
+            return t.get(kernel_key)
     return None
 
 

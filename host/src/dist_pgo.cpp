@@ -143,7 +143,7 @@ int main(int argc, char *argv[]) {
   }
   std::map<std::string, std::string> opt = {{"iters", "1000"}, {"dist_init", "true"}, {"loss", "trivial"},
                                              {"accelerated", "true"}, {"save", "true"}, {"algorithm", "hash"},
-                                             {"device", "0"}};
+                                             {"device", "0"}, {"dist_init_fallback", "false"}};
   for (int a = 1; a < argc; ++a) {
     std::string s = argv[a];
     if (s == "--help") {
@@ -159,6 +159,7 @@ int main(int argc, char *argv[]) {
                    "  --algorithm arg (=hash)    \"hash\" (AMM-PGO# / MM-PGO) or \"star\" (AMM-PGO*)\n"
                    "  --device arg (=0)          CUDA device ordinal\n"
                    "  --init arg                 text file with the initial iterate ((d+1)N rows of d numbers)\n"
+                   "  --dist_init_fallback arg (=false)  with --dist_init true: use the centralised chordal initialisation\n"
                    "  --parse_only arg           only read the dataset and print its checksums\n";
       return 0;
     }
@@ -207,9 +208,17 @@ int main(int argc, char *argv[]) {
                 << " " << sj << " " << st << " " << sk << " " << sR << " " << stt << std::endl;
       return 0;
     }
-    if (dist_chordal)
-      std::cout << "note: the distributed chordal initialisation (DChordal) is host code outside this path; "
-                   "using the centralised chordal initialisation" << std::endl;
+    // --dist_init true (the reference's default, dist_pgo.cpp:144-415) asks for the distributed chordal
+    // initialisation (C++/DChordal), host code outside this path: refused unless the caller opts into the
+    // centralised chordal initialisation (--dist_init false, or --dist_init_fallback true) or passes --init
+    if (dist_chordal && !opt.count("init") && !parse_bool(opt["dist_init_fallback"])) {
+      std::cerr << "--dist_init true: the distributed chordal initialisation (DChordal) is not part of this path "
+                   "(MMPGO_ERR_UNSUPPORTED).  Pass --dist_init false (centralised chordal initialisation, "
+                   "dist_pgo.cpp:416-444), --dist_init_fallback true, or --init <file>." << std::endl;
+      return MMPGO_ERR_UNSUPPORTED;
+    }
+    if (dist_chordal && !opt.count("init"))
+      std::cout << "note: --dist_init_fallback: using the centralised chordal initialisation" << std::endl;
     Matrix X;
     if (opt.count("init")) {
       // an initial iterate from a text file: (d+1)N rows of d numbers, the reference's layout

@@ -77,3 +77,13 @@ def test_cli_chordal_initialisation_is_a_sane_start(tmp_path):
     drv = D.DPGOStar(D.read_g2o(path), 4)
     f_gt = 2 * drv.evaluate_f(Xgt)
     assert f0 < 3 * f_gt                    # the chordal relaxation starts near the ground-truth cost
+
+
+def test_dist_init_true_is_refused_not_silently_replaced(tmp_path):
+    """--dist_init true (the reference's default) asks for DChordal, which is host code outside this path: the CLI
+    returns MMPGO_ERR_UNSUPPORTED instead of silently running another initialisation (no device is touched)."""
+    g = D.grid3d(4, 4, 3, seed=2)[0]
+    path = str(tmp_path / "g.g2o")
+    D.write_g2o(path, g)
+    r = _run(["--dataset", path, "--num_nodes", "2", "--iters", "1"], cwd=str(tmp_path))
+    assert r.returncode != 0 and "MMPGO_ERR_UNSUPPORTED" in r.stderr

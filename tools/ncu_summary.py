@@ -7,7 +7,7 @@ import csv, io, re, subprocess, sys
 
 
 def short(name):
-    m = re.match(r"void (?:mmpgo::)?(\w+)(<[^>]*>)?", name)
+    m = re.match(r"void (?:mmpgo::)?(?:<?unnamed>::)?(\w+)(<[^>]*>)?", name)
     if not m:
         return name[:60]
     t = (m.group(2) or "").replace("(int)", "").replace("mmpgo::", "")
@@ -19,10 +19,10 @@ def launches(path):
     h = rows[0]
     kn, bs, gs, mv = h.index("Kernel Name"), h.index("Block Size"), h.index("Grid Size"), h.index("Metric Value")
     seq = [(short(r[kn]), r[bs], r[gs], float(r[mv]) / 1e3) for r in rows[1:]]
-    # timed steps = from one k_prox launch to the k_prox launch `n` steps later (bench: 1 warm-up + 3 timed)
+    # one step = from the k_prox launch of one iteration to the k_prox launch of the next (bench.py --steps 2
+    # --warmup 1: the second and third k_prox; later k_prox launches belong to the profile passes)
     prox = [i for i, s in enumerate(seq) if s[0].startswith("k_prox")]
-    # k_prox also runs once in the profile pass; the steps are the first launches
-    lo, hi, nsteps = prox[1], prox[3], 2
+    lo, hi, nsteps = prox[1], prox[2], 1
     agg = {}
     for name, b, g, us in seq[lo:hi]:
         a = agg.setdefault((name, b, g), [0, 0.0])
@@ -33,8 +33,8 @@ def launches(path):
     for (name, b, g), (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("| `%s` | %s | %s | %.1f | %.3f | %.3f | %.1f |" % (name, b, g, n / nsteps, us / nsteps / 1e3, us / tot, us / n))
     print("\nSum of kernel time: %.2f ms/step under ncu (%d launches/step)." % (tot / nsteps / 1e3, sum(v[0] for v in agg.values()) / nsteps))
-    ts = sum(v[1] for k, v in agg.items() if k[0].startswith("k_tsolve"))
-    print("Share of the translation solve (k_tsolve + resumed tail in k_tsolve_lite): %.3f" % (ts / tot))
+    ts = sum(v[1] for k, v in agg.items() if k[0].startswith("k_tsolve") or k[0].startswith("k_mf_solve"))
+    print("Share of the translation solve (k_mf_solve, or k_tsolve + k_tsolve_lite on the PCG path): %.3f" % (ts / tot))
 
 
 def full(path):
