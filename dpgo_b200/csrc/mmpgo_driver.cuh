@@ -119,7 +119,7 @@ struct Handle {
   std::vector<int> h_mf_perm;
   std::vector<int> mf_stage_jobs;      // per stage (forward stages, then backward): warp jobs, CTA jobs
   int mf_grid = 0;
-  bool mf_dry = false;
+  bool mf_dry = false, mf_level_sync = false, mf_level_sync_auto = true;
   int64_t mf_nnz = 0, mf_entries = 0, mf_tasks = 0;
   int mf_height = 0, mf_supernodes = 0;
   int64_t dense_poses = 0;

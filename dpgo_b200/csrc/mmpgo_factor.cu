@@ -361,6 +361,12 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
       sn.rowoff = (int)ro; sn.boff = (int)bo; sn.uoff = uo;
       sn.nchild = (nf.child0[s] >= 0) + (nf.child1[s] >= 0);
       uoff[s] = uo;
+      MfFactor::Dep dp;
+      std::memset(&dp, 0, sizeof(dp));
+      dp.child0 = nf.child0[s] >= 0 ? base + nf.child0[s] : -1;
+      dp.child1 = nf.child1[s] >= 0 ? base + nf.child1[s] : -1;
+      dp.parent = -1;
+      F.dep.push_back(dp);
       for (int t = 0; t < m; ++t) F.bidx[bo + t] = row_off + nf.bnd[s][t];
       // children's update rows land on rows of this front
       int slot = 0;
@@ -385,6 +391,8 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
       F.height = std::max(F.height, nf.height[s]);
       ro += R; bo += m; uo += m;
     }
+    for (int s = 0; s < ns; ++s)
+      for (int c : {nf.child0[s], nf.child1[s]}) if (c >= 0) F.dep[base + c].parent = base + s;
     mo += nf.M.size(); mto += nf.MT.size();
     row_off += nf.n;
     nf = NodeFactor();     // release the node's copy
@@ -395,6 +403,7 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
   // warp jobs.  Forward: fronts with at most MF_KS columns are cut into jobs of 64 rows (whole front if it has at
   // most 128), wider ones into jobs of 2 MF_SROWS rows summed in slices.  Backward: fronts with at most MF_RS rows
   // are one job, taller ones are cut into jobs of 2 MF_SROWS columns summed in slices.
+  auto mkjob = [](int sn, int r0, int n) { MfJob j; std::memset(&j, 0, sizeof(j)); j.sn = sn; j.r0 = r0; j.n = n; j.wait0 = j.wait1 = -1; return j; };
   for (int dir = 0; dir < 2; ++dir) {
     const std::vector<std::vector<int>> &stages = dir == 0 ? fw : bw;
     F.wstage[dir].assign(1, 0);
@@ -403,16 +412,29 @@ int mf_factor(const std::vector<MfMatrix> &mats, int block, int leaf, bool symbo
         const MfSn &sn = F.sn[s];
         F.max_R = std::max(F.max_R, sn.R);
         if (dir == 0) {
-          if (sn.k > MF_KS) for (int r0 = 0; r0 < sn.R; r0 += 2 * MF_SROWS) F.wjobs[0].push_back({s, r0, std::min(2 * MF_SROWS, sn.R - r0), 0});
-          else if (sn.R <= 128) F.wjobs[0].push_back({s, 0, sn.R, 0});
-          else for (int r0 = 0; r0 < sn.R; r0 += 64) F.wjobs[0].push_back({s, r0, std::min(64, sn.R - r0), 0});
+          if (sn.k > MF_KS) for (int r0 = 0; r0 < sn.R; r0 += 2 * MF_SROWS) F.wjobs[0].push_back(mkjob(s, r0, std::min(2 * MF_SROWS, sn.R - r0)));
+          else if (sn.R <= 128) F.wjobs[0].push_back(mkjob(s, 0, sn.R));
+          else for (int r0 = 0; r0 < sn.R; r0 += 64) F.wjobs[0].push_back(mkjob(s, r0, std::min(64, sn.R - r0)));
         } else {
-          if (sn.R > MF_RS) for (int c0 = 0; c0 < sn.k; c0 += 2 * MF_SROWS) F.wjobs[1].push_back({s, c0, std::min(2 * MF_SROWS, sn.k - c0), 0});
-          else F.wjobs[1].push_back({s, 0, sn.k, 0});
+          if (sn.R > MF_RS) for (int c0 = 0; c0 < sn.k; c0 += 2 * MF_SROWS) F.wjobs[1].push_back(mkjob(s, c0, std::min(2 * MF_SROWS, sn.k - c0)));
+          else F.wjobs[1].push_back(mkjob(s, 0, sn.k));
         }
       }
       F.wstage[dir].push_back((int)F.wjobs[dir].size());
     }
+    for (const MfJob &jb : F.wjobs[dir]) (dir == 0 ? F.dep[jb.sn].nf : F.dep[jb.sn].nb)++;
+  }
+  // what every job waits for: counters of MfDevice::done ([0, nsn) forward, [nsn, 2 nsn) backward) and their targets
+  const int nsn = (int)F.sn.size();
+  for (MfJob &jb : F.wjobs[0]) {
+    const MfFactor::Dep &dp = F.dep[jb.sn];
+    if (dp.child0 >= 0) { jb.wait0 = dp.child0; jb.need0 = F.dep[dp.child0].nf; }
+    if (dp.child1 >= 0) { jb.wait1 = dp.child1; jb.need1 = F.dep[dp.child1].nf; }
+  }
+  for (MfJob &jb : F.wjobs[1]) {
+    const MfFactor::Dep &dp = F.dep[jb.sn];
+    if (dp.parent >= 0) { jb.wait0 = nsn + dp.parent; jb.need0 = F.dep[dp.parent].nb; }
+    else { jb.wait0 = jb.sn; jb.need0 = dp.nf; }           // the root turns around when its forward jobs are done
   }
   return 0;
 }

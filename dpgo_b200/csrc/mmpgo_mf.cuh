@@ -44,7 +44,10 @@ struct MfSn {             // one supernode, 48 bytes
 static_assert(sizeof(MfSn) == 48, "MfSn must be 48 bytes");
 
 // One warp job: rows [r0, r0 + n) of supernode sn in the forward sweep, columns [r0, r0 + n) in the backward sweep.
-struct MfJob { int sn, r0, n, pad; };
+// It may start when the counters wait0 / wait1 (indices into MfDevice::done, -1: none) have reached need0 / need1:
+// forward the finished forward jobs of the two children, backward those of the parent (the root: its own forward jobs).
+struct MfJob { int sn, r0, n, wait0, wait1, need0, need1, pad; };
+static_assert(sizeof(MfJob) == 32, "MfJob must be 32 bytes");
 
 constexpr int MF_THREADS = 512;    // one persistent CTA per SM: 16 warps with up to 128 registers each (measured per solve on the
                                    // 1 M-pose grid: 256 threads 1.29, 384: 1.10, 512: 0.97, 768: 1.16, 1024 (spills): 1.62 ms)
@@ -71,6 +74,10 @@ struct MfFactor {
   // per sweep (0 forward, 1 backward): the warp jobs with their ranges per stage
   std::vector<MfJob> wjobs[2];
   std::vector<int> wstage[2];              // [stage[s], stage[s+1])
+  // dependencies between supernodes: a forward job waits for all forward jobs of the two children, a backward job for
+  // all backward jobs of the parent (the root: for its own forward jobs)
+  struct Dep { int child0, child1, parent, nf, nb, pad[3]; };
+  std::vector<Dep> dep;
   int urows = 0;                       // rows of the u buffer
   int max_R = 0;                       // largest front
   int64_t nnz = 0;                     // sum k(k+1)/2 + k m  (entries of L)
@@ -103,6 +110,9 @@ struct MfDevice {
   const int *wstage[2] = {nullptr, nullptr};
   int n_stage[2] = {0, 0};
   double *y = nullptr, *xp = nullptr, *u = nullptr;     // [nrows][D] permuted, [urows][D]
+  const MfFactor::Dep *dep = nullptr;                   // per supernode: children, parent, job counts
+  unsigned *done = nullptr;                             // [2][supernodes] finished forward / backward jobs (zeroed before launch)
+  int n_sn = 0;
   unsigned *barrier = nullptr;                          // grid barrier counter (zeroed before launch)
   unsigned long long *stage_ns = nullptr;               // [n_stage[0] + n_stage[1] + 1] globaltimer of CTA 0 at every stage boundary
   int smem_bytes = 0;
@@ -116,6 +126,8 @@ struct MfSolveArgs {
   int out_stride;
   double sign;
   int dry;                  // measurement: walk the stages and barriers without executing the jobs
+  int level_sync;           // 1: a grid barrier after every level of the separator tree (per-level timing); 0: every job
+                            // waits for the supernodes it depends on only, levels and nodes overlap
 };
 template <int D> int launch_mf_solve(const MfSolveArgs &a, int grid, cudaStream_t s);
 template <int D> int mf_solve_max_grid(int device, int smem_bytes);

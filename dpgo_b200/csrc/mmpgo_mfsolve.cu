@@ -30,6 +30,22 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
   return v;
 }
 
+__device__ __forceinline__ void red_release_u32(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// lane 0 waits until `*ctr` has reached `need` (the jobs this one depends on have published their results); the
+// other lanes follow through the warp barrier.  A wait of seconds means a broken dependency list: trap rather than hang.
+__device__ __forceinline__ void wait_count(const unsigned *ctr, unsigned need) {
+  // back off while waiting: thousands of warps polling the L2 would slow down the ones that work
+  long long spins = 0;
+  unsigned ns = 64;
+  while (ld_acquire_u32(ctr) < need) {
+    __nanosleep(ns);
+    if (ns < 1024) ns *= 2;
+    if (++spins > (1ll << 21)) __trap();
+  }
+}
+
 // all threads of all CTAs; `target` counts arrivals since the launch (the counter is zeroed before it)
 __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
   __syncthreads();
@@ -220,7 +236,6 @@ __device__ __forceinline__ void backward_store(const MfSolveArgs &a, const MfSn 
 template <int D>
 __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn, int r0, int n, double *buf, int lane) {
   const MfDevice &f = a.f;
-  if (a.active && !a.active[sn.node]) return;
   const int k = sn.k, kp = (k + 1) & ~1, Rp = (sn.R + 1) & ~1;
   const double *Mc = f.M + sn.moff;                       // column-major, leading dimension Rp
   double a0[D], a1[D];
@@ -275,7 +290,6 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
 template <int D>
 __device__ __forceinline__ void backward_job(const MfSolveArgs &a, const MfSn &sn, int c0, int n, double *buf, int lane) {
   const MfDevice &f = a.f;
-  if (a.active && !a.active[sn.node]) return;
   const int R = sn.R, Rp = (R + 1) & ~1, kp = (sn.k + 1) & ~1;
   const double *Mr = f.MT + sn.mtoff;                     // row-major, leading dimension kp
   double a0[D], a1[D];
@@ -342,20 +356,36 @@ __global__ void __launch_bounds__(MF_THREADS, 1) k_mf_solve(MfSolveArgs a) {
   for (int dir = 0; dir < 2; ++dir) {
     const MfJob *wj = f.wjobs[dir];
     for (int st = 0; st < f.n_stage[dir]; ++st) {
-      // every warp strides over the stage's job list, the next job record in flight while the current one runs
-      const int w1 = f.wstage[dir][st + 1];
-      int t = f.wstage[dir][st] + gw;
-      MfJob cur = {0, 0, 0, 0};
+      // every warp strides over the job list (ordered by level), the next job record in flight while the current
+      // one runs.  Without level barriers (the default) the loop covers the whole sweep at once and a job waits only
+      // for the supernodes it depends on: levels overlap, and so do the robot nodes.
+      const int w0 = a.level_sync ? f.wstage[dir][st] : f.wstage[dir][0];
+      const int w1 = a.level_sync ? f.wstage[dir][st + 1] : f.wstage[dir][f.n_stage[dir]];
+      unsigned *done = f.done + (size_t)dir * f.n_sn;
+      int t = w0 + gw;
+      MfJob cur = {0, 0, 0, -1, -1, 0, 0, 0};
       if (t < w1) cur = wj[t];
       while (t < w1) {
         const int tn = t + nw;
-        MfJob nxt = {0, 0, 0, 0};
+        MfJob nxt = {0, 0, 0, -1, -1, 0, 0, 0};
         if (tn < w1) nxt = wj[tn];
         const MfSn sn = f.sn[cur.sn];
-        if (a.dry) { t = tn; cur = nxt; continue; }
+        if (a.dry || (a.active && !a.active[sn.node])) { t = tn; cur = nxt; continue; }
+        if (!a.level_sync) {
+          if (lane == 0) {
+            if (cur.wait0 >= 0) wait_count(f.done + cur.wait0, (unsigned)cur.need0);
+            if (cur.wait1 >= 0) wait_count(f.done + cur.wait1, (unsigned)cur.need1);
+          }
+          __syncwarp();
+        }
         if (dir == 0) forward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane); else backward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane);
+        if (!a.level_sync) {
+          __syncwarp();
+          if (lane == 0) red_release_u32(done + cur.sn, 1u);
+        }
         t = tn; cur = nxt;
       }
+      if (!a.level_sync) { mark(); break; }
       if (dir == 0 || st + 1 < f.n_stage[1]) grid_barrier(f.barrier, target);
       mark();
     }
@@ -367,6 +397,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) k_mf_solve(MfSolveArgs a) {
 template <int D> int launch_mf_solve(const MfSolveArgs &a, int grid, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(a.f.barrier, 0, sizeof(unsigned), s);
   if (e != cudaSuccess) return (int)e;
+  if (!a.level_sync && (e = cudaMemsetAsync(a.f.done, 0, sizeof(unsigned) * 2 * (size_t)a.f.n_sn, s)) != cudaSuccess) return (int)e;
   if (a.f.smem_bytes > 48 * 1024) {
     e = cudaFuncSetAttribute(k_mf_solve<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.f.smem_bytes);
     if (e != cudaSuccess) return (int)e;
