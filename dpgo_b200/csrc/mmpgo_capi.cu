@@ -61,13 +61,15 @@ void mmpgo_default_options(mmpgo_options *o) {
   o->translation_solve_max_iters = 4000;
   o->device = 0;
   o->translation_solver = MMPGO_TSOLVE_AUTO;
+  o->rescale = MMPGO_RESCALE_STATIC;        // dist_pgo.cpp:105
+  o->max_rescale_count = 5;                // DPGO_types.h:131
 }
 
 int mmpgo_create(const mmpgo_options *opts, mmpgo_handle *out) {
   if (!opts || !out) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
   if (opts->loss < 0 || opts->loss > 3 || opts->preconditioner < 0 || opts->preconditioner > 2 ||
       opts->algorithm < 0 || opts->algorithm > 1 || opts->scheme < 0 || opts->scheme > 1 ||
-      opts->translation_solver < 0 || opts->translation_solver > 4) {
+      opts->translation_solver < 0 || opts->translation_solver > 4 || opts->rescale < 0 || opts->rescale > 1) {
     mmpgo::set_error("invalid enum value in options");
     return MMPGO_ERR_ARG;
   }
@@ -156,6 +158,7 @@ int mmpgo_get_node_scalars(mmpgo_handle hh, int32_t node, mmpgo_node_scalars *ou
   out->refined = s.refined ? 1 : 0; out->restarts = s.restarts;
   out->tcg_iterations = s.tcg_iterations; out->tnt_iterations = s.tnt_iterations;
   out->n0 = ni.n0; out->n1 = ni.n1; out->m0 = ni.m0; out->m1 = ni.m1;
+  out->reserved = s.rescales;
   return MMPGO_OK;
 }
 

@@ -649,9 +649,37 @@ template <int D> struct Drv {
       std::swap(h->w_cur, h->w_prev);
       ia.w_prev = h->w_prev; ia.w_out = h->w_cur;
     }
+    const bool dyn = h->dynamic;
+    if (dyn) { ia.resc = h->resc; ia.split_g = 1; }
     launch_inter<D>(trivial ? I_TRIVIAL : I_ROBUST, tl, ia, h->stream);
     h->ctr.launches++; h->ctr.inter_passes++;
     RC(reduce_async(h, 0));
+    if (dyn) {
+      // Rescale::Dynamic (DPGOProblem.cpp:301-321, 465-485): the weights just found decide per node whether its
+      // rescale vector is replaced; the history terms above used the old one, g / Dfobj / f below use the new one
+      RC(host_sync(h));
+      Mask resc(A, 0);
+      const double *s0 = slot_host(h, 0);
+      for (int n = 0; n < A; ++n) if (m[n]) {
+        NodeState &st = h->st[n];
+        if (st.rescale_count >= o.max_rescale_count || s0[n * NS + 6] > 0.0) { resc[n] = 1; st.rescale_count = 0; st.rescales++; }
+        else st.rescale_count++;
+      }
+      if (any(resc)) {
+        Tiles tr; RC(make_tiles(h, resc, &tr, h->d_active2));
+        RescaleArgs ra; std::memset(&ra, 0, sizeof(ra));
+        ra.rowptr = h->d_xrowptr; ra.rec = h->d_xrec; ra.w = h->w_cur; ra.resc = h->resc; ra.dintra = h->d_dintra;
+        ra.dinter = h->d_dinter; ra.gdiag = h->d_gdiag; ra.tnv = h->d_tnv; ra.d00 = h->d_d00;
+        ra.ts_rec = h->ts_rec; ra.pose_rec = h->d_pose_rec; ra.xi = o.regularizer;
+        launch_rescale<D>(tr, ra, h->stream);
+        h->ctr.launches++;
+      }
+      GFixArgs ga; std::memset(&ga, 0, sizeof(ga));
+      ga.x = Xk; ga.dinter = h->d_dinter; ga.g = gk; ga.xi = o.regularizer; ga.partials = h->d_partials;
+      launch_gfix<D>(tl, ga, h->stream);
+      h->ctr.launches++;
+      RC(reduce_async(h, 2));
+    }
     // gradient pass: Dfobj = g + G x   (its sums are read back with those of K1: one synchronisation)
     GPassArgs a = gargs(h);
     a.x = Xk; a.g = gk; a.out = Dfk;
@@ -662,6 +690,7 @@ template <int D> struct Drv {
     const double *s = slot_host(h, 0);
     std::vector<double> i0(A), i1(A), i2(A), i3(A), i4(A), i5(A);
     for (int n = 0; n < A; ++n) { i0[n] = s[n*NS]; i1[n] = s[n*NS+1]; i2[n] = s[n*NS+2]; i3[n] = s[n*NS+3]; i4[n] = s[n*NS+4]; i5[n] = s[n*NS+5]; }
+    if (dyn) for (int n = 0; n < A; ++n) i4[n] = slot_host(h, 2)[n * NS + 4];      // x^T D x with the new D (k_gfix)
     s = slot_host(h, 1);
     const double xi = o.regularizer;
     for (int n = 0; n < A; ++n) if (m[n]) {
@@ -1083,6 +1112,21 @@ int driver_initialize(Handle *h, const double *X, int64_t ldx) {
   CK(cudaMemsetAsync(h->tdot_prev, 0, sizeof(double) * (size_t)h->NO * (h->d + 1) * h->d, h->stream));
   for (auto &s : h->st) { s = NodeState(); s.updated = false; }
   h->star_restarts = 0;
+  if (h->dynamic) {
+    // Rescale::Dynamic starts from the all-ones rescale vector (DPGOProblem.cpp:31, 84): rebuild the per-pose
+    // constants with the kernel that will maintain them (w = 0.8 => s = clamp(1.25 w) = 1)
+    std::vector<double> w((size_t)h->n_inter_he, 0.8);
+    CK(cudaMemcpyAsync(h->w_tmp, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice, h->stream));
+    Tiles tl;
+    tl.n_tiles = h->n_tiles; tl.node = h->d_tile_node; tl.start = h->d_tile_start; tl.cnt = h->d_tile_cnt; tl.active = nullptr;
+    RescaleArgs ra; std::memset(&ra, 0, sizeof(ra));
+    ra.rowptr = h->d_xrowptr; ra.rec = h->d_xrec; ra.w = h->w_tmp; ra.resc = h->resc; ra.dintra = h->d_dintra;
+    ra.dinter = h->d_dinter; ra.gdiag = h->d_gdiag; ra.tnv = h->d_tnv; ra.d00 = h->d_d00;
+    ra.ts_rec = h->ts_rec; ra.pose_rec = h->d_pose_rec; ra.xi = h->opt.regularizer;
+    if (h->d == 2) launch_rescale<2>(tl, ra, h->stream); else launch_rescale<3>(tl, ra, h->stream);
+    h->ctr.launches++;
+    CK(cudaStreamSynchronize(h->stream));          // w is a temporary
+  }
   if (h->opt.algorithm == MMPGO_ALG_STAR) {
     double f = 0.0;
     int rc = h->d == 2 ? Drv<2>::edge_objective(h, h->X[h->ik], &f, false)

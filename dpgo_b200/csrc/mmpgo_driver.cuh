@@ -29,6 +29,8 @@ struct NodeState {
   double fobjE = 0.0;
   double gradFnorm = 0.0;
   bool refined = false;
+  int rescale_count = 0;        // Rescale::Dynamic (DPGO_types.h:277)
+  int rescales = 0;
   int restarts = 0, tcg_iterations = 0, tnt_iterations = 0;
 };
 
@@ -133,6 +135,9 @@ struct Handle {
   int tsl_plan_tpc = -1, tsl_stage_bytes = 0, tsl_vec_off = -1, tsl_z_off = -1, tsl_dyn_bytes = 0;   // shared-memory plan for `tpc` tiles per CTA
   // per half-edge
   double *w_cur = nullptr, *w_prev = nullptr, *w_tmp = nullptr;
+  double *resc = nullptr;            // Rescale::Dynamic: rescale s_e of the owning node's majoriser (ones at set_graph)
+  int *d_pose_rec = nullptr;         // own pose -> index of its diagonal entry in the PCG tile records
+  bool dynamic = false;
   // scalars
   double *d_node_scal2 = nullptr;
   double *d_partials = nullptr, *d_node_scal = nullptr, *d_coef = nullptr, *d_gamma = nullptr;

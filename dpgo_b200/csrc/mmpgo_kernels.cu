@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(TILE) k_inter(Tiles tl, InterArgs a) {
   const int p = tl.start[tile] + pl;
   const bool valid = pl < tl.cnt[tile];
   const double gam = (a.gamma && a.xb) ? a.gamma[node] : 0.0;
-  double sc[6] = {0, 0, 0, 0, 0, 0};
+  double sc[7] = {0, 0, 0, 0, 0, 0, 0};
   if (valid) {
     // own pose: z (possibly extrapolated), previous z0, v (= z or z - z0)
     double z[PB], z0[PB], acc[PB];
@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(TILE) k_inter(Tiles tl, InterArgs a) {
         double rho;
         const double w = irls_weight(a.loss, e, a.loss_reg, rho);
         sc[0] += rho;
+        if (a.split_g && w > a.resc[he]) sc[6] += 1.0;          // a rescale is due (DPGOProblem.cpp:305-306)
         if (a.w_out) a.w_out[he] = w;
         if (a.e_out) a.e_out[he] = e;
         // weighted gradient rows of the own endpoint
@@ -592,7 +593,8 @@ __global__ void __launch_bounds__(TILE) k_inter(Tiles tl, InterArgs a) {
 #pragma unroll
           for (int k = D; k < PB; ++k) { nyi += yi[k] * yi[k]; nyj += yj[k] * yj[k]; }
           sc[1] += a.w_prev[he] * dot;
-          sc[2] += qd + kap * nyi + tau * ntj + kap * nyj;
+          const double se = a.resc ? a.resc[he] : 1.0;         // Rescale::Dynamic: Q carries s_e on both endpoint blocks
+          sc[2] += se * (qd + kap * nyi + tau * ntj + kap * nyj);
         }
       }
     }
@@ -642,7 +644,8 @@ __global__ void __launch_bounds__(TILE) k_inter(Tiles tl, InterArgs a) {
       }
 #pragma unroll
       for (int k = 0; k < PB; ++k) {
-        const double dx = 2.0 * dz[k] + a.xi * z[k];
+        // Rescale::Dynamic: D is rebuilt from the weights found here before it is applied (k_gfix)
+        const double dx = a.split_g ? 0.0 : 2.0 * dz[k] + a.xi * z[k];
         a.g[(size_t)p * PB + k] = acc[k] - dx;
         sc[3] += z[k] * acc[k];      // x.DfobjE
         sc[4] += z[k] * dx;          // x^T D x
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(TILE) k_inter(Tiles tl, InterArgs a) {
       (void)ydy;
     }
   }
-  block_reduce_store<6, TILE>(sc, a.partials + (size_t)tile * NS);
+  block_reduce_store<7, TILE>(sc, a.partials + (size_t)tile * NS);
 }
 
 template <int D> void launch_inter(int mode, const Tiles &tl, const InterArgs &a, cudaStream_t s) {
@@ -660,6 +663,109 @@ template <int D> void launch_inter(int mode, const Tiles &tl, const InterArgs &a
 }
 template void launch_inter<2>(int, const Tiles &, const InterArgs &, cudaStream_t);
 template void launch_inter<3>(int, const Tiles &, const InterArgs &, cudaStream_t);
+
+// =============================================================================
+// Rescale::Dynamic.  update_quadratic_mat (DPGOProblem.cpp:751-840) for the nodes whose rescale vector is replaced:
+// s_e = clamp(1.25 omega_e, 0.01, 1) (:309-311), then everything that depends on it, per own pose: the inter-node
+// diagonal sum  Dinter = sum_e s_e M_own,e,  the diagonal block of G,  T, N, V' of the proximal step (0.5 xi on the
+// auxiliary matrices in this builder, DPGO_utils.cpp:3621, 3635) and the diagonal of G00 (the only part of G00 that
+// changes: the PCG translation solve just sees a new diagonal where the reference refactorises).
+// =============================================================================
+template <int D>
+__global__ void __launch_bounds__(TILE) k_rescale(Tiles tl, RescaleArgs a) {
+  constexpr int R = Dim<D>::R, SYM = Dim<D>::SYM, TNV = Dim<D>::TNV;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  if ((int)threadIdx.x >= tl.cnt[tile]) return;
+  const int p = tl.start[tile] + threadIdx.x;
+  double dx[SYM];
+#pragma unroll
+  for (int k = 0; k < SYM; ++k) dx[k] = 0.0;
+  for (int he = a.rowptr[p]; he < a.rowptr[p + 1]; ++he) {
+    const InterRec *r = a.rec + he;
+    const double s = fmax(fmin(1.25 * a.w[he], 1.0), 0.01);
+    a.resc[he] = s;
+    const double tau = r->tau, kap = r->kappa;
+    // own = i: [[tau, tau t^T], [tau t, kappa I + tau t t^T]];  own = j: [[tau, 0], [0, kappa I]]
+    dx[symidx(0, 0)] += s * tau;
+#pragma unroll
+    for (int k = 0; k < D; ++k) dx[symidx(1 + k, 1 + k)] += s * kap;
+    if (r->own_is_i) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        dx[symidx(1 + k, 0)] += s * tau * r->t[k];
+#pragma unroll
+        for (int c = 0; c <= k; ++c) dx[symidx(1 + k, 1 + c)] += s * tau * r->t[k] * r->t[c];
+      }
+    }
+  }
+  double Gm[R * R], Hm[R * R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      const double di = a.dintra[(size_t)p * SYM + symidx(r, c)], dv = dx[symidx(r, c)];
+      Gm[r * R + c] = di + 2.0 * dv + (r == c ? a.xi : 0.0);
+      Hm[r * R + c] = 2.0 * di + 2.0 * dv + (r == c ? 0.5 * a.xi : 0.0);
+    }
+#pragma unroll
+  for (int k = 0; k < SYM; ++k) a.dinter[(size_t)p * SYM + k] = dx[k];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) a.gdiag[(size_t)p * SYM + symidx(r, c)] = Gm[r * R + c];
+  double *c_ = a.tnv + (size_t)p * TNV;
+  const double T = 1.0 / Hm[0];
+  c_[0] = T;
+#pragma unroll
+  for (int k = 0; k < D; ++k) c_[1 + k] = T * Hm[1 + k];
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) c_[1 + D + r * D + c] = Hm[(1 + r) * R + 1 + c] - Hm[(1 + r) * R] * (T * Hm[1 + c]);
+  a.d00[p] = Gm[0];
+  a.ts_rec[a.pose_rec[p]] = Gm[0];
+}
+template <int D> void launch_rescale(const Tiles &tl, const RescaleArgs &a, cudaStream_t s) {
+  k_rescale<D><<<tl.n_tiles, TILE, 0, s>>>(tl, a);
+}
+template void launch_rescale<2>(const Tiles &, const RescaleArgs &, cudaStream_t);
+template void launch_rescale<3>(const Tiles &, const RescaleArgs &, cudaStream_t);
+
+// g = DfobjE_own - D x with D = 2 Dinter + xi (DPGOProblem.cpp:323-327 / :487-488, after the rescale)
+template <int D>
+__global__ void __launch_bounds__(TILE) k_gfix(Tiles tl, GFixArgs a) {
+  constexpr int PB = Dim<D>::PB, SYM = Dim<D>::SYM;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  const int p = tl.start[tile] + threadIdx.x;
+  double sc[5] = {0, 0, 0, 0, 0};
+  if ((int)threadIdx.x < tl.cnt[tile]) {
+    double z[PB];
+#pragma unroll
+    for (int k = 0; k < PB; ++k) z[k] = a.x[(size_t)p * PB + k];
+    const double *dg = a.dinter + (size_t)p * SYM;
+#pragma unroll
+    for (int rr = 0; rr < D + 1; ++rr)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < D + 1; ++cc) s += dg[symidx(rr, cc)] * z[cc * D + k];
+        const double dxv = 2.0 * s + a.xi * z[rr * D + k];
+        a.g[(size_t)p * PB + rr * D + k] -= dxv;
+        sc[4] += z[rr * D + k] * dxv;
+      }
+  }
+  block_reduce_store<5, TILE>(sc, a.partials + (size_t)tile * NS);
+}
+template <int D> void launch_gfix(const Tiles &tl, const GFixArgs &a, cudaStream_t s) {
+  k_gfix<D><<<tl.n_tiles, TILE, 0, s>>>(tl, a);
+}
+template void launch_gfix<2>(const Tiles &, const GFixArgs &, cudaStream_t);
+template void launch_gfix<3>(const Tiles &, const GFixArgs &, cudaStream_t);
 
 // Tile <-> registers through shared memory: the CTA reads / writes the tile's pose blocks as one
 // contiguous run of doubles (coalesced), every thread then picks up / deposits its own pose.

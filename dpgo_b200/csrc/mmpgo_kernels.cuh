@@ -88,6 +88,29 @@ struct InterArgs {
   double *g;                  // [NO] pose blocks: g
   double *yex;                // extrapolated own poses (may be null)
   double *partials;
+  // Rescale::Dynamic (null / 0 otherwise)
+  const double *resc;         // per half-edge rescale s_e of the node's majoriser: weighs the Q history term
+  int split_g;                // 1: write g = DfobjE_own only and count omega_e > s_e in slot 6; D x follows in k_gfix
+};
+
+// ---- Rescale::Dynamic: per-pose constants from the rescale vector (update_quadratic_mat, DPGOProblem.cpp:751-840) ----
+struct RescaleArgs {
+  const int *rowptr;          // inter half-edges per own pose
+  const InterRec *rec;
+  const double *w;            // IRLS weights of the last evaluate_E per half-edge
+  double *resc;               // out: s_e = clamp(1.25 w_e, 0.01, 1)
+  const double *dintra;       // [NO][SYM]
+  double *dinter, *gdiag, *tnv, *d00;
+  double *ts_rec;             // PCG tile records; pose_rec[p] = index of the pose's diagonal entry
+  const int *pose_rec;
+  double xi;
+};
+struct GFixArgs {
+  const double *x;            // Z_k own rows
+  const double *dinter;
+  double *g;                  // in: DfobjE_own, out: g = DfobjE_own - D x
+  double xi;
+  double *partials;           // slot 4: x^T D x
 };
 
 // ---- K3: fused extrapolation + proximal + polar projection -------------------
@@ -197,6 +220,8 @@ static_assert(sizeof(EdgeRec) == 128, "EdgeRec must be 128 bytes");
 template <int D> void launch_gpass(int mode, const Tiles &tl, const GPassArgs &a, cudaStream_t s);
 template <int D> void launch_inter(int mode, const Tiles &tl, const InterArgs &a, cudaStream_t s);
 template <int D> void launch_prox(const Tiles &tl, const ProxArgs &a, cudaStream_t s);
+template <int D> void launch_rescale(const Tiles &tl, const RescaleArgs &a, cudaStream_t s);
+template <int D> void launch_gfix(const Tiles &tl, const GFixArgs &a, cudaStream_t s);
 template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cudaStream_t s);
 void launch_reduce(int num_nodes, const int *node_tile_begin, const int *node_tile_end,
                    const double *partials, double *node_scal, cudaStream_t s);

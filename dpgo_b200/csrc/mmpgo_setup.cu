@@ -169,6 +169,17 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     return MMPGO_ERR_ARG;
   }
   if (h->graph_set) { set_error("graph already set"); return MMPGO_ERR_STATE; }
+  // Rescale::Dynamic (robust losses; DPGOProblem.cpp:40-86): G00 changes with the weights, on its diagonal only --
+  // no factor or dense inverse is kept, every node runs the PCG translation solve
+  h->dynamic = h->opt.rescale == MMPGO_RESCALE_DYNAMIC && h->opt.loss != MMPGO_LOSS_NONE;
+  if (h->dynamic) {
+    if (h->opt.translation_solver == MMPGO_TSOLVE_DIRECT) {
+      set_error("Rescale::Dynamic changes G00 every few iterations: translation_solver = DIRECT is not available");
+      return MMPGO_ERR_UNSUPPORTED;
+    }
+    if (h->opt.translation_solver == MMPGO_TSOLVE_AUTO) h->opt.translation_solver = MMPGO_TSOLVE_PCG;
+    h->opt.dense_solve_max_n = 0;
+  }
   h->d = d; h->N = N; h->num_nodes = num_nodes; h->node_begin = nb; h->node_end = ne; h->A = ne - nb;
   const int A = h->A, Rr = d + 1, PB = (d + 1) * d, BB = Rr * Rr, SYM = Rr * (Rr + 1) / 2, TNV = 1 + d + d * d;
   const Partition part(N, num_nodes);
@@ -317,7 +328,8 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     for (int r = 0; r < Rr; ++r) for (int c = 0; c < Rr; ++c) {
       const double di = dintra[(size_t)p * SYM + symi(r, c)], dx = dinter[(size_t)p * SYM + symi(r, c)];
       Gm[r * Rr + c] = di + 2.0 * dx + (r == c ? xi : 0.0);          // :2212-2243
-      Hm[r * Rr + c] = 2.0 * di + 2.0 * dx + (r == c ? 1.5 * xi : 0.0); // :1679-1755, 2038-2096
+      // :1679-1755, 2038-2096; the Dynamic builder carries 0.5 xi on the auxiliary matrices (:3621, :3635)
+      Hm[r * Rr + c] = 2.0 * di + 2.0 * dx + (r == c ? (h->dynamic ? 0.5 : 1.5) * xi : 0.0);
     }
     for (int r = 0; r < Rr; ++r) for (int c = 0; c <= r; ++c) gdiag[(size_t)p * SYM + symi(r, c)] = Gm[r * Rr + c];
     double *c_ = &tnv[(size_t)p * TNV];
@@ -618,6 +630,14 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
   }
   double **wv[] = {&h->w_cur, &h->w_prev, &h->w_tmp};
   for (auto q : wv) if ((rc = dalloc(h, q, (size_t)nxe))) return rc;
+  if (h->dynamic) {
+    std::vector<double> ones((size_t)nxe, 1.0);                  // DiagReScale_.setOnes (DPGOProblem.cpp:31)
+    if ((rc = upload(h, &h->resc, ones))) return rc;
+    std::vector<int> pose_rec(NO, 0);
+    for (int c = 0; c < h->n_ctiles; ++c)
+      for (int k = 0; k < ct_cnt[c]; ++k) pose_rec[ct_start[c] + k] = (int)((size_t)c * RL + 3 * CTILE * d + k);
+    if ((rc = upload(h, &h->d_pose_rec, pose_rec))) return rc;
+  }
   if ((rc = dalloc(h, &h->d_partials, (size_t)h->n_tiles * NS))) return rc;
   if ((rc = dalloc(h, &h->d_node_scal, (size_t)A * NS))) return rc;
   if ((rc = dalloc(h, &h->d_node_scal2, (size_t)A * NS))) return rc;

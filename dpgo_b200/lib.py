@@ -39,7 +39,8 @@ class Options(C.Structure):
         ("dense_solve_max_n", C.c_int32),
         ("translation_solve_tol", C.c_double),
         ("translation_solve_max_iters", C.c_int32), ("device", C.c_int32),
-        ("translation_solver", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("translation_solver", C.c_int32), ("rescale", C.c_int32), ("max_rescale_count", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -73,6 +74,7 @@ LOSS = {"trivial": 0, "none": 0, "huber": 1, "gm": 2, "geman-mcclure": 2, "welsc
 PRECON = {"None": 0, "Jacobi": 1, "BlockJacobi": 2}
 ALGORITHM = {"hash": 0, "star": 1}
 SCHEME = {"MM": 0, "AMM": 1}
+RESCALE = {"Static": 0, "Dynamic": 1}
 TSOLVER = {"auto": 0, "pcg": 1, "pcg_ring": 2, "pcg_lite": 3, "direct": 4}
 
 # every symbol include/mmpgo.h declares, with its signature

@@ -38,6 +38,8 @@ class Options:
                 self.c.scheme = L.SCHEME[v]
             elif k == "translation_solver":
                 self.c.translation_solver = L.TSOLVER[v]
+            elif k == "rescale":
+                self.c.rescale = L.RESCALE[v]
             elif k in ("eta", "max_soft_restart_hits"):
                 arr = getattr(self.c, k)
                 arr[0], arr[1] = v

@@ -50,6 +50,11 @@ enum mmpgo_preconditioner { MMPGO_PRECON_NONE = 0, MMPGO_PRECON_JACOBI = 1,
  * budget (thick 3-D nodes), then PCG. */
 enum mmpgo_translation_solver { MMPGO_TSOLVE_AUTO = 0, MMPGO_TSOLVE_PCG = 1, MMPGO_TSOLVE_PCG_RING = 2,
                                 MMPGO_TSOLVE_PCG_LITE = 3, MMPGO_TSOLVE_DIRECT = 4 };
+/* DPGO::Rescale.  DYNAMIC (robust losses): every update() may replace the per-measurement rescale vector of a node by
+ * clamp(1.25 omega, 0.01, 1) (DPGOProblem.cpp:301-321, 465-485) and rebuild the majoriser's inter-node diagonal
+ * blocks, D, Q, T, N, V' from it (update_quadratic_mat, :751-840); G00 changes on its diagonal only, so the
+ * translation solve runs the PCG kernels (the reference refactorises with CHOLMOD, :315). */
+enum mmpgo_rescale { MMPGO_RESCALE_STATIC = 0, MMPGO_RESCALE_DYNAMIC = 1 };
 /* Which driver class the handle emulates. */
 enum mmpgo_algorithm { MMPGO_ALG_HASH = 0,   /* DPGOHash: AMM-PGO# / MM-PGO */
                        MMPGO_ALG_STAR = 1 }; /* DPGOStar: AMM-PGO*          */
@@ -83,7 +88,10 @@ typedef struct mmpgo_options {
   int32_t translation_solve_max_iters;
   int32_t device;                /* CUDA device ordinal */
   int32_t translation_solver;    /* mmpgo_translation_solver; nodes above dense_solve_max_n */
-  int32_t reserved[6];
+  int32_t rescale;               /* mmpgo_rescale: DPGO::Rescale (DPGO_types.h:42-46, Options::rescale :128); dist_pgo
+                                    pins Static (dist_pgo.cpp:105), which is the default here */
+  int32_t max_rescale_count;     /* 5 (DPGO_types.h:131) */
+  int32_t reserved[4];
 } mmpgo_options;
 
 /* DPGOResult scalars a caller of results() reads (DPGO_types.h:204-322). */
@@ -92,7 +100,8 @@ typedef struct mmpgo_node_scalars {
   int32_t iters, soft_restart_hits[2], num_oscillations;
   int32_t refined, restarts, tcg_iterations, tnt_iterations;
   int32_t n0, n1, m0, m1;
-  int32_t translation_solve_iters, reserved;
+  int32_t translation_solve_iters;
+  int32_t reserved;              /* Rescale::Dynamic: how often the node's rescale vector was replaced */
 } mmpgo_node_scalars;
 
 /* Kernel launch / byte accounting used by bench.py (gpu_launches, roofline). */

@@ -162,9 +162,14 @@ def _B_rows(meas, I, J, ncols):
     return sp.coo_matrix((v, (r, c)), shape=((d + 1) * m, ncols)).tocsr()
 
 
-def build_data_matrices(info, xi, quadratic):
+def build_data_matrices(info, xi, quadratic, rescale=None, dynamic=False):
     """quadratic=True : simplify_quadratic_data_matrix (DPGO_utils.cpp:1398-2288)
     quadratic=False: simplify_regular_data_matrix, Static (:2290-2967).
+    dynamic=True (robust losses only): the Rescale::Dynamic builder (:2969-3903) evaluated at the per-measurement
+    rescale vector `rescale` (DiagReScale_, one entry per inter-node measurement; ones at construction,
+    DPGOProblem.cpp:31, 84): the inter-node blocks E s / F s that update_quadratic_mat (DPGOProblem.cpp:751-840)
+    adds to M, D0, Q0, T0, N0, V0 are the Static blocks scaled by s_e (own endpoint: :3518-3550 E; neighbour
+    endpoint: F, enters Q only), and the auxiliary matrices carry 0.5 xi instead of 1.5 xi (:3621, :3635).
     Returns a dict of scipy CSR matrices named as in the reference."""
     d, (n0, n1) = info.d, info.n
     a = info.node
@@ -194,6 +199,11 @@ def build_data_matrices(info, xi, quadratic):
     Mji = np.transpose(Mij, (0, 2, 1))
     own_i = inter.i_node == a
     own_j = ~own_i
+    if dynamic:
+        assert not quadratic
+        sc = np.ones(len(inter)) if rescale is None else np.asarray(rescale, dtype=float)
+        Mii = Mii * sc[:, None, None]
+        Mjj = Mjj * sc[:, None, None]
     if quadratic:
         for T_, sd, so in ((Q, -0.5, 0.5), (P0, 0.5, -0.5)):
             # Q = 1/2 M_e - blockdiag ; P0 = blockdiag - 1/2 M_e
@@ -212,7 +222,7 @@ def build_data_matrices(info, xi, quadratic):
 
     # ---- regulariser xi (:2212-2243 / :2906-2927)
     own_rows = np.arange(NX)
-    G.diag(own_rows, xi); D.diag(own_rows, xi); H.diag(own_rows, 1.5 * xi)
+    G.diag(own_rows, xi); D.diag(own_rows, xi); H.diag(own_rows, (0.5 if dynamic else 1.5) * xi)
     if quadratic:
         S.diag(own_rows, -xi); Q.diag(own_rows, -xi)
         P.diag(own_rows, xi); P0.diag(own_rows, xi)

@@ -35,6 +35,8 @@ class Options:
         self.max_oscillations = 12
         self.loss = "trivial"          # trivial | huber | gm | welsch
         self.loss_reg = 0.25
+        self.rescale = "Static"        # Static (what dist_pgo sets, dist_pgo.cpp:105) | Dynamic (DPGO_types.h:128)
+        self.max_rescale_count = 5     # DPGO_types.h:131
         self.grad_norm_tol = 1e-3
         self.rel_func_decrease_tol = 1e-6
         self.stepsize_tol = 1e-4
@@ -87,7 +89,10 @@ class DPGOProblem:
         self.n = info.n
         self.m = info.m
         self.quadratic = opts.loss == "trivial"     # SIMPLE == 1
-        mats = dm.build_data_matrices(info, opts.regularizer, self.quadratic)
+        self.dynamic = (opts.rescale == "Dynamic") and not self.quadratic
+        self.DiagReScale = np.ones(self.m[1])                    # DPGOProblem.cpp:31
+        mats = dm.build_data_matrices(info, opts.regularizer, self.quadratic,
+                                      self.DiagReScale if self.dynamic else None, self.dynamic)
         self.__dict__.update(mats)
         n0 = self.n[0]
         self.size0 = (d + 1) * n0
@@ -127,6 +132,65 @@ class DPGOProblem:
                                       options=dict(SymmetricMode=True))
         elif self.precon_kind != "None":
             raise ValueError(self.precon_kind)
+
+    # ---- Rescale::Dynamic -------------------------------------------------
+    MAX_RESCALE, MIN_RESCALE = 1.0, 0.01                         # DPGOProblem.h:17-18
+
+    def update_quadratic_mat(self, DiagReScale):
+        """DPGOProblem.cpp:751-840 + L_.factorize (:315, :479): the majoriser G, D, Q and the auxiliary T, N, V at
+        the new rescale vector.  (The preconditioner is NOT refreshed, as in the reference.)"""
+        self.DiagReScale = DiagReScale
+        mats = dm.build_data_matrices(self.info, self.opts.regularizer, False, DiagReScale, True)
+        for k in ("G", "D", "Q", "H", "G00", "G01", "G10", "G11", "T", "N", "V"):
+            setattr(self, k, mats[k])
+        self.L = spla.splu(sp.csc_matrix(self.G00), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0,
+                           options=dict(SymmetricMode=True))
+
+    def _maybe_rescale(self, w, rescale_count, max_rescale_count):
+        """DPGOProblem.cpp:301-321 / :465-485.  Returns the new rescale_count."""
+        rescaled = (rescale_count >= max_rescale_count) or bool(np.any(w > self.DiagReScale))
+        if rescaled:
+            self.update_quadratic_mat(np.clip(1.25 * w, self.MIN_RESCALE, self.MAX_RESCALE))
+            return 0
+        return rescale_count + 1
+
+    def evaluate_g_and_f0_rescale(self, Z, rescale_count, max_rescale_count):
+        """DPGOProblem.cpp:289-358 -> (g, f0, Dfobj, fobj, DfobjE, fobjE, rescale_count)."""
+        s0 = self.size0
+        w, DfobjE, fobjE = self.evaluate_E(Z)
+        if self.dynamic:
+            rescale_count = self._maybe_rescale(w, rescale_count, max_rescale_count)
+        X = Z[:s0]
+        g = DfobjE[:s0].copy()
+        temp = self.D @ X
+        g -= temp
+        temp = 0.5 * temp - DfobjE[:s0]
+        f0 = 0.5 * fobjE + _tr(X, temp)
+        temp = self.G @ X
+        Dfobj = g + temp
+        temp = 0.5 * temp + g
+        fobj = f0 + _tr(X, temp)
+        return g, f0, Dfobj, fobj, DfobjE, fobjE, rescale_count
+
+    def evaluate_g_and_f_rescale(self, Z, Z0, G, DfobjE0, fobjE0, rescale_count, max_rescale_count):
+        """DPGOProblem.cpp:426-514 (robust branch) -> (g, f, Dfobj, fobj, DfobjE, fobjE, rescale_count).  The
+        history term uses Q BEFORE the rescale, g / Dfobj / f use D and G AFTER it."""
+        s0 = self.size0
+        X = Z[:s0]
+        Y = Z - Z0
+        temp = DfobjE0 + 0.5 * (self.Q @ Y)
+        fobj = G - 0.5 * fobjE0
+        fobj -= 0.5 * _tr(Y, temp)
+        w, DfobjE, fobjE = self.evaluate_E(Z)
+        fobj += 0.5 * fobjE
+        if self.dynamic:
+            rescale_count = self._maybe_rescale(w, rescale_count, max_rescale_count)
+        g = DfobjE[:s0] - self.D @ X
+        temp = self.G @ X
+        Dfobj = g + temp
+        temp = 0.5 * temp + g
+        f = fobj - _tr(X, temp)
+        return g, f, Dfobj, fobj, DfobjE, fobjE, rescale_count
 
     # ---- geometry -------------------------------------------------------
     def recover_translations(self, R, g):
@@ -291,6 +355,7 @@ class NodeState:
         self.g_prev = None
         self.Dfobj_prev = None
         self.tcg_iters = 0
+        self.rescale_count = 0           # DPGO_types.h:277
         self.n_restarts = 0
         self.last_refined = False
 
@@ -374,12 +439,19 @@ class DPGOHash:
             else:
                 g, f, fobj = p.evaluate_none_g_and_f(X_it, st.X_cur, st.Gk)
             Dfobj = None
-        else:
+        elif o.rescale == "Static":
             if it == 0:
                 g, f, Dfobj, fobj, st.DfobjE, st.fobjE = p.evaluate_g_and_f0(X_it)
             else:
                 g, f, Dfobj, fobj, st.DfobjE, st.fobjE = p.evaluate_g_and_f(
                     X_it, st.X_cur, st.Gk, st.DfobjE, st.fobjE)
+        else:                                                   # DPGOHash.cpp:131-143
+            if it == 0:
+                g, f, Dfobj, fobj, st.DfobjE, st.fobjE, st.rescale_count = p.evaluate_g_and_f0_rescale(
+                    X_it, st.rescale_count, o.max_rescale_count)
+            else:
+                g, f, Dfobj, fobj, st.DfobjE, st.fobjE, st.rescale_count = p.evaluate_g_and_f_rescale(
+                    X_it, st.X_cur, st.Gk, st.DfobjE, st.fobjE, st.rescale_count, o.max_rescale_count)
         if it == 0:
             st.Fk = [fobj, fobj]
             st.Gk = fobj
@@ -719,8 +791,11 @@ class DPGOStar:
             g, f = p.evaluate_none_g_and_f0(X_it)
             fobj = p.evaluate_G(st.Xak, g, f)
             Dfobj = g + p.G @ st.Xak
-        else:
+        elif self.opts.rescale == "Static":
             g, f, Dfobj, fobj, st.DfobjE, st.fobjE = p.evaluate_g_and_f0(X_it)
+        else:                                                   # DPGOStar.cpp:350-355
+            g, f, Dfobj, fobj, st.DfobjE, st.fobjE, st.rescale_count = p.evaluate_g_and_f0_rescale(
+                X_it, st.rescale_count, self.opts.max_rescale_count)
         st.Gk = fobj
         st.gradF = p.full_tangent_space_projection(st.Xak, Dfobj)
         st.gradFnorm = float(np.linalg.norm(st.gradF))

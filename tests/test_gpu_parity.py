@@ -482,3 +482,44 @@ def test_direct_solve_bitwise_equals_host_restatement():
                                          L.dptr(b), L.dptr(x), None))
     t = drv.translation_solve(b)
     assert np.array_equal(t, -x), np.abs(t + x).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# Rescale::Dynamic (DPGOProblem.cpp:289-358, 426-514, 751-840)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("loss", ["huber", "gm", "welsch"])
+@pytest.mark.parametrize("alg", ["hash", "star"])
+def test_dynamic_rescale_parity(alg, loss):
+    """The per-measurement rescale vector clamp(1.25 omega, 0.01, 1) replaces the unit weights of the majoriser's
+    inter-node blocks every time a weight outgrows it or five updates have passed; 25 iterations cover several
+    replacements on a graph with 20 % outlier loop closures."""
+    g, _, X0 = D.city2d(14, 12, outlier_fraction=0.2, seed=9)
+    out = parity.run_both(g, 4, X0, 25, loss=loss, algorithm=alg, rescale="Dynamic")
+    _check(out, 2)
+    assert max(out["drv"].node_scalars(a).reserved for a in range(4)) >= 3        # rescales happened
+    # and it is a different algorithm than Static: the traces part once the first rescale has happened
+    ref = parity.run_both(g, 4, X0, 25, loss=loss, algorithm=alg)
+    assert np.abs(out["fobj_gpu"].sum(axis=1) - ref["fobj_gpu"].sum(axis=1)).max() > 1e-6 * out["fobj_gpu"].sum(axis=1)[0]
+
+
+def test_dynamic_rescale_se3_reinitialize_and_sharded():
+    """SE(3), re-initialisation of a handle that has rescaled (the all-ones vector comes back), and a sharded run."""
+    from inproc_world import InProcWorld
+    g, _, X0 = D.grid3d(8, 8, 6, seed=7)
+    out = parity.run_both(g, 4, X0, 14, loss="welsch", algorithm="hash", rescale="Dynamic")
+    _check(out, 3)
+    drv = out["drv"]
+    X1 = drv.X()
+    assert drv.initialize(X0) == 0 and drv.update() == 0
+    for _ in range(14):
+        assert drv.iterate() == 0 and drv.communicate() == 0 and drv.update() == 0
+    assert np.array_equal(drv.X(), X1)
+    world = InProcWorld(g, 4, 2, "hash", loss="welsch", rescale="Dynamic")
+    trace, X = world.run(X0, 14)
+    assert np.array_equal(X, X1)
+
+
+def test_dynamic_rescale_refuses_a_static_factor():
+    g, _, _ = D.grid3d(6, 6, 6, seed=1)
+    with pytest.raises(D.MmpgoError):
+        D.DPGOHash(g, 4, D.Options(loss="huber", rescale="Dynamic", translation_solver="direct"))

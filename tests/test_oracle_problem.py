@@ -165,3 +165,35 @@ def test_preconditioner_changes_the_trajectory_not_the_limit():
     a, b = out["BlockJacobi"], out["RegularizedCholesky"]
     assert abs(a[-1] - b[-1]) <= 1e-4 * abs(b[-1])            # same limit ...
     assert np.abs(a - b).max() > 1e-8 * abs(b[0])             # ... by different roads
+
+
+def test_dynamic_rescale_restatement():
+    """Rescale::Dynamic (DPGO_utils.cpp:2969-3903, DPGOProblem.cpp:751-840): at the all-ones rescale vector the
+    majoriser equals the Static one (the auxiliary matrices differ by the xi coefficient only); scaling the vector
+    scales exactly the inter-node diagonal blocks; the run rescales after max_rescale_count updates and still descends."""
+    import numpy as np
+    import dpgo_b200 as D
+    from oracle import data_matrix as dm, dist_pgo as odist, dpgo as odpgo, g2o as og2o
+    from parity import to_measurements
+    g, _, X0 = D.city2d(10, 8, outlier_fraction=0.2, seed=3)
+    meas = to_measurements(g)
+    per_node, g_index, part = og2o.partition(g.num_poses, 3, meas)
+    info = dm.generate_data_info(1, per_node[1])
+    st = dm.build_data_matrices(info, 1e-11, False)
+    dy = dm.build_data_matrices(info, 1e-11, False, np.ones(info.m[1]), True)
+    for k in ("G", "D", "Q", "G00", "G01", "G11"):
+        assert abs(st[k] - dy[k]).max() == 0.0
+    assert abs(st["V"] - dy["V"]).max() < 1e-9 and abs(st["T"] - dy["T"]).max() < 1e-9
+    s = np.random.default_rng(0).uniform(0.01, 1.0, info.m[1])
+    ds = dm.build_data_matrices(info, 1e-11, False, s, True)
+    # D(s) - xi I = sum_e s_e (2 x own diagonal block): linear in s
+    half = dm.build_data_matrices(info, 1e-11, False, 0.5 * s, True)
+    xiI = 1e-11 * np.eye(ds["D"].shape[0])
+    assert np.abs((ds["D"].toarray() - xiI) - 2 * (half["D"].toarray() - xiI)).max() < 1e-9
+    assert abs(ds["G"] - ds["D"] - (st["G"] - st["D"])).max() < 1e-9        # the intra-node part does not move
+    a = odist.run(meas, g.num_poses, 3, odpgo.Options(loss="gm", preconditioner="BlockJacobi", rescale="Dynamic"), X0, 12, "hash")
+    b = odist.run(meas, g.num_poses, 3, odpgo.Options(loss="gm", preconditioner="BlockJacobi"), X0, 12, "hash")
+    ta, tb = np.array(a["trace"])[:, 0], np.array(b["trace"])[:, 0]
+    assert np.allclose(ta[:5], tb[:5], rtol=1e-12)       # the first rescale comes after max_rescale_count = 5 updates
+    assert abs(ta[-1] - tb[-1]) > 1e-9 * tb[-1] and ta[-1] < ta[0]
+    assert all(h.st.rescale_count <= 5 for h in a["hashes"])
