@@ -159,6 +159,7 @@ int mmpgo_get_node_scalars(mmpgo_handle hh, int32_t node, mmpgo_node_scalars *ou
   out->tcg_iterations = s.tcg_iterations; out->tnt_iterations = s.tnt_iterations;
   out->n0 = ni.n0; out->n1 = ni.n1; out->m0 = ni.m0; out->m1 = ni.m1;
   out->reserved = s.rescales;
+  out->translation_solve_iters = h->h_ts_stats ? (int32_t)h->h_ts_stats[3] : 0;
   return MMPGO_OK;
 }
 

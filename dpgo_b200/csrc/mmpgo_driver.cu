@@ -296,6 +296,7 @@ template <int D> struct Drv {
         CK((cudaError_t)launch_tsolve_lite<D>(ta, (h->n_ctiles + tpc - 1) / tpc, h->stream));
         h->ctr.launches++;
         h->ctr.reserved[1]++;                                 // solves served by k_tsolve_lite
+        CK(cudaMemcpyAsync(h->h_ts_stats, h->d_ts_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         return 0;
       }
       int grid = std::max(1, std::min(std::min(h->ts_max_grid, 1024), h->n_ctiles));
@@ -322,6 +323,7 @@ template <int D> struct Drv {
         CK((cudaError_t)launch_tsolve_lite<D>(ta, lgrid, h->stream));
         h->ctr.launches++;
       }
+      CK(cudaMemcpyAsync(h->h_ts_stats, h->d_ts_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     }
     return 0;
   }
@@ -1140,13 +1142,30 @@ int driver_initialize(Handle *h, const double *X, int64_t ldx) {
   return 0;
 }
 
+// The reference's L_.solve is exact (CHOLMOD, DPGOProblem.cpp:140, 568); a PCG solve that stops on
+// translation_solve_max_iters above translation_solve_tol is a deviation and is reported, not hidden:
+// the first driver call that observes the device-side count (it travels with every PCG launch and is
+// visible after the call's next host synchronisation; update() always ends with one) fails.
+static int check_pcg(Handle *h) {
+  if (!h->h_ts_stats || h->h_ts_stats[2] <= h->ts_unconv_seen) return 0;
+  const unsigned long long n = h->h_ts_stats[2] - h->ts_unconv_seen;
+  h->ts_unconv_seen = h->h_ts_stats[2];
+  char buf[256];
+  std::snprintf(buf, sizeof(buf), "translation solve: %llu node solve(s) stopped at translation_solve_max_iters = %d "
+                "above translation_solve_tol = %g (raise the limit or use the direct solver)", n,
+                h->opt.translation_solve_max_iters, h->opt.translation_solve_tol);
+  set_error(buf);
+  return MMPGO_ERR_NOT_CONVERGED;
+}
 int driver_update(Handle *h) {
   if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
-  return h->d == 2 ? Drv<2>::update(h) : Drv<3>::update(h);
+  const int rc = h->d == 2 ? Drv<2>::update(h) : Drv<3>::update(h);
+  return rc ? rc : check_pcg(h);
 }
 int driver_iterate(Handle *h) {
   if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
-  return h->d == 2 ? Drv<2>::iterate(h) : Drv<3>::iterate(h);
+  const int rc = h->d == 2 ? Drv<2>::iterate(h) : Drv<3>::iterate(h);
+  return rc ? rc : check_pcg(h);
 }
 int driver_communicate(Handle *h) {
   if (!h->initialized) { set_error("initialize first"); return MMPGO_ERR_STATE; }
@@ -1271,7 +1290,8 @@ template <int D> static int translation_solve_t(Handle *h, const double *rhs, do
 }
 int driver_translation_solve(Handle *h, const double *rhs, double *t) {
   if (!h->graph_set) { set_error("set_graph first"); return MMPGO_ERR_STATE; }
-  return h->d == 2 ? translation_solve_t<2>(h, rhs, t) : translation_solve_t<3>(h, rhs, t);
+  const int rc = h->d == 2 ? translation_solve_t<2>(h, rhs, t) : translation_solve_t<3>(h, rhs, t);
+  return rc ? rc : check_pcg(h);     // the solve above ended with a host synchronisation
 }
 
 // Times `reps` back-to-back launches of one hot kernel on the handle's stream with CUDA
@@ -1346,16 +1366,22 @@ int driver_profile_pass(Handle *h, int kind, int reps, float *ms_avg) {
 // reserved[0] = pose-iterations, the unit of its byte accounting)
 int driver_sync_counters(Handle *h) {
   if (!h->graph_set) return 0;
-  unsigned long long st[2] = {0, 0};
+  if (!h->d_ts_stats) return 0;
+  unsigned long long st[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(st, h->d_ts_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->ctr.solve_iters = (int64_t)st[0];
   h->ctr.reserved[0] = (int64_t)st[1];
+  h->ctr.reserved[3] = (int64_t)st[2];
+  h->ctr.reserved[4] = (int64_t)st[3];
   return 0;
 }
 int driver_reset_solve_stats(Handle *h) {
-  if (!h->graph_set) return 0;
-  CK(cudaMemsetAsync(h->d_ts_stats, 0, 2 * sizeof(unsigned long long), h->stream));
+  if (!h->graph_set || !h->d_ts_stats) return 0;
+  CK(cudaMemsetAsync(h->d_ts_stats, 0, 4 * sizeof(unsigned long long), h->stream));
+  CK(cudaStreamSynchronize(h->stream));             // no PCG launch's copy of the old counts is in flight any more
+  std::memset(h->h_ts_stats, 0, 4 * sizeof(unsigned long long));
+  h->ts_unconv_seen = 0;
   return 0;
 }
 

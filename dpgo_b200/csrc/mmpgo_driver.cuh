@@ -106,7 +106,9 @@ struct Handle {
   int n_ctiles = 0;
   double *ts_rec = nullptr, *ts_z = nullptr, *ts_z_base = nullptr;
   double *ts_partials = nullptr, *ts_nstate = nullptr;
-  unsigned long long *d_ts_stats = nullptr;
+  unsigned long long *d_ts_stats = nullptr;   // [0] node-iterations [1] pose-iterations [2] node solves stopped on max_iters [3] max iterations of a node
+  unsigned long long *h_ts_stats = nullptr;   // pinned copy, refreshed after every PCG launch
+  unsigned long long ts_unconv_seen = 0;       // h_ts_stats[2] already reported
   int ts_max_grid = 0, ts_grid_override = 0;
   // tile dealing of the copy-ring kernel (host-built table)
   std::vector<int> h_node_ctb, h_node_cte;

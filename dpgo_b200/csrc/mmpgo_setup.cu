@@ -55,6 +55,8 @@ void driver_free(Handle *h) {
   h->h_pinned = nullptr;
   if (h->h_slot) cudaFreeHost(h->h_slot);
   h->h_slot = nullptr;
+  if (h->h_ts_stats) cudaFreeHost(h->h_ts_stats);
+  h->h_ts_stats = nullptr;
 }
 
 // the `index` lambda of read_g2o, DPGO_utils.cpp:147-158
@@ -619,7 +621,10 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     if ((rc = dalloc(h, &h->ts_partials, (size_t)h->n_ctiles * 4 * 2))) return rc;   // two buffers (k_tsolve_lite)
     if ((rc = dalloc(h, &h->ts_nstate, (size_t)A * 8))) return rc;
     if ((rc = dalloc(h, &h->d_ts_sync, (size_t)3 * A + 8))) return rc;
-    if ((rc = dalloc(h, &h->d_ts_stats, (size_t)2))) return rc;
+    if ((rc = dalloc(h, &h->d_ts_stats, (size_t)4))) return rc;
+    CK(cudaMallocHost((void **)&h->h_ts_stats, 4 * sizeof(unsigned long long)));
+    std::memset(h->h_ts_stats, 0, 4 * sizeof(unsigned long long));
+    h->ts_unconv_seen = 0;
     if ((rc = dalloc(h, &h->d_cta_ptr, (size_t)1024 + 1))) return rc;
     if ((rc = dalloc(h, &h->d_cta_tiles, (size_t)h->n_ctiles + 1))) return rc;
     if ((rc = dalloc(h, &h->d_node_parts, (size_t)A))) return rc;

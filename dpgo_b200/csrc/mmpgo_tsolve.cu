@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
             const int round = __shfl_sync(0xffffffffu, rnd, src);
             double *nst = a.nstate + (size_t)nd * 8;
             const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
-            bool done = false, handoff = false;
+            bool done = false, handoff = false, unconv = false;
             if (round == 0) {
               double sm[3];
               node_sum<3>(a.partials, cb, ce, lane, sm);
@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
               __syncwarp();
               if (lane == 0) { nst[3] = sm[0] / rz; nst[0] = sm[0]; nst[5] = sm[2]; nst[4] = it; }
               done = !(sm[2] > a.tol2 * bb) || !(sm[0] > 0.0) || it >= (double)a.max_iters;
+              unconv = (sm[2] > a.tol2 * bb) && (sm[0] > 0.0) && it >= (double)a.max_iters;
               // hand-off: once only a few nodes are still iterating, a phase is bound by this kernel's
               // rendezvous chain (~17 us) and not by HBM; those nodes leave here with their CG state
               // in place and k_tsolve_lite (resume mode, ~4 us per rendezvous, all SMs) finishes them
@@ -294,6 +295,8 @@ __global__ void __launch_bounds__(TS_NGRP * CTILE + 96, 1) k_tsolve(TSolveArgs a
                 const unsigned long long it = (unsigned long long)(round / 2);
                 atomicAdd(a.stats, it);
                 atomicAdd(a.stats + 1, it * (unsigned long long)(__ldg(a.node_off + nd + 1) - __ldg(a.node_off + nd)));
+                if (unconv) atomicAdd(a.stats + 2, 1ull);      // stopped on max_iters above the tolerance
+                atomicMax(a.stats + 3, it);
               }
               st_release(epoch + nd, (round + 1) | (done ? DONE_BIT : 0));
             }
@@ -874,7 +877,7 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
         fence_acq_rel();                                   // acquire: what the other CTAs stored before arriving
       }
       const int cb = __ldg(a.node_ctb + nd), ce = __ldg(a.node_cte + nd);
-      bool done = false;
+      bool done = false, unconv = false;
       if (round == 0) {
         double sm[3];
         node_sum<3>(pbuf, cb, ce, lane, sm);
@@ -892,6 +895,7 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
         __syncwarp();
         if (lane == 0) { sg_coef[s] = sm[0] / rz; sg_rz[s] = sm[0]; sg_it[s] = it; }   // beta for phase A
         done = !(sm[2] > a.tol2 * bb) || !(sm[0] > 0.0) || it >= (double)a.max_iters;
+        unconv = (sm[2] > a.tol2 * bb) && (sm[0] > 0.0) && it >= (double)a.max_iters;
       }
       if (done && lane == 0) {
         sg_state[s] = 1;                                   // publish in the next pass, then retire
@@ -899,6 +903,8 @@ __global__ void __launch_bounds__(NG * CTILE, 1) k_tsolve_lite(TSolveArgs a) {
           const unsigned long long it = (unsigned long long)sg_it[s];   // completed CG iterations (= round / 2)
           atomicAdd(a.stats, it);
           atomicAdd(a.stats + 1, it * (unsigned long long)(__ldg(a.node_off + nd + 1) - __ldg(a.node_off + nd)));
+          if (unconv) atomicAdd(a.stats + 2, 1ull);        // stopped on max_iters above the tolerance
+          atomicMax(a.stats + 3, it);
         }
       }
     }

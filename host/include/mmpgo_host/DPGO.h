@@ -13,10 +13,12 @@
 // [t (N rows); R blocks (dN rows)] x d (dist_pgo.cpp:502-511) -- what Eigen::MatrixXd::data() is.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
 #include <fstream>
+#include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -246,5 +248,149 @@ class DPGOStar : public DPGODriver {
   DPGOStar(const Loaded &l, int num_nodes, const Options &opt)
       : DPGODriver(MMPGO_ALG_STAR, num_nodes, l.d, l.N, l.m, opt, 0, -1) {}
 };
+
+// ---------------------------------------------------------------------------------------------
+// Per-node facade: the reference's call sequence, unchanged.
+//
+// The reference builds ONE driver object per node (`dpgo_hash[alpha] = make_shared<DPGOHash>(alpha, ...)`,
+// dist_pgo.cpp:129-135) and loops over them for every phase (dist_pgo.cpp:446-531):
+//     for alpha: initialize(Xk[alpha]); update();
+//     loop { for alpha: iterate();   for alpha: X <- results().Xk;   for alpha: communicate(dpgo_hash);
+//            for alpha: update(); }
+// PerNode<Driver> keeps those names and that sequence on top of ONE batched driver per GPU.  Every
+// method is a request; the batched call on the device runs when the LAST local node has made the
+// request for the round, so each `for alpha` loop costs one C-ABI call and the objects stay in lock
+// step exactly like the reference's.  A node that runs ahead of the others by more than one round
+// gets -1 (the reference would compute on stale neighbour copies there).
+// results() is valid once every local node has completed the phase, which is when the reference reads it.
+// ---------------------------------------------------------------------------------------------
+
+/** What dist_pgo reads from DPGOHash::results() (DPGO_types.h:204-322): the node's own poses in the
+ * reference's per-node layout [t (n0 rows); R blocks (d n0 rows)] x d, and the scalars. */
+struct NodeResult {
+  Matrix Xk;
+  DPGOResult scalars;
+};
+
+class NodeBatch {
+ public:
+  enum Phase { INITIALIZE = 0, UPDATE = 1, ITERATE = 2, COMMUNICATE = 3, NUM_PHASES = 4 };
+
+  NodeBatch(std::shared_ptr<DPGODriver> drv, int num_nodes, int node_begin, int node_end)
+      : drv_(std::move(drv)), A_(num_nodes), nb_(node_begin), ne_(node_end < 0 ? num_nodes : node_end),
+        X_((int64_t)(drv_->d() + 1) * drv_->num_poses(), drv_->d()) {
+    for (auto &c : calls_) c.assign((size_t)(ne_ - nb_), 0);
+  }
+  /** first global pose and number of poses of a node: DPGO_utils.cpp:147-158 (the first N % A nodes hold one more) */
+  void range(int node, int64_t &first, int64_t &n0) const {
+    const int64_t N = drv_->num_poses(), q = N / A_, r = N % A_;
+    first = (int64_t)node * q + std::min<int64_t>(node, r);
+    n0 = q + (node < r ? 1 : 0);
+  }
+  /** rows of node `node` of a per-node iterate -> the staged global iterate */
+  int stage(int node, const Matrix &Xk) {
+    int64_t first, n0;
+    range(node, first, n0);
+    const int d = drv_->d();
+    if (Xk.cols() != d || Xk.rows() < (d + 1) * n0) return -1;     // neighbour rows below the own ones are ignored
+    const int64_t N = drv_->num_poses();
+    for (int c = 0; c < d; ++c) {
+      for (int64_t i = 0; i < n0; ++i) X_(first + i, c) = Xk(i, c);
+      for (int64_t i = 0; i < d * n0; ++i) X_(N + d * first + i, c) = Xk(n0 + i, c);
+    }
+    return 0;
+  }
+  int request(int node, Phase ph) {
+    if (node < nb_ || node >= ne_) return -1;
+    std::vector<int64_t> &c = calls_[ph];
+    if (c[(size_t)(node - nb_)] > done_[ph]) return -1;            // a second request before the round ran
+    ++c[(size_t)(node - nb_)];
+    for (int64_t v : c) if (v <= done_[ph]) return 0;              // somebody has not asked yet: deferred
+    ++done_[ph];
+    fresh_ = false;
+    switch (ph) {
+      case INITIALIZE: return drv_->initialize(X_);
+      case UPDATE: return drv_->update();
+      case ITERATE: return drv_->iterate();
+      default: return drv_->communicate();
+    }
+  }
+  /** own rows + scalars of a node from the device iterate (one mmpgo_get_poses per round, shared by all nodes) */
+  int results(int node, NodeResult &out) {
+    if (node < nb_ || node >= ne_) return -1;
+    if (!fresh_) {
+      const int rc = drv_->X(X_);
+      if (rc) return rc;
+      fresh_ = true;
+    }
+    int64_t first, n0;
+    range(node, first, n0);
+    const int d = drv_->d();
+    const int64_t N = drv_->num_poses();
+    if (out.Xk.rows() != (d + 1) * n0 || out.Xk.cols() != d) out.Xk = Matrix((d + 1) * n0, d);
+    for (int c = 0; c < d; ++c) {
+      for (int64_t i = 0; i < n0; ++i) out.Xk(i, c) = X_(first + i, c);
+      for (int64_t i = 0; i < d * n0; ++i) out.Xk(n0 + i, c) = X_(N + d * first + i, c);
+    }
+    return drv_->results(node, out.scalars);
+  }
+  const std::shared_ptr<DPGODriver> &driver() const { return drv_; }
+  int node_begin() const { return nb_; }
+  int node_end() const { return ne_; }
+
+ private:
+  std::shared_ptr<DPGODriver> drv_;
+  int A_, nb_, ne_;
+  Matrix X_;                       // staged global iterate (initialize) / last device iterate (results)
+  bool fresh_ = false;
+  std::array<std::vector<int64_t>, NUM_PHASES> calls_;
+  std::array<int64_t, NUM_PHASES> done_{{0, 0, 0, 0}};
+};
+
+/** One object per node with the reference's per-node methods (DPGOHash.h:18-90); Driver = DPGOHash or DPGOStar. */
+template <class Driver>
+class PerNode {
+ public:
+  PerNode(int node, std::shared_ptr<NodeBatch> batch) : node_(node), batch_(std::move(batch)) {}
+  /** x: the node's iterate, own poses first ([t; R] of the n0 own poses, DPGOHash.cpp:20-43).  The neighbour
+   * copies that follow in the reference's Xk are the owners' rows after DPGO::communicate (dist_pgo.cpp:446)
+   * and are taken from the owners here. */
+  int initialize(const Matrix &x) const {
+    const int rc = batch_->stage(node_, x);
+    return rc ? rc : batch_->request(node_, NodeBatch::INITIALIZE);
+  }
+  int update() const { return batch_->request(node_, NodeBatch::UPDATE); }
+  int iterate() const { return batch_->request(node_, NodeBatch::ITERATE); }
+  /** DPGOHash::communicate(pgos) (DPGOHash.h:28-86): the boundary poses move on the device */
+  template <typename PGO>
+  int communicate(const std::vector<std::shared_ptr<PGO>> &pgos) const {
+    if ((int)pgos.size() < batch_->node_end() - batch_->node_begin()) return -1;   // "No information for node"
+    return batch_->request(node_, NodeBatch::COMMUNICATE);
+  }
+  const NodeResult &results() const {
+    if (batch_->results(node_, res_)) throw std::runtime_error(mmpgo_last_error());
+    return res_;
+  }
+  int node() const { return node_; }
+  const std::shared_ptr<NodeBatch> &batch() const { return batch_; }
+
+ private:
+  int node_;
+  std::shared_ptr<NodeBatch> batch_;
+  mutable NodeResult res_;
+};
+
+/** dpgo_hash[alpha] for alpha in [node_begin, node_end): the replacement of dist_pgo.cpp:129-135. */
+template <class Driver>
+std::vector<std::shared_ptr<PerNode<Driver>>> make_per_node(int num_nodes, int d, int64_t num_poses,
+                                                            const measurements_t &meas, const Options &opt,
+                                                            int node_begin = 0, int node_end = -1) {
+  auto drv = std::make_shared<Driver>(num_nodes, d, num_poses, meas, opt, node_begin, node_end);
+  if (node_end < 0) node_end = num_nodes;
+  auto batch = std::make_shared<NodeBatch>(drv, num_nodes, node_begin, node_end);
+  std::vector<std::shared_ptr<PerNode<Driver>>> out;
+  for (int a = node_begin; a < node_end; ++a) out.push_back(std::make_shared<PerNode<Driver>>(a, batch));
+  return out;
+}
 
 }  // namespace DPGO

@@ -30,7 +30,8 @@ enum mmpgo_status {
   MMPGO_ERR_ARG = -1,        /* inconsistent sizes (reference: LOG(ERROR); return -1) */
   MMPGO_ERR_CUDA = -2,       /* a CUDA call failed; see mmpgo_last_error */
   MMPGO_ERR_STATE = -3,      /* call order violated (e.g. iterate before update) */
-  MMPGO_ERR_UNSUPPORTED = -4
+  MMPGO_ERR_UNSUPPORTED = -4,
+  MMPGO_ERR_NOT_CONVERGED = -5  /* a PCG translation solve stopped on translation_solve_max_iters above the tolerance */
 };
 
 /* DPGO::Loss, C++/DPGO/include/DPGO/DPGO_types.h:67 */
@@ -100,7 +101,8 @@ typedef struct mmpgo_node_scalars {
   int32_t iters, soft_restart_hits[2], num_oscillations;
   int32_t refined, restarts, tcg_iterations, tnt_iterations;
   int32_t n0, n1, m0, m1;
-  int32_t translation_solve_iters;
+  int32_t translation_solve_iters; /* PCG solver only: most iterations one node took in a solve since the last
+                                      mmpgo_reset_counters (handle-wide, as of the last host synchronisation); 0 = direct */
   int32_t reserved;              /* Rescale::Dynamic: how often the node's rescale vector was replaced */
 } mmpgo_node_scalars;
 
@@ -114,7 +116,8 @@ typedef struct mmpgo_counters {
   int64_t tcg_iterations, tnt_iterations;
   int64_t vector_passes;
   int64_t reserved[7];            /* [0] pose-iterations of the G00 PCG, [1] solves served by the small-shard PCG kernel,
-                                     [2] solves served by the sparse direct kernel */
+                                     [2] solves served by the sparse direct kernel, [3] PCG node solves that stopped on
+                                     translation_solve_max_iters above the tolerance, [4] most PCG iterations one node took */
 } mmpgo_counters;
 
 const char *mmpgo_version(void);

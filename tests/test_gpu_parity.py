@@ -523,3 +523,36 @@ def test_dynamic_rescale_refuses_a_static_factor():
     g, _, _ = D.grid3d(6, 6, 6, seed=1)
     with pytest.raises(D.MmpgoError):
         D.DPGOHash(g, 4, D.Options(loss="huber", rescale="Dynamic", translation_solver="direct"))
+
+
+@pytest.mark.parametrize("kernel", ["pcg_ring", "pcg_lite"])
+def test_pcg_reports_a_solve_that_stops_on_max_iters(kernel):
+    """The reference's L_.solve is exact (CHOLMOD, DPGOProblem.cpp:140, 568).  A PCG solve cut off at
+    translation_solve_max_iters above translation_solve_tol is reported with MMPGO_ERR_NOT_CONVERGED and counted,
+    by the bare solve and by the driver methods; with the default limit the same nodes are solved to scipy's
+    answer and nothing is reported."""
+    import scipy.sparse.linalg as spla
+    from dpgo_b200 import lib as L
+    (g, _, X0), nodes = D.sphere_rings(2, 6000, seed=4), 2
+    A = _g00(g, nodes)
+    rng = np.random.default_rng(9)
+    b = rng.standard_normal((g.num_poses, g.d)) * 10.0
+    want = -spla.splu(A.tocsc()).solve(b)
+    ok = D.DPGOHash(g, nodes, D.Options(dense_solve_max_n=0, translation_solver=kernel))
+    t = ok.translation_solve(b)
+    assert np.abs(t - want).max() <= 1e-10 * np.abs(want).max()
+    c = ok.counters()
+    need = c.reserved[4]                                        # most iterations one node took
+    assert c.reserved[3] == 0 and 5 < need < 4000
+    drv = D.DPGOHash(g, nodes, D.Options(dense_solve_max_n=0, translation_solver=kernel, translation_solve_max_iters=5))
+    with pytest.raises(L.MmpgoError) as e:
+        drv.translation_solve(b)
+    assert e.value.code == -5 and "translation_solve_max_iters" in str(e.value)
+    c = drv.counters()
+    assert c.reserved[3] == 2 and c.reserved[4] == 5            # both nodes stopped at the limit
+    # the driver methods report it as well, once per offending call
+    drv.reset_counters()
+    assert drv.initialize(X0) == 0
+    rcs = [drv.update(), drv.iterate(), drv.update()]
+    assert -5 in rcs and all(rc in (0, -5) for rc in rcs)
+    assert drv.node_scalars(0).translation_solve_iters == 5
