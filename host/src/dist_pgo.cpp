@@ -136,6 +136,64 @@ static int chordal_initialization(int d, int64_t N, const measurements_t &meas, 
   return 0;
 }
 
+// dist_pgo.cpp:446-531 with the per-node objects: same loops, same reads of results().Xk, the objective and the
+// gradient norm evaluated on the gathered X like the reference's dpgo_star.evaluate_f / evaluate_grad.
+template <class PGO>
+static int per_node_loop(const std::vector<std::shared_ptr<PGO>> &dpgo, const Matrix &X0, int d, int64_t num_poses,
+                         int num_nodes, int num_iters) {
+  auto &batch = *dpgo[0]->batch();
+  std::vector<Matrix> Xk(num_nodes);
+  for (int alpha = 0; alpha < num_nodes; alpha++) {
+    int64_t index, n;
+    batch.range(alpha, index, n);
+    Xk[alpha] = Matrix((d + 1) * n, d);
+    for (int c = 0; c < d; ++c) {
+      for (int64_t i = 0; i < n; ++i) Xk[alpha](i, c) = X0(index + i, c);
+      for (int64_t i = 0; i < d * n; ++i) Xk[alpha](n + i, c) = X0(num_poses + d * index + i, c);
+    }
+  }
+  for (int alpha = 0; alpha < num_nodes; alpha++) {
+    if (dpgo[alpha]->initialize(Xk[alpha]) || dpgo[alpha]->update()) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
+  }
+  Matrix X((d + 1) * num_poses, d), gradF;
+  auto gather = [&]() {
+    for (int alpha = 0; alpha < num_nodes; alpha++) {
+      int64_t i, n;
+      batch.range(alpha, i, n);
+      const Matrix &R = dpgo[alpha]->results().Xk;
+      for (int c = 0; c < d; ++c) {
+        for (int64_t k = 0; k < n; ++k) X(i + k, c) = R(k, c);
+        for (int64_t k = 0; k < d * n; ++k) X(num_poses + d * i + k, c) = R(n + k, c);
+      }
+    }
+  };
+  auto norm = [](const Matrix &G) {
+    double s = 0;
+    for (int64_t i = 0; i < G.rows(); ++i) for (int64_t c = 0; c < G.cols(); ++c) s += G(i, c) * G(i, c);
+    return std::sqrt(s);
+  };
+  double fobj = 0, grad = 0;
+  gather();
+  if (batch.driver()->evaluate_f(X, fobj) || batch.driver()->evaluate_grad(X, gradF)) return -1;
+  fobj *= 2; grad = 2 * norm(gradF);
+  std::cout << "===============================================" << std::endl;
+  std::cout << "Distributed PGO" << std::endl;
+  std::cout << "-----------------------------------------------" << std::endl;
+  for (int iter = 0; iter < num_iters; iter++) {
+    std::cout << iter << ": " << std::setprecision(20) << fobj << " " << grad << std::endl;
+    for (int alpha = 0; alpha < num_nodes; alpha++) if (dpgo[alpha]->iterate()) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
+    gather();
+    for (int alpha = 0; alpha < num_nodes; alpha++) if (dpgo[alpha]->communicate(dpgo)) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
+    for (int alpha = 0; alpha < num_nodes; alpha++) if (dpgo[alpha]->update()) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
+    if (batch.driver()->evaluate_f(X, fobj) || batch.driver()->evaluate_grad(X, gradF)) return -1;
+    fobj *= 2; grad = 2 * norm(gradF);
+  }
+  std::cout << "---------------------------------------" << std::endl;
+  std::cout << "final objective: " << fobj << std::endl;
+  std::cout << "final gradient: " << grad << std::endl;
+  return 0;
+}
+
 int main(int argc, char *argv[]) {
   if (argc < 2) {
     std::cout << "Usage: " << argv[0] << " [input .g2o file]" << std::endl;
@@ -143,7 +201,7 @@ int main(int argc, char *argv[]) {
   }
   std::map<std::string, std::string> opt = {{"iters", "1000"}, {"dist_init", "true"}, {"loss", "trivial"},
                                              {"accelerated", "true"}, {"save", "true"}, {"algorithm", "hash"},
-                                             {"device", "0"}, {"dist_init_fallback", "false"}};
+                                             {"device", "0"}, {"dist_init_fallback", "false"}, {"per_node", "false"}};
   for (int a = 1; a < argc; ++a) {
     std::string s = argv[a];
     if (s == "--help") {
@@ -160,6 +218,7 @@ int main(int argc, char *argv[]) {
                    "  --device arg (=0)          CUDA device ordinal\n"
                    "  --init arg                 text file with the initial iterate ((d+1)N rows of d numbers)\n"
                    "  --dist_init_fallback arg (=false)  with --dist_init true: use the centralised chordal initialisation\n"
+                   "  --per_node arg (=false)    run the reference's loop with one driver object per node (DPGO::PerNode)\n"
                    "  --parse_only arg           only read the dataset and print its checksums\n";
       return 0;
     }
@@ -230,6 +289,15 @@ int main(int argc, char *argv[]) {
           if (!(in >> X(i, c))) throw std::runtime_error("initial iterate file too short");
     } else if (chordal_initialization(d, num_poses, measurements, options.device, X)) return -1;
 
+    if (parse_bool(opt["per_node"])) {
+      // The reference's main loop as it stands (dist_pgo.cpp:446-531), one object per node: the objects
+      // forward to one batched driver (DPGO::PerNode, mmpgo_host/DPGO.h).
+      if (star)
+        return per_node_loop(DPGO::make_per_node<DPGO::DPGOStar>(num_nodes, d, num_poses, measurements, options), X, d,
+                             num_poses, num_nodes, num_iters);
+      return per_node_loop(DPGO::make_per_node<DPGO::DPGOHash>(num_nodes, d, num_poses, measurements, options), X, d,
+                           num_poses, num_nodes, num_iters);
+    }
     std::unique_ptr<DPGO::DPGODriver> dpgo;
     if (star) dpgo.reset(new DPGO::DPGOStar(num_nodes, d, num_poses, measurements, options));
     else dpgo.reset(new DPGO::DPGOHash(num_nodes, d, num_poses, measurements, options));

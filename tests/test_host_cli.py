@@ -66,6 +66,34 @@ def test_cli_trace_equals_python_driver(tmp_path, alg, loss):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("alg,loss,nodes", [("hash", "trivial", 4), ("star", "trivial", 5), ("hash", "welsch", 3)])
+def test_per_node_objects_run_the_reference_loop(tmp_path, alg, loss, nodes):
+    """dist_pgo.cpp:446-531 literally -- one driver object per node (DPGO::PerNode), `for alpha` loops over
+    initialize/update, iterate, results().Xk, communicate(dpgo_hash), update, the objective and gradient norm from
+    evaluate_f / evaluate_grad on the gathered X -- prints the trace of the batched driver (ragged partition: 216
+    poses over 5 nodes)."""
+    g, _, X0 = D.grid3d(6, 6, 6, seed=2)
+    path = str(tmp_path / "g.g2o")
+    D.write_g2o(path, g)
+    g = D.read_g2o(path)
+    np.savetxt(str(tmp_path / "x0.txt"), X0, fmt="%.17g")
+    iters = 8
+    r = _run(["--dataset", path, "--num_nodes", str(nodes), "--iters", str(iters), "--loss", loss, "--algorithm", alg,
+              "--init", str(tmp_path / "x0.txt"), "--per_node", "true", "--save", "false"], cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr + r.stdout
+    rows = [l.split() for l in r.stdout.splitlines() if l[:1].isdigit() and ": " in l]
+    got = np.array([[float(x[1]), float(x[2])] for x in rows])
+    assert got.shape == (iters, 2)
+    _, trace = D.run_dist_pgo(g, nodes, X0, iters, D.Options(loss=loss), alg)
+    want = np.array([[t[0], t[1]] for t in trace])[:iters]
+    # evaluate_f sums the edges of the global graph, the batched trace sums the nodes' objectives: the same
+    # number for the trivial loss (DPGOStar.cpp:719-722), equal up to the R^T R != I discrepancy otherwise
+    tol = 1e-11 if loss == "trivial" else 1e-6
+    assert np.allclose(got[:, 0], want[:, 0], rtol=tol)
+    assert np.allclose(got[:, 1], want[:, 1], rtol=1e-6 if loss == "trivial" else 1e-3)
+
+
+@pytest.mark.gpu
 def test_cli_chordal_initialisation_is_a_sane_start(tmp_path):
     g, Xgt, _ = D.grid3d(5, 5, 4, seed=4)
     path = str(tmp_path / "g.g2o")
