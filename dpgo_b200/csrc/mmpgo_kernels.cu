@@ -1,5 +1,6 @@
 // Hand-written sm_100a FP64 kernels of the MM-PGO / AMM-PGO iteration.
 // See mmpgo_kernels.cuh for the data model and DESIGN.md for the rooflines.
+#include <cstdlib>
 #include "mmpgo_kernels.cuh"
 #include "so3_project.cuh"
 
@@ -40,18 +41,32 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[K], double *dst) 
   }
 }
 
+// o = row r (run-time) of the NR x D register array M, as a chain of selects: indexing a register array with a
+// run-time row would put it in local memory
+template <int D, int NR>
+__device__ __forceinline__ void sel_row(const double *M, int r, double *o) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) o[k] = M[k];
+#pragma unroll
+  for (int rr = 1; rr < NR; ++rr) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = (r == rr) ? M[rr * D + k] : o[k];
+  }
+}
+
 // P = V - sym(V Y^T) Y for one pose, row r of the d x d block  (SOdProduct.h:64-103)
 template <int D>
 __device__ __forceinline__ void proj_row(const double *V, const double *Y, int r, double *out) {
   // S[r][c] = 0.5 (V_r . Y_c + Y_r . V_c)
-  double S[D];
+  double S[D], Yr[D];
+  sel_row<D, D>(Y, r, Yr);
 #pragma unroll
   for (int c = 0; c < D; ++c) {
     double a = 0.0, b = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       a += V[r * D + k] * Y[c * D + k];
-      b += Y[r * D + k] * V[c * D + k];
+      b += Yr[k] * V[c * D + k];
     }
     S[c] = 0.5 * (a + b);
   }
@@ -61,6 +76,182 @@ __device__ __forceinline__ void proj_row(const double *V, const double *Y, int r
 #pragma unroll
     for (int c = 0; c < D; ++c) acc += S[c] * Y[c * D + k];
     out[k] = V[r * D + k] - acc;
+  }
+}
+
+// L2 prefetch of a contiguous byte range (cp.async.bulk.prefetch.L2: one instruction, no registers, no smem).
+// The streaming kernels here are bound by DRAM latency x the loads a resident CTA keeps in flight, not by
+// bandwidth: a CTA asks for the data of the CTA that will run one wave later, which then finds it in L2.
+__device__ __forceinline__ void l2_prefetch(const void *p, size_t bytes) {
+  const size_t a0 = reinterpret_cast<size_t>(p) & ~size_t(15);
+  const size_t a1 = (reinterpret_cast<size_t>(p) + bytes + 15) & ~size_t(15);
+  for (size_t a = a0; a < a1; a += 16384) {
+    const unsigned n = (unsigned)min((size_t)16384, a1 - a);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+  }
+}
+
+// The tile that a CTA `PF_DIST` blocks later will work on: first own pose and pose count; false when there is none or
+// its node is masked out.  Measured on the 1 M-pose grid (k_gpass): any distance from 8 to 200 tiles gives the same
+// 13-16 % (the data only has to be on its way before the CTA starts), 592 (a full wave) and more lose it again.
+constexpr int PF_DIST = 64;
+__device__ __forceinline__ bool tile_ahead(const Tiles &tl, int tile, int &ps, int &pc) {
+  const int tf = tile + PF_DIST;
+  if (tf >= tl.n_tiles) return false;
+  if (tl.active && !tl.active[tl.node[tf]]) return false;
+  ps = tl.start[tf]; pc = tl.cnt[tf];
+  return true;
+}
+// rows [ps, ps + pc) of a per-pose array with `stride` doubles per pose (null: nothing)
+__device__ __forceinline__ void l2_prefetch_rows(const double *base, int stride, int ps, int pc) {
+  if (base) l2_prefetch(base + (size_t)ps * stride, (size_t)pc * stride * sizeof(double));
+}
+
+// =============================================================================
+// K2 epilogues (shared by the two thread mappings below).  Called by every thread of the CTA;
+// `valid` selects the threads that own output row `row` of local pose `pl` (global pose p) with
+// the complete row acc = (G x)_row and the pose block xp of the input vector.
+// =============================================================================
+template <int D, int MODE, int NT>
+__device__ __forceinline__ void gpass_epilogue(const bool valid, const int pl, const int row, const int p, const int tile,
+                                               const double (&acc)[D], const double (&xp)[(D + 1) * D],
+                                               const GPassArgs &a) {
+  constexpr int PB = Dim<D>::PB;
+  double xr[D];                        // row `row` of the input pose block
+  sel_row<D, D + 1>(xp, row, xr);
+  double sc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (MODE == G_EVAL) {
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double gv = a.g ? a.g[(size_t)p * PB + row * D + c] : 0.0;
+        sc[0] += xr[c] * (gv + 0.5 * acc[c]);
+      }
+    }
+    block_reduce_store<1, NT>(reinterpret_cast<double(&)[1]>(sc), a.partials + (size_t)tile * NS);
+    return;
+  }
+  if (MODE == G_RHS_T) {
+    if (valid && row == 0) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double gv = a.g ? a.g[(size_t)p * PB + c] : 0.0;
+        a.out[(size_t)(a.out_perm ? a.out_perm[p] : p) * D + c] = gv + acc[c];
+      }
+    }
+    return;
+  }
+  // modes that need the whole pose block of the result: stage in shared memory
+  __shared__ double sV[TILE][PB];
+  if (MODE == G_GRAD) {
+    double v[D];
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double gv = a.g[(size_t)p * PB + row * D + c];
+        v[c] = gv + acc[c];
+        a.out[(size_t)p * PB + row * D + c] = v[c];
+        sV[pl][row * D + c] = v[c];
+        sc[0] += xr[c] * (gv + 0.5 * acc[c]);
+        sc[2] += xr[c] * acc[c];
+        sc[3] += xr[c] * gv;
+      }
+    }
+    __syncthreads();
+    if (valid) {
+      if (row == 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) sc[1] += v[c] * v[c];
+      } else {
+        double pr[D];
+        proj_row<D>(&sV[pl][D], xp + D, row - 1, pr);
+#pragma unroll
+        for (int c = 0; c < D; ++c) sc[1] += pr[c] * pr[c];
+      }
+    }
+    block_reduce_store<4, NT>(sc, a.partials + (size_t)tile * NS);
+    return;
+  }
+  if (MODE == G_REDGRAD) {
+    // all rows of G x are formed, so the surrogate value s1 = sum x.(g + 1/2 G x) comes for free
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double gv = a.g[(size_t)p * PB + row * D + c];
+        sc[1] += xr[c] * (gv + 0.5 * acc[c]);
+        if (row >= 1) {
+          const double v = gv + acc[c];
+          a.out[(size_t)p * PB + row * D + c] = v;
+          sV[pl][row * D + c] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (valid && row >= 1) {
+      double pr[D];
+      proj_row<D>(&sV[pl][D], xp + D, row - 1, pr);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        a.out2[(size_t)p * PB + row * D + c] = pr[c];
+        sc[0] += pr[c] * pr[c];
+      }
+    }
+    block_reduce_store<2, NT>(reinterpret_cast<double(&)[2]>(sc), a.partials + (size_t)tile * NS);
+    return;
+  }
+  if (MODE == G_HV) {
+    // xp holds the direction p = [tdot; Rdot]; Y and nab come from xref / nab
+    double Y[D * D], NB[D * D];
+    if (valid) {
+      const double *yp = a.xref + (size_t)p * PB + D;
+      const double *np = a.nab + (size_t)p * PB + D;
+#pragma unroll
+      for (int k = 0; k < D * D; ++k) { Y[k] = yp[k]; NB[k] = np[k]; }
+    }
+    if (valid && row >= 1) {
+      // E_r = acc - (sym(nab Y^T) Rdot)_r     (SymBlockDiagProduct, SOdProduct.h:64-89)
+      const int r = row - 1;
+      double S[D], Yr[D], NBr[D];
+      sel_row<D, D>(Y, r, Yr);
+      sel_row<D, D>(NB, r, NBr);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double u = 0.0, w = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          u += NBr[k] * Y[c * D + k];
+          w += Yr[k] * NB[c * D + k];
+        }
+        S[c] = 0.5 * (u + w);
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) t += S[c] * xp[(1 + c) * D + k];
+        sV[pl][row * D + k] = acc[k] - t;
+      }
+    }
+    __syncthreads();
+    if (valid) {
+      if (row >= 1) {
+        double pr[D];
+        proj_row<D>(&sV[pl][D], Y, row - 1, pr);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          a.out[(size_t)p * PB + row * D + c] = pr[c];
+          const double pv = xr[c];
+          sc[0] += pv * pr[c];
+          sc[1] += pr[c] * pr[c];
+          sc[2] += pv * pv;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) a.out[(size_t)p * PB + c] = 0.0;
+      }
+    }
+    block_reduce_store<3, NT>(reinterpret_cast<double(&)[3]>(sc), a.partials + (size_t)tile * NS);
+    return;
   }
 }
 
@@ -75,6 +266,22 @@ k_gpass(Tiles tl, GPassArgs a) {
   const int tile = blockIdx.x;
   const int node = tl.node[tile];
   if (tl.active && !tl.active[node]) return;
+  if (threadIdx.x < 4) {
+    int ps, pc;
+    if (tile_ahead(tl, tile, ps, pc)) {
+      if (threadIdx.x < 2) {
+        const int ef0 = a.rowptr[ps], ef1 = a.rowptr[ps + pc];
+        if (threadIdx.x == 0) l2_prefetch(a.blk + (size_t)ef0 * BB, (size_t)(ef1 - ef0) * BB * sizeof(double));
+        else l2_prefetch(a.col + ef0, (size_t)(ef1 - ef0) * sizeof(int));
+      } else if (threadIdx.x == 2) {
+        l2_prefetch_rows(a.x, PB, ps, pc);
+        l2_prefetch_rows(a.diag, SYM, ps, pc);
+      } else {
+        l2_prefetch_rows(a.g, PB, ps, pc);
+        if (MODE == G_HV) { l2_prefetch_rows(a.xref, PB, ps, pc); l2_prefetch_rows(a.nab, PB, ps, pc); }
+      }
+    }
+  }
   const int pl = threadIdx.x / R, row = threadIdx.x % R;
   const int cnt = tl.cnt[tile];
   const int p = tl.start[tile] + pl;
@@ -134,138 +341,7 @@ k_gpass(Tiles tl, GPassArgs a) {
     }
   }
 
-  double sc[4] = {0.0, 0.0, 0.0, 0.0};
-  if (MODE == G_EVAL) {
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const double gv = a.g ? a.g[(size_t)p * PB + row * D + c] : 0.0;
-        sc[0] += xp[row * D + c] * (gv + 0.5 * acc[c]);
-      }
-    }
-    block_reduce_store<1, NT>(reinterpret_cast<double(&)[1]>(sc), a.partials + (size_t)tile * NS);
-    return;
-  }
-  if (MODE == G_RHS_T) {
-    if (valid && row == 0) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const double gv = a.g ? a.g[(size_t)p * PB + c] : 0.0;
-        a.out[(size_t)(a.out_perm ? a.out_perm[p] : p) * D + c] = gv + acc[c];
-      }
-    }
-    return;
-  }
-  // modes that need the whole pose block of the result: stage in shared memory
-  __shared__ double sV[TILE][PB];
-  if (MODE == G_GRAD) {
-    double v[D];
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const double gv = a.g[(size_t)p * PB + row * D + c];
-        v[c] = gv + acc[c];
-        a.out[(size_t)p * PB + row * D + c] = v[c];
-        sV[pl][row * D + c] = v[c];
-        sc[0] += xp[row * D + c] * (gv + 0.5 * acc[c]);
-        sc[2] += xp[row * D + c] * acc[c];
-        sc[3] += xp[row * D + c] * gv;
-      }
-    }
-    __syncthreads();
-    if (valid) {
-      if (row == 0) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) sc[1] += v[c] * v[c];
-      } else {
-        double pr[D];
-        proj_row<D>(&sV[pl][D], xp + D, row - 1, pr);
-#pragma unroll
-        for (int c = 0; c < D; ++c) sc[1] += pr[c] * pr[c];
-      }
-    }
-    block_reduce_store<4, NT>(sc, a.partials + (size_t)tile * NS);
-    return;
-  }
-  if (MODE == G_REDGRAD) {
-    // all rows of G x are formed, so the surrogate value s1 = sum x.(g + 1/2 G x) comes for free
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        const double gv = a.g[(size_t)p * PB + row * D + c];
-        sc[1] += xp[row * D + c] * (gv + 0.5 * acc[c]);
-        if (row >= 1) {
-          const double v = gv + acc[c];
-          a.out[(size_t)p * PB + row * D + c] = v;
-          sV[pl][row * D + c] = v;
-        }
-      }
-    }
-    __syncthreads();
-    if (valid && row >= 1) {
-      double pr[D];
-      proj_row<D>(&sV[pl][D], xp + D, row - 1, pr);
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        a.out2[(size_t)p * PB + row * D + c] = pr[c];
-        sc[0] += pr[c] * pr[c];
-      }
-    }
-    block_reduce_store<2, NT>(reinterpret_cast<double(&)[2]>(sc), a.partials + (size_t)tile * NS);
-    return;
-  }
-  if (MODE == G_HV) {
-    // xp holds the direction p = [tdot; Rdot]; Y and nab come from xref / nab
-    double Y[D * D], NB[D * D];
-    if (valid) {
-      const double *yp = a.xref + (size_t)p * PB + D;
-      const double *np = a.nab + (size_t)p * PB + D;
-#pragma unroll
-      for (int k = 0; k < D * D; ++k) { Y[k] = yp[k]; NB[k] = np[k]; }
-    }
-    if (valid && row >= 1) {
-      // E_r = acc - (sym(nab Y^T) Rdot)_r     (SymBlockDiagProduct, SOdProduct.h:64-89)
-      const int r = row - 1;
-      double S[D];
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        double u = 0.0, w = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          u += NB[r * D + k] * Y[c * D + k];
-          w += Y[r * D + k] * NB[c * D + k];
-        }
-        S[c] = 0.5 * (u + w);
-      }
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c < D; ++c) t += S[c] * xp[(1 + c) * D + k];
-        sV[pl][row * D + k] = acc[k] - t;
-      }
-    }
-    __syncthreads();
-    if (valid) {
-      if (row >= 1) {
-        double pr[D];
-        proj_row<D>(&sV[pl][D], Y, row - 1, pr);
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-          a.out[(size_t)p * PB + row * D + c] = pr[c];
-          const double pv = xp[row * D + c];
-          sc[0] += pv * pr[c];
-          sc[1] += pr[c] * pr[c];
-          sc[2] += pv * pv;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < D; ++c) a.out[(size_t)p * PB + c] = 0.0;
-      }
-    }
-    block_reduce_store<3, NT>(reinterpret_cast<double(&)[3]>(sc), a.partials + (size_t)tile * NS);
-    return;
-  }
+  gpass_epilogue<D, MODE, NT>(valid, pl, row, p, tile, acc, xp, a);
 }
 
 // G_RHS_T as its own kernel: rhs_t = g_t + G01 Y needs only row 0 of every block and the rotation
@@ -317,12 +393,80 @@ __global__ void __launch_bounds__(TILE) k_g01(Tiles tl, GPassArgs a) {
   }
 }
 
+// k_g01 for SE(3), 2 lanes per pose: lane h reads columns
+// 2h, 2h+1 of the compact row (one 16-byte load) and the neighbour's rows 2h, 2h+1 (h = 0: rotation row 1 only).
+__global__ void __launch_bounds__(TILE * 2) k_g01_3(Tiles tl, GPassArgs a) {
+  constexpr int D = 3, R = 4, PB = 12, SYM = 10;
+  const int tile = blockIdx.x;
+  const int node = tl.node[tile];
+  if (tl.active && !tl.active[node]) return;
+  if (threadIdx.x < 4) {
+    int ps, pc;
+    if (tile_ahead(tl, tile, ps, pc)) {
+      if (threadIdx.x < 2) {
+        const int ef0 = a.rowptr[ps], ef1 = a.rowptr[ps + pc];
+        if (threadIdx.x == 0) l2_prefetch(a.blk0 + (size_t)ef0 * R, (size_t)(ef1 - ef0) * R * sizeof(double));
+        else l2_prefetch(a.col + ef0, (size_t)(ef1 - ef0) * sizeof(int));
+      } else if (threadIdx.x == 2) {
+        l2_prefetch_rows(a.x, PB, ps, pc);
+      } else {
+        l2_prefetch_rows(a.diag, SYM, ps, pc);
+        l2_prefetch_rows(a.g, PB, ps, pc);
+      }
+    }
+  }
+  const int pl = threadIdx.x >> 1, h = threadIdx.x & 1;
+  const bool valid = pl < tl.cnt[tile];
+  const int p = tl.start[tile] + pl;
+  double acc[D] = {0.0, 0.0, 0.0};
+  if (valid) {
+    const int e0 = a.rowptr[p], e1 = a.rowptr[p + 1];
+    int qn = e0 < e1 ? __ldg(a.col + e0) : 0;
+#pragma unroll 2
+    for (int e = e0; e < e1; ++e) {
+      const int q = qn;
+      qn = e + 1 < e1 ? __ldg(a.col + e + 1) : 0;
+      const double2 b2 = __ldg(reinterpret_cast<const double2 *>(a.blk0 + (size_t)e * R) + h);
+      const double2 *xq2 = reinterpret_cast<const double2 *>(a.x + (size_t)q * PB) + 3 * h;
+      const double2 v1 = __ldg(xq2 + 1), v2 = __ldg(xq2 + 2);
+      if (h) {                               // column 2 (rotation row 2); column 0 is the translation row: not part of G01
+        const double2 v0 = __ldg(xq2);
+        acc[0] = fma(b2.x, v0.x, acc[0]); acc[1] = fma(b2.x, v0.y, acc[1]); acc[2] = fma(b2.x, v1.x, acc[2]);
+      }
+      acc[0] = fma(b2.y, v1.y, acc[0]); acc[1] = fma(b2.y, v2.x, acc[1]); acc[2] = fma(b2.y, v2.y, acc[2]);
+    }
+    const double *dg = a.diag + (size_t)p * SYM;
+    const double *xh = a.x + (size_t)p * PB + 6 * h;
+    const double d1 = dg[symidx(0, 2 * h + 1)];
+    if (h) {
+      const double d0 = dg[symidx(0, 2)];
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[c] = fma(d0, xh[c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = fma(d1, xh[3 + c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < D; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+  if (valid && h == 0) {
+    const size_t orow = a.out_perm ? (size_t)a.out_perm[p] : (size_t)p;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const double gv = a.g ? a.g[(size_t)p * PB + c] : 0.0;
+      a.out[orow * D + c] = gv + acc[c];
+    }
+  }
+}
+
 template <int D> void launch_gpass(int mode, const Tiles &tl, const GPassArgs &a, cudaStream_t s) {
   const dim3 grid(tl.n_tiles), block(TILE * (D + 1));
   switch (mode) {
     case G_EVAL: k_gpass<D, G_EVAL><<<grid, block, 0, s>>>(tl, a); break;
     case G_GRAD: k_gpass<D, G_GRAD><<<grid, block, 0, s>>>(tl, a); break;
-    case G_RHS_T: k_g01<D><<<grid, TILE, 0, s>>>(tl, a); break;
+    case G_RHS_T:
+      if (D == 3) k_g01_3<<<grid, TILE * 2, 0, s>>>(tl, a);
+      else k_g01<D><<<grid, TILE, 0, s>>>(tl, a);
+      break;
     case G_REDGRAD: k_gpass<D, G_REDGRAD><<<grid, block, 0, s>>>(tl, a); break;
     case G_HV: k_gpass<D, G_HV><<<grid, block, 0, s>>>(tl, a); break;
   }
@@ -359,6 +503,19 @@ __global__ void __launch_bounds__(TILE) k_inter(Tiles tl, InterArgs a) {
   const int tile = blockIdx.x;
   const int node = tl.node[tile];
   if (tl.active && !tl.active[node]) return;
+  if (threadIdx.x < 3) {
+    int ps, pc;
+    if (tile_ahead(tl, tile, ps, pc)) {
+      if (threadIdx.x == 0) {
+        const int ef0 = a.rowptr[ps], ef1 = a.rowptr[ps + pc];
+        l2_prefetch(a.rec + ef0, (size_t)(ef1 - ef0) * sizeof(InterRec));
+      } else if (threadIdx.x == 1) {
+        l2_prefetch_rows(a.xa, PB, ps, pc);
+      } else {
+        l2_prefetch_rows(a.xb, PB, ps, pc);
+      }
+    }
+  }
   const int pl = threadIdx.x;
   const int p = tl.start[tile] + pl;
   const bool valid = pl < tl.cnt[tile];
@@ -814,6 +971,15 @@ __global__ void __launch_bounds__(TILE) k_prox(Tiles tl, ProxArgs a) {
   const int tile = blockIdx.x;
   const int node = tl.node[tile];
   if (tl.active && !tl.active[node]) return;
+  if (threadIdx.x < 8) {
+    int ps, pc;
+    if (tile_ahead(tl, tile, ps, pc)) {
+      const int j = threadIdx.x;
+      const double *q = j == 0 ? a.xa : j == 1 ? a.xb : j == 2 ? a.dfa : j == 3 ? a.dfb : j == 4 ? a.ga : j == 5 ? a.gb
+                      : j == 6 ? a.xref : a.tnv;
+      l2_prefetch_rows(q, j == 7 ? TNV : PB, ps, pc);
+    }
+  }
   const int p = tl.start[tile] + threadIdx.x;
   const bool valid = threadIdx.x < tl.cnt[tile];
   double sc[1] = {0.0};
@@ -924,6 +1090,13 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
   const int tile = blockIdx.x;
   const int node = tl.node[tile];
   if (tl.active && !tl.active[node]) return;
+  if (threadIdx.x < 4) {
+    int ps, pc;
+    if (tile_ahead(tl, tile, ps, pc)) {
+      const int j = threadIdx.x;
+      l2_prefetch_rows(j == 0 ? a.a : j == 1 ? a.b : j == 2 ? a.c : a.y, PB, ps, pc);
+    }
+  }
   const int p0 = tl.start[tile], cnt = tl.cnt[tile];
   const int p = p0 + threadIdx.x;
   const bool valid = threadIdx.x < cnt;
