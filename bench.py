@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--nodes", type=int, default=64)
     ap.add_argument("--loss", default="trivial")
     ap.add_argument("--algorithm", default="star", choices=["star", "hash"])
+    ap.add_argument("--preconditioner", default="BlockJacobi", choices=["BlockJacobi", "RegularizedCholesky", "Jacobi", "None"],
+                    help="tCG preconditioner of both arms (the headline is quoted with BlockJacobi; RegularizedCholesky is the "
+                         "reference's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--time-to-cost-cpu", type=int, default=0, metavar="ITERS",
@@ -193,9 +196,9 @@ def cpu_reference_driver(args, g, nodes, workers, threads):
     from oracle import cpu_ref
     from oracle import dpgo as odpgo
     from parity import to_measurements
-    if not cpu_ref.available():
-        return None
-    opts = odpgo.Options(loss=args.loss, preconditioner="BlockJacobi")
+    if not cpu_ref.available() or args.preconditioner not in cpu_ref.PRECON:
+        return None                          # (the C++ restatement carries None / Jacobi / BlockJacobi)
+    opts = odpgo.Options(loss=args.loss, preconditioner=args.preconditioner)
     return cpu_ref.CpuDPGO(to_measurements(g), g.num_poses, nodes, opts, args.algorithm, workers=workers,
                            threads=threads, mode=0)
 
@@ -269,7 +272,7 @@ def time_to_cost_vs_cpu(args, iters, device, sample_grid=(100, 125, 5), sample_n
     target = (1.0 + 1e-3) * ctrace[-1]
     k_cpu = next(k for k, f in enumerate(ctrace) if f <= target)
     cls = D.DPGOStar if args.algorithm == "star" else D.DPGOHash
-    drv = cls(g, sample_nodes, D.Options(loss=args.loss, device=device))
+    drv = cls(g, sample_nodes, D.Options(loss=args.loss, device=device, preconditioner=args.preconditioner))
     assert drv.initialize(X0) == 0
     D.lib.check(drv.update())
     for _ in range(3):                                    # warm the kernels, then start again
@@ -309,7 +312,7 @@ def numpy_oracle_sample(args, sample_grid, sample_nodes, iters):
     from parity import to_measurements
     g, _, X0 = make_graph(args, sample_grid)
     timing = {}
-    odist.run(to_measurements(g), g.num_poses, sample_nodes, odpgo.Options(loss=args.loss, preconditioner="BlockJacobi"),
+    odist.run(to_measurements(g), g.num_poses, sample_nodes, odpgo.Options(loss=args.loss, preconditioner=args.preconditioner),
               X0, iters, args.algorithm, log_global=False, timing=timing)
     return {"value": g.num_edges * iters / timing["seconds"], "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "numpy/scipy oracle (libcpu_dpgo.so not built) on a %dx%dx%d slab, %d robot nodes, %d iterations"
@@ -353,7 +356,7 @@ def run_reference(args):
         "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": n, "warmup": args.warmup, "ms_per_step": 1e3 * secs / n, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, N, E), "preconditioner": "BlockJacobi",
+        "config": {"workload": workload_name(args, N, E), "preconditioner": args.preconditioner,
                    "final_2F": 2 * fobj, "step_seconds": per,
                    "note": "upstream dist_pgo cannot be built here (no Eigen / SuiteSparse / glog / Boost); this arm times the "
                            "restated reference algorithm in C++17 + OpenMP (oracle/cpu_dpgo.cpp: the reference's scalar CSR "
@@ -387,7 +390,7 @@ def run_ours(args):
 
     g, _, X0 = make_graph(args)
     N, E, d = g.num_poses, g.num_edges, g.d
-    opts = D.Options(loss=args.loss, device=local_rank)
+    opts = D.Options(loss=args.loss, device=local_rank, preconditioner=args.preconditioner)
     drv = multi.make_driver(g, args.nodes, opts, args.algorithm, rank, world)
 
     def barrier():
@@ -575,7 +578,7 @@ def run_ours(args):
             "config": {"workload": workload_name(args, N, E),
                        "l2": "working set (graph %.0f MB + iterates) is larger than the 126 MB L2" % (
                            (sizes["bsr_entries"] * 132 + HE * 128) / 1e6),
-                       "preconditioner": "BlockJacobi", "nodes_per_gpu": args.nodes // world,
+                       "preconditioner": args.preconditioner, "nodes_per_gpu": args.nodes // world,
                        "translation_solver": sinfo,
                        "final_2F": 2 * F, "final_2gradnorm": 2 * gn,
                        "objective_trace": {"digest": trace_digest, "first_2F": 2 * float(f_trace[0]), "last_2F": 2 * float(f_trace[-1]),

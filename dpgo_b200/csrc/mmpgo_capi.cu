@@ -63,11 +63,12 @@ void mmpgo_default_options(mmpgo_options *o) {
   o->translation_solver = MMPGO_TSOLVE_AUTO;
   o->rescale = MMPGO_RESCALE_STATIC;        // dist_pgo.cpp:105
   o->max_rescale_count = 5;                // DPGO_types.h:131
+  o->reg_Cholesky_precon_max_condition_number = 1e6;   // DPGO_types.h:159
 }
 
 int mmpgo_create(const mmpgo_options *opts, mmpgo_handle *out) {
   if (!opts || !out) { mmpgo::set_error("null argument"); return MMPGO_ERR_ARG; }
-  if (opts->loss < 0 || opts->loss > 3 || opts->preconditioner < 0 || opts->preconditioner > 2 ||
+  if (opts->loss < 0 || opts->loss > 3 || opts->preconditioner < 0 || opts->preconditioner > 3 ||
       opts->algorithm < 0 || opts->algorithm > 1 || opts->scheme < 0 || opts->scheme > 1 ||
       opts->translation_solver < 0 || opts->translation_solver > 4 || opts->rescale < 0 || opts->rescale > 1) {
     mmpgo::set_error("invalid enum value in options");
@@ -283,6 +284,15 @@ int mmpgo_graph_sizes(mmpgo_handle hh, int64_t *sizes /* [8] */) {
   if (!sizes || !h->graph_set) { mmpgo::set_error("bad argument"); return MMPGO_ERR_ARG; }
   sizes[0] = h->NO; sizes[1] = h->NH; sizes[2] = h->n_intra_entries; sizes[3] = h->n_inter_he;
   sizes[4] = h->n_edges_owned; sizes[5] = h->n_tiles; sizes[6] = h->A; sizes[7] = h->d;
+  return MMPGO_OK;
+}
+
+int mmpgo_preconditioner_info(mmpgo_handle hh, int32_t node, double *lambda_max, int64_t *factor_nnz) {
+  H_OR_FAIL(hh);
+  if (!h->graph_set || node < h->node_begin || node >= h->node_end) { mmpgo::set_error("node not local"); return MMPGO_ERR_ARG; }
+  if (!h->use_regchol) { mmpgo::set_error("the handle does not run the RegularizedCholesky preconditioner"); return MMPGO_ERR_STATE; }
+  if (lambda_max) *lambda_max = h->lambda_max[node - h->node_begin];
+  if (factor_nnz) *factor_nnz = h->mf11_nnz;
   return MMPGO_OK;
 }
 

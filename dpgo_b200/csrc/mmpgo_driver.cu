@@ -356,14 +356,41 @@ template <int D> struct Drv {
     return 0;
   }
 
+  // RegularizedCholesky: pre_buf (rotation rows) = (G11 + reg)^{-1} src for the nodes of m -- reg_Chol_precon_.solve
+  // (DPGOProblem.cpp:592-594) as a gather into elimination order and one persistent launch of the supernodal sweeps
+  static int precon_solve(Handle *h, const double *src, const Mask &m) {
+    Tiles tl; RC(make_tiles(h, m, &tl));
+    launch_gather_rot<D>(tl, src, h->d_mf11_perm, h->rhs11, h->stream);
+    MfSolveArgs ma;
+    ma.f = h->mf11;
+    ma.active = tl.active;                 // the mask make_tiles uploaded (stream-ordered before the launch)
+    ma.rhs = h->rhs11; ma.out = h->pre_buf; ma.out_stride = D; ma.sign = 1.0; ma.dry = 0;
+    ma.level_sync = h->mf11_level_sync ? 1 : 0;
+    CK((cudaError_t)launch_mf_solve<D>(ma, h->mf11_grid, h->stream));
+    h->ctr.launches += 2;
+    h->ctr.reserved[5]++;                  // preconditioner solves
+    return 0;
+  }
   static int vec(Handle *h, int op, const Mask &m, const double *a_, const double *b_, double *o1, double *o2,
                  double *o3, double *o4, const double *y, double *o5 = nullptr) {
+    const bool regchol = h->opt.preconditioner == MMPGO_PRECON_REGULARIZED_CHOLESKY;
+    // the preconditioner is a per-node sparse solve, not a pose-local product: do it before the kernel that
+    // projects its result (CG_INIT, PRECOND) or between the two halves of CG_STEP (the solve needs the new r)
+    if (regchol && (op == V_CG_INIT || op == V_PRECOND)) RC(precon_solve(h, a_, m));
     Tiles tl; RC(make_tiles(h, m, &tl));
     VecArgs a; std::memset(&a, 0, sizeof(a));
     a.a = a_; a.b = b_; a.o1 = o1; a.o2 = o2; a.o3 = o3; a.o4 = o4; a.o5 = o5; a.y = y;
     a.pinv = h->d_pinv; a.precon = h->opt.preconditioner; a.coef = h->d_coef; a.partials = h->d_partials;
+    a.pre = h->pre_buf;
     launch_vec<D>(op, tl, a, h->stream);
     h->ctr.launches++; h->ctr.vector_passes++;
+    if (regchol && op == V_CG_STEP) {
+      RC(precon_solve(h, o2, m));          // o2 = r, just updated
+      RC(make_tiles(h, m, &tl));
+      a.a = o2;
+      launch_vec<D>(V_CG_PRE, tl, a, h->stream);
+      h->ctr.launches++; h->ctr.vector_passes++;
+    }
     return 0;
   }
 

@@ -123,6 +123,16 @@ struct Handle {
   std::vector<int> h_mf_perm;
   std::vector<int> mf_stage_jobs;      // per stage (forward stages, then backward): warp jobs, CTA jobs
   int mf_grid = 0;
+  // RegularizedCholesky preconditioner: factor of G11 + (lambda_max / max_cond) I per node, d scalar rows per pose
+  bool use_regchol = false;
+  MfDevice mf11;
+  int mf11_grid = 0;
+  bool mf11_level_sync = true;
+  int *d_mf11_perm = nullptr;            // scalar row (pose * d + r) -> position in the elimination order
+  double *rhs11 = nullptr;               // [NO d][d] right-hand side in elimination order
+  double *pre_buf = nullptr;             // [NO][PB] (G11 + reg)^{-1} r in pose-block layout (rotation rows)
+  int64_t mf11_nnz = 0;
+  std::vector<double> lambda_max;        // per local node
   bool mf_dry = false, mf_level_sync = false, mf_level_sync_auto = true;
   int64_t mf_nnz = 0, mf_entries = 0, mf_tasks = 0;
   int mf_height = 0, mf_supernodes = 0;

@@ -1063,7 +1063,12 @@ __device__ __forceinline__ void apply_precon(const VecArgs &a, int p, const doub
     for (int k = 0; k < D * D; ++k) v[k] = r[k];
     return;
   }
-  if (a.precon == 1) {
+  if (a.precon == 3) {
+    // RegularizedCholesky: reg_Chol_precon_.solve(Ydot) was done by the sparse sweeps (DPGOProblem.cpp:592-594)
+    const double *z = a.pre + (size_t)p * (D + 1) * D + D;
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) u[k] = z[k];
+  } else if (a.precon == 1) {
 #pragma unroll
     for (int rr = 0; rr < D; ++rr)
 #pragma unroll
@@ -1177,14 +1182,16 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
       double v[DD];
 #pragma unroll
       for (int k = D; k < PB; ++k) A4[k] = A4[k] + al * A2[k];
-      apply_precon<D>(a, p, A4 + D, Yb + D, v);
+      if (a.precon != 3) {
+        apply_precon<D>(a, p, A4 + D, Yb + D, v);
 #pragma unroll
-      for (int k = 0; k < D; ++k) A1[k] = 0.0;
+        for (int k = 0; k < D; ++k) A1[k] = 0.0;
 #pragma unroll
-      for (int k = 0; k < DD; ++k) { A1[D + k] = v[k]; sc[0] += A4[D + k] * v[k]; }
+        for (int k = 0; k < DD; ++k) { A1[D + k] = v[k]; sc[0] += A4[D + k] * v[k]; }
+      }
     }
     tile_store<D>(a.o2, p0, cnt, sm, A4);
-    tile_store<D>(a.o3, p0, cnt, sm, A1);
+    if (a.precon != 3) tile_store<D>(a.o3, p0, cnt, sm, A1);   // precon 3: v follows in V_CG_PRE, after the sweeps on the new r
   } else if (OP == V_RETRACT) {
     // a = x, b = s; o1 = xprop: rotation rows = proj(x.Y + s.Y), translation rows copied from x
     tile_load<D>(a.a, p0, cnt, sm, A1);
@@ -1200,6 +1207,19 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
       for (int k = 0; k < D; ++k) A1[k] = A1[k] + A2[k];   // t + s.t: first-order guess for recover_translations
     }
     tile_store<D>(a.o1, p0, cnt, sm, A1);
+  } else if (OP == V_CG_PRE) {
+    // a = r, o3 = v: v = Proj(Y, pre), s0 = r.v
+    tile_load<D>(a.a, p0, cnt, sm, A1);
+    tile_load<D>(a.y, p0, cnt, sm, Yb);
+    if (valid) {
+      double v[DD];
+      apply_precon<D>(a, p, A1 + D, Yb + D, v);
+#pragma unroll
+      for (int k = 0; k < D; ++k) A2[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < DD; ++k) { A2[D + k] = v[k]; sc[0] += A1[D + k] * v[k]; }
+    }
+    tile_store<D>(a.o3, p0, cnt, sm, A2);
   } else if (OP == V_PRECOND) {
     tile_load<D>(a.a, p0, cnt, sm, A1);
     tile_load<D>(a.y, p0, cnt, sm, Yb);
@@ -1213,9 +1233,29 @@ __global__ void __launch_bounds__(TILE) k_vec(Tiles tl, VecArgs a) {
     }
     if (a.o1) tile_store<D>(a.o1, p0, cnt, sm, A2);
   }
-  if (OP == V_CG_INIT || OP == V_CG_STEP || OP == V_PRECOND)
+  if (OP == V_CG_INIT || OP == V_CG_STEP || OP == V_PRECOND || OP == V_CG_PRE)
     block_reduce_store<3, TILE>(sc, a.partials + (size_t)tile * NS);
 }
+
+// rhs[perm[p d + r]][c] = src[p][1 + r][c]: the rotation rows of a pose-block vector in the elimination order of the
+// G11 factor (RegularizedCholesky preconditioner)
+template <int D>
+__global__ void __launch_bounds__(TILE) k_gather_rot(Tiles tl, const double *src, const int *perm, double *rhs) {
+  constexpr int PB = Dim<D>::PB;
+  const int tile = blockIdx.x;
+  if (tl.active && !tl.active[tl.node[tile]]) return;
+  const int p0 = tl.start[tile], n = tl.cnt[tile] * D * D;
+  for (int i = threadIdx.x; i < n; i += TILE) {
+    const int pl = i / (D * D), k = i % (D * D);
+    const int p = p0 + pl;
+    rhs[(size_t)__ldg(perm + p * D + k / D) * D + k % D] = src[(size_t)p * PB + D + k];
+  }
+}
+template <int D> void launch_gather_rot(const Tiles &tl, const double *src, const int *perm, double *rhs, cudaStream_t s) {
+  k_gather_rot<D><<<tl.n_tiles, TILE, 0, s>>>(tl, src, perm, rhs);
+}
+template void launch_gather_rot<2>(const Tiles &, const double *, const int *, double *, cudaStream_t);
+template void launch_gather_rot<3>(const Tiles &, const double *, const int *, double *, cudaStream_t);
 
 template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cudaStream_t s) {
 #define MMPGO_VEC_CASE(OP) case OP: k_vec<D, OP><<<tl.n_tiles, TILE, 0, s>>>(tl, a); break;
@@ -1223,7 +1263,7 @@ template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cuda
     MMPGO_VEC_CASE(V_CG_INIT) MMPGO_VEC_CASE(V_CG_STEP) MMPGO_VEC_CASE(V_CG_DIR)
     MMPGO_VEC_CASE(V_CG_FINAL) MMPGO_VEC_CASE(V_RETRACT) MMPGO_VEC_CASE(V_DOTS)
     MMPGO_VEC_CASE(V_COPY_ROT) MMPGO_VEC_CASE(V_COPY) MMPGO_VEC_CASE(V_PRECOND)
-    MMPGO_VEC_CASE(V_DIFFNORM) MMPGO_VEC_CASE(V_COPY_T)
+    MMPGO_VEC_CASE(V_DIFFNORM) MMPGO_VEC_CASE(V_COPY_T) MMPGO_VEC_CASE(V_CG_PRE)
   }
 #undef MMPGO_VEC_CASE
 }

@@ -138,7 +138,8 @@ enum VecOp {
   V_COPY = 7,      // out = a
   V_PRECOND = 8,   // out = P(a); s0 = out.out
   V_DIFFNORM = 10, // s0 = |a - b|^2 (all rows)
-  V_COPY_T = 13    // o1.t = a.t
+  V_COPY_T = 13,   // o1.t = a.t
+  V_CG_PRE = 14    // RegularizedCholesky, second half of V_CG_STEP: v = Proj(Y, pre); s0 = r.v   (a = r, o3 = v)
 };
 
 struct VecArgs {
@@ -147,7 +148,8 @@ struct VecArgs {
   double *o5;               // tCG: H s, accumulated alongside s (H s = sum alpha_k H p_k)
   const double *y;          // point for tangent projection (pose blocks)
   const double *pinv;       // [NO][d*d] block-Jacobi inverse or [NO][d] Jacobi
-  int precon;               // 0 none, 1 jacobi, 2 block jacobi
+  int precon;               // 0 none, 1 jacobi, 2 block jacobi, 3 regularized Cholesky (M^{-1} r precomputed in `pre`)
+  const double *pre;        // precon 3: (G11 + reg)^{-1} r in pose-block layout, written by the sparse sweeps before the launch
   const double *coef;       // [num_nodes][MAXC] per-node coefficients
   double *partials;
 };
@@ -223,6 +225,8 @@ template <int D> void launch_prox(const Tiles &tl, const ProxArgs &a, cudaStream
 template <int D> void launch_rescale(const Tiles &tl, const RescaleArgs &a, cudaStream_t s);
 template <int D> void launch_gfix(const Tiles &tl, const GFixArgs &a, cudaStream_t s);
 template <int D> void launch_vec(int op, const Tiles &tl, const VecArgs &a, cudaStream_t s);
+// rotation rows of a pose-block vector -> right-hand side of the G11 sweeps in elimination order
+template <int D> void launch_gather_rot(const Tiles &tl, const double *src, const int *perm, double *rhs, cudaStream_t s);
 void launch_reduce(int num_nodes, const int *node_tile_begin, const int *node_tile_end,
                    const double *partials, double *node_scal, cudaStream_t s);
 template <int D> void launch_edge_objective(int64_t n_edges, const int *idx, const double *val, const double *x,

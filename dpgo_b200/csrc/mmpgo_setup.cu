@@ -162,6 +162,63 @@ static bool small_inverse(int d, const double *M, double *out) {
   return true;
 }
 
+// Uploads a host factor (mmpgo_factor.cu) and sizes the persistent launch of its sweeps.  `rows_out`: for every
+// permuted position the row of the caller's output array it is scattered to (units of out_stride doubles);
+// null = the factor's own numbering.
+static int mf_upload(Handle *h, const MfFactor &F, int d, const std::vector<int> *rows_out, MfDevice &m, int *grid,
+                     bool *level_sync_auto, int64_t *tasks, std::vector<int> *stage_jobs) {
+  int rc = 0;
+  const int smem = (int)sizeof(double) * (MF_WARPS + 1) * MF_BUF * d;   // one front buffer per warp (+ one spare: the last warp's loops may overrun)
+  if (smem > 200 * 1024) return 1;
+  MfSn *sn_d; double *M_d, *MT_d; int *p0, *p1, *bi, *ip;
+  if ((rc = upload(h, &sn_d, F.sn))) return rc;
+  if ((rc = upload(h, &M_d, F.M))) return rc;
+  if ((rc = upload(h, &MT_d, F.MT))) return rc;
+  if ((rc = upload(h, &p0, F.pull0))) return rc;
+  if ((rc = upload(h, &p1, F.pull1))) return rc;
+  if ((rc = upload(h, &bi, F.bidx))) return rc;
+  if ((rc = upload(h, &ip, rows_out ? *rows_out : F.iperm))) return rc;
+  m.sn = sn_d; m.M = M_d; m.MT = MT_d; m.pull0 = p0; m.pull1 = p1; m.bidx = bi; m.iperm = ip;
+  for (int dir = 0; dir < 2; ++dir) {
+    MfJob *wj; int *ws;
+    if ((rc = upload(h, &wj, F.wjobs[dir]))) return rc;
+    if ((rc = upload(h, &ws, F.wstage[dir]))) return rc;
+    m.wjobs[dir] = wj; m.wstage[dir] = ws;
+    m.n_stage[dir] = (int)F.wstage[dir].size() - 1;
+    for (int st = 0; st < m.n_stage[dir]; ++st)
+      m.max_ctas = std::max(m.max_ctas, (F.wstage[dir][st + 1] - F.wstage[dir][st] + MF_WARPS - 1) / MF_WARPS);
+    if (tasks) *tasks += (int64_t)F.wjobs[dir].size();
+  }
+  if ((rc = dalloc(h, &m.y, (size_t)F.nrows * d))) return rc;
+  if ((rc = dalloc(h, &m.xp, (size_t)F.nrows * d))) return rc;
+  if ((rc = dalloc(h, &m.u, (size_t)std::max(F.urows, 1) * d))) return rc;
+  if ((rc = dalloc(h, &m.barrier, (size_t)4))) return rc;
+  {
+    MfFactor::Dep *dp;
+    if ((rc = upload(h, &dp, F.dep))) return rc;
+    m.dep = dp; m.n_sn = (int)F.sn.size();
+    if ((rc = dalloc(h, &m.done, (size_t)2 * F.sn.size() + 2))) return rc;
+  }
+  if ((rc = dalloc(h, &m.stage_ns, (size_t)(F.wstage[0].size() + F.wstage[1].size() + 2)))) return rc;
+  if (stage_jobs) {
+    stage_jobs->clear();
+    for (int dir = 0; dir < 2; ++dir)
+      for (size_t st = 0; st + 1 < F.wstage[dir].size(); ++st) {
+        stage_jobs->push_back(F.wstage[dir][st + 1] - F.wstage[dir][st]);
+        stage_jobs->push_back(0);
+      }
+  }
+  m.smem_bytes = smem;
+  const int mg = d == 2 ? mf_solve_max_grid<2>(h->opt.device, smem) : mf_solve_max_grid<3>(h->opt.device, smem);
+  if (mg <= 0) { set_error("occupancy query for the sparse direct solve failed"); return MMPGO_ERR_CUDA; }
+  *grid = std::max(1, std::min(mg, m.max_ctas));
+  // level barriers or per-supernode dependencies?  Same arithmetic, same bits.  With many jobs per warp (the 64
+  // nodes of the 1 M-pose grid on one GPU: 29) letting levels and nodes overlap wins (0.86 -> 0.77 ms per solve);
+  // with few (8 or 16 nodes: 5-7) the per-job acquire / release costs more than 28 barriers (0.48 vs 0.57 ms)
+  *level_sync_auto = (int64_t)F.wjobs[0].size() < (int64_t)20 * (*grid) * MF_WARPS;
+  return 0;
+}
+
 int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne, int64_t E, const int32_t *ei,
                      const int32_t *ej, const double *R, const double *t, const double *kappa,
                      const double *tau) {
@@ -487,56 +544,11 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
     }
     if (fits) {
       if (mf_factor(mats, 1, leaf, false, &F) != 0) { set_error("G00 is not positive definite"); return MMPGO_ERR_ARG; }
-      // shared memory: one front buffer of MF_BUF rows per warp (+ one spare: the last warp's loops may overrun)
-      const int smem = (int)sizeof(double) * (MF_WARPS + 1) * MF_BUF * d;
-      if (smem <= 200 * 1024) {
-        MfDevice &m = h->mf;
-        MfSn *sn_d; double *M_d, *MT_d; int *p0, *p1, *bi, *ip;
-        if ((rc = upload(h, &sn_d, F.sn))) return rc;
-        if ((rc = upload(h, &M_d, F.M))) return rc;
-        if ((rc = upload(h, &MT_d, F.MT))) return rc;
-        if ((rc = upload(h, &p0, F.pull0))) return rc;
-        if ((rc = upload(h, &p1, F.pull1))) return rc;
-        if ((rc = upload(h, &bi, F.bidx))) return rc;
-        if ((rc = upload(h, &ip, F.iperm))) return rc;
+      rc = mf_upload(h, F, d, nullptr, h->mf, &h->mf_grid, &h->mf_level_sync_auto, &h->mf_tasks, &h->mf_stage_jobs);
+      if (rc < 0) return rc;
+      if (rc == 0) {
         if ((rc = upload(h, &h->d_mf_perm, F.perm))) return rc;
         h->h_mf_perm = F.perm;
-        m.sn = sn_d; m.M = M_d; m.MT = MT_d; m.pull0 = p0; m.pull1 = p1; m.bidx = bi; m.iperm = ip;
-        for (int dir = 0; dir < 2; ++dir) {
-          MfJob *wj; int *ws;
-          if ((rc = upload(h, &wj, F.wjobs[dir]))) return rc;
-          if ((rc = upload(h, &ws, F.wstage[dir]))) return rc;
-          m.wjobs[dir] = wj; m.wstage[dir] = ws;
-          m.n_stage[dir] = (int)F.wstage[dir].size() - 1;
-          for (int st = 0; st < m.n_stage[dir]; ++st)
-            m.max_ctas = std::max(m.max_ctas, (F.wstage[dir][st + 1] - F.wstage[dir][st] + MF_WARPS - 1) / MF_WARPS);
-          h->mf_tasks += (int64_t)F.wjobs[dir].size();
-        }
-        if ((rc = dalloc(h, &m.y, (size_t)NO * d))) return rc;
-        if ((rc = dalloc(h, &m.xp, (size_t)NO * d))) return rc;
-        if ((rc = dalloc(h, &m.u, (size_t)std::max(F.urows, 1) * d))) return rc;
-        if ((rc = dalloc(h, &m.barrier, (size_t)4))) return rc;
-        {
-          MfFactor::Dep *dp;
-          if ((rc = upload(h, &dp, F.dep))) return rc;
-          m.dep = dp; m.n_sn = (int)F.sn.size();
-          if ((rc = dalloc(h, &m.done, (size_t)2 * F.sn.size() + 2))) return rc;
-        }
-        if ((rc = dalloc(h, &m.stage_ns, (size_t)(F.wstage[0].size() + F.wstage[1].size() + 2)))) return rc;
-        h->mf_stage_jobs.clear();
-        for (int dir = 0; dir < 2; ++dir)
-          for (size_t st = 0; st + 1 < F.wstage[dir].size(); ++st) {
-            h->mf_stage_jobs.push_back(F.wstage[dir][st + 1] - F.wstage[dir][st]);
-            h->mf_stage_jobs.push_back(0);
-          }
-        m.smem_bytes = smem;
-        const int mg = d == 2 ? mf_solve_max_grid<2>(h->opt.device, smem) : mf_solve_max_grid<3>(h->opt.device, smem);
-        if (mg <= 0) { set_error("occupancy query for the sparse direct solve failed"); return MMPGO_ERR_CUDA; }
-        h->mf_grid = std::max(1, std::min(mg, m.max_ctas));
-        // level barriers or per-supernode dependencies?  Same arithmetic, same bits.  With many jobs per warp (the 64
-        // nodes of the 1 M-pose grid on one GPU: 29) letting levels and nodes overlap wins (0.86 -> 0.77 ms per solve);
-        // with few (8 or 16 nodes: 5-7) the per-job acquire / release costs more than 28 barriers (0.48 vs 0.57 ms)
-        h->mf_level_sync_auto = (int64_t)F.wjobs[0].size() < (int64_t)20 * h->mf_grid * MF_WARPS;
         h->use_direct = true;
         h->mf_nnz = F.nnz; h->mf_entries = 2 * (int64_t)F.M.size(); h->mf_height = F.height;
         h->mf_supernodes = (int)F.sn.size();
@@ -545,6 +557,102 @@ int driver_set_graph(Handle *h, int d, int64_t N, int num_nodes, int nb, int ne,
         return MMPGO_ERR_UNSUPPORTED;
       }
     }
+  }
+
+  // ---- RegularizedCholesky preconditioner (the reference's default, DPGO_types.h:155): Cholesky factor of
+  // G11 + (lambda_max / max_cond) I per node (DPGOProblem.cpp:101-124), G11 = the rotation rows / columns of the
+  // majoriser G.  Same host factorisation and device sweeps as G00, d scalar rows per pose.
+  h->use_regchol = false;
+  if (h->opt.preconditioner == MMPGO_PRECON_REGULARIZED_CHOLESKY) {
+    const int64_t rows = (int64_t)NO * d;
+    std::vector<int> mptr((size_t)rows + A, 0), mcol;
+    std::vector<double> mval;
+    mcol.reserve(((size_t)nnz + NO) * d * d); mval.reserve(((size_t)nnz + NO) * d * d);
+    std::vector<MfMatrix> mats(A);
+    std::vector<size_t> ptr_off(A);
+    h->lambda_max.assign(A, 0.0);
+    size_t po = 0;
+    for (int a = 0; a < A; ++a) {
+      const int off = h->node_off[a], n0 = h->info[a].n0;
+      ptr_off[a] = po;
+      for (int p = 0; p < n0; ++p)
+        for (int r = 0; r < d; ++r) {
+          mptr[po + (size_t)p * d + r] = (int)mcol.size();
+          for (int c = 0; c < d; ++c) {
+            mcol.push_back(p * d + c);
+            mval.push_back(gdiag[(size_t)(off + p) * SYM + symi(std::max(1 + r, 1 + c), std::min(1 + r, 1 + c))]);
+          }
+          for (int s2 = rowptr[off + p]; s2 < rowptr[off + p + 1]; ++s2)
+            for (int c = 0; c < d; ++c) {
+              mcol.push_back((col[s2] - off) * d + c);
+              mval.push_back(blk[(size_t)s2 * BB + (1 + r) * Rr + 1 + c]);
+            }
+        }
+      mptr[po + (size_t)n0 * d] = (int)mcol.size();
+      po += (size_t)n0 * d + 1;
+    }
+    // lambda_max of every node's G11 (the reference asks Spectra for a loose estimate, tolerance 1e-4): power
+    // iteration on the positive semidefinite matrix, Rayleigh quotient stationary to 1e-6 relative
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int a = 0; a < A; ++a) {
+      const int n = h->info[a].n0 * d;
+      const int *ptr = &mptr[ptr_off[a]];
+      std::vector<double> v((size_t)n), w((size_t)n);
+      for (int i = 0; i < n; ++i) v[i] = 1.0 + 0.5 * std::sin(0.7 * i + 0.3);
+      double lam = 0.0;
+      for (int it = 0; it < 2000; ++it) {
+        double nv = 0.0;
+        for (int i = 0; i < n; ++i) nv += v[i] * v[i];
+        nv = 1.0 / std::sqrt(nv);
+        for (int i = 0; i < n; ++i) v[i] *= nv;
+        double rq = 0.0;
+        for (int i = 0; i < n; ++i) {
+          double t = 0.0;
+          for (int e = ptr[i]; e < ptr[i + 1]; ++e) t += mval[e] * v[mcol[e]];
+          w[i] = t; rq += t * v[i];
+        }
+        v.swap(w);
+        const bool stop = it > 8 && std::fabs(rq - lam) <= 1e-6 * std::fabs(rq);
+        lam = rq;
+        if (stop) break;
+      }
+      h->lambda_max[a] = lam;
+    }
+    // the regulariser goes onto the (first) diagonal entry of every row
+    for (int a = 0; a < A; ++a) {
+      const int n = h->info[a].n0 * d;
+      const int *ptr = &mptr[ptr_off[a]];
+      const double reg = h->lambda_max[a] / h->opt.reg_Cholesky_precon_max_condition_number;
+      for (int i = 0; i < n; ++i)
+        for (int e = ptr[i]; e < ptr[i + 1]; ++e)
+          if (mcol[e] == i) { mval[e] += reg; break; }
+      mats[a].n = n; mats[a].ptr = ptr; mats[a].col = mcol.data(); mats[a].val = mval.data(); mats[a].skip = false;
+    }
+    const int leaf11 = d == 3 ? 12 : 16;               // vertices (poses) per leaf: ~36 / 32 scalar columns
+    MfFactor F;
+    mf_factor(mats, d, leaf11, true, &F);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (16.0 * (double)F.nnz * 1.35 > 0.5 * (double)free_b || F.flops > 4e13) {
+      set_error("preconditioner = RegularizedCholesky: the sparse factor of G11 exceeds the memory / setup budget");
+      return MMPGO_ERR_UNSUPPORTED;
+    }
+    if (mf_factor(mats, d, leaf11, false, &F) != 0) { set_error("G11 + reg is not positive definite"); return MMPGO_ERR_ARG; }
+    // permuted position -> row of a pose-block array (d + 1 rows of d doubles per pose; rotation row r of pose p is
+    // row p (d + 1) + 1 + r), so that the backward sweep scatters straight into pose-block layout
+    std::vector<int> rows_out(F.iperm.size());
+    for (size_t i = 0; i < F.iperm.size(); ++i) rows_out[i] = (F.iperm[i] / d) * (d + 1) + 1 + F.iperm[i] % d;
+    int64_t tasks = 0;
+    rc = mf_upload(h, F, d, &rows_out, h->mf11, &h->mf11_grid, &h->mf11_level_sync, &tasks, nullptr);
+    if (rc != 0) {
+      if (rc > 0) { set_error("preconditioner = RegularizedCholesky: a front of the sparse factor does not fit shared memory"); rc = MMPGO_ERR_UNSUPPORTED; }
+      return rc;
+    }
+    if ((rc = upload(h, &h->d_mf11_perm, F.perm))) return rc;
+    if ((rc = dalloc(h, &h->rhs11, (size_t)rows * d))) return rc;
+    if ((rc = dalloc(h, &h->pre_buf, (size_t)NO * (d + 1) * d))) return rc;
+    h->use_regchol = true;
+    h->mf11_nnz = F.nnz;
   }
 
   // ---- upload

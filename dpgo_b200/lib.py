@@ -40,7 +40,7 @@ class Options(C.Structure):
         ("translation_solve_tol", C.c_double),
         ("translation_solve_max_iters", C.c_int32), ("device", C.c_int32),
         ("translation_solver", C.c_int32), ("rescale", C.c_int32), ("max_rescale_count", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("reg_Cholesky_precon_max_condition_number", C.c_double), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -71,7 +71,7 @@ class Counters(C.Structure):
 
 
 LOSS = {"trivial": 0, "none": 0, "huber": 1, "gm": 2, "geman-mcclure": 2, "welsch": 3}
-PRECON = {"None": 0, "Jacobi": 1, "BlockJacobi": 2}
+PRECON = {"None": 0, "Jacobi": 1, "BlockJacobi": 2, "RegularizedCholesky": 3}
 ALGORITHM = {"hash": 0, "star": 1}
 SCHEME = {"MM": 0, "AMM": 1}
 RESCALE = {"Static": 0, "Dynamic": 1}
@@ -115,6 +115,7 @@ SIGNATURES = {
     "mmpgo_star_objective": (C.c_int, [_P, _dp, _dp, _ip]),
     "mmpgo_graph_sizes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "mmpgo_solver_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "mmpgo_preconditioner_info": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mmpgo_stage_range": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mmpgo_solver_stage_times": (C.c_int, [_P, _dp, _ip, _ip, C.c_int32, _ip]),
     "mmpgo_profile_pass": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),

@@ -172,6 +172,13 @@ class _Driver:
         L.check(self.lib.mmpgo_translation_solve(self._h, L.dptr(rhs), L.dptr(t)))
         return t
 
+    def preconditioner_info(self, node):
+        """(lambda_max estimate of the node's G11, entries of the factor of all local G11 + reg I) of the
+        RegularizedCholesky preconditioner (DPGOProblem.cpp:101-124)."""
+        lam, nnz = C.c_double(), C.c_int64()
+        L.check(self.lib.mmpgo_preconditioner_info(self._h, node, C.byref(lam), C.byref(nnz)))
+        return lam.value, nnz.value
+
     def stage_range(self):
         """[lo, hi): the global pose ids whose rows initialize / evaluate_f / evaluate_grad copy to the device
         (the local nodes' own poses and their remote neighbours)."""

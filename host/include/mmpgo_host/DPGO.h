@@ -34,7 +34,7 @@ typedef double Scalar;
 
 enum class Loss { None = 0, Huber = 1, GemanMcClure = 2, Welsch = 3 };   // DPGO_types.h:67
 enum class Scheme { MM = 0, AMM = 1 };                                   // DPGO_types.h:70-75
-enum class Preconditioner { None = 0, Jacobi = 1, BlockJacobi = 2 };     // device path
+enum class Preconditioner { None = 0, Jacobi = 1, BlockJacobi = 2, RegularizedCholesky = 3 };   // DPGO_types.h:35-40 + the device path's block-Jacobi
 enum class Rescale { Static = 0, Dynamic = 1 };                          // DPGO_types.h:42-46
 
 /** One relative pose measurement i -> j (RelativePoseMeasurement.h:11-29); poses are GLOBAL ids,
@@ -67,6 +67,7 @@ struct Options {
   Scheme scheme = Scheme::AMM;
   Preconditioner preconditioner = Preconditioner::BlockJacobi;
   Scalar regularizer = 1e-11, loss_reg = 0.25;
+  Scalar reg_Cholesky_precon_max_condition_number = 1e6;   // DPGO_types.h:159
   Rescale rescale = Rescale::Static;     // what dist_pgo sets (dist_pgo.cpp:105); the struct's own default is Dynamic (:128)
   int max_rescale_count = 5;             // DPGO_types.h:131
   int device = 0;
@@ -76,6 +77,7 @@ struct Options {
     c->loss = (int)loss; c->scheme = (int)scheme; c->preconditioner = (int)preconditioner;
     c->regularizer = regularizer; c->loss_reg = loss_reg; c->device = device;
     c->rescale = (int)rescale; c->max_rescale_count = max_rescale_count;
+    c->reg_Cholesky_precon_max_condition_number = reg_Cholesky_precon_max_condition_number;
   }
 };
 

@@ -201,7 +201,8 @@ int main(int argc, char *argv[]) {
   }
   std::map<std::string, std::string> opt = {{"iters", "1000"}, {"dist_init", "true"}, {"loss", "trivial"},
                                              {"accelerated", "true"}, {"save", "true"}, {"algorithm", "hash"},
-                                             {"device", "0"}, {"dist_init_fallback", "false"}, {"per_node", "false"}};
+                                             {"device", "0"}, {"dist_init_fallback", "false"}, {"per_node", "false"},
+                                             {"preconditioner", "block_jacobi"}};
   for (int a = 1; a < argc; ++a) {
     std::string s = argv[a];
     if (s == "--help") {
@@ -219,6 +220,8 @@ int main(int argc, char *argv[]) {
                    "  --init arg                 text file with the initial iterate ((d+1)N rows of d numbers)\n"
                    "  --dist_init_fallback arg (=false)  with --dist_init true: use the centralised chordal initialisation\n"
                    "  --per_node arg (=false)    run the reference's loop with one driver object per node (DPGO::PerNode)\n"
+                   "  --preconditioner arg (=block_jacobi)  tCG preconditioner: \"block_jacobi\", \"regularized_cholesky\" (the\n"
+                   "                             reference's default, DPGO_types.h:155), \"jacobi\" or \"none\"\n"
                    "  --parse_only arg           only read the dataset and print its checksums\n";
       return 0;
     }
@@ -247,6 +250,17 @@ int main(int argc, char *argv[]) {
     return -1;
   }
   options.scheme = accelerated ? DPGO::Scheme::AMM : DPGO::Scheme::MM;
+  {
+    const std::string pre = opt["preconditioner"];
+    if (pre == "block_jacobi") options.preconditioner = DPGO::Preconditioner::BlockJacobi;
+    else if (pre == "regularized_cholesky") options.preconditioner = DPGO::Preconditioner::RegularizedCholesky;
+    else if (pre == "jacobi") options.preconditioner = DPGO::Preconditioner::Jacobi;
+    else if (pre == "none") options.preconditioner = DPGO::Preconditioner::None;
+    else {
+      std::cerr << " The preconditioner can only be \"block_jacobi\", \"regularized_cholesky\", \"jacobi\" or \"none\"." << std::endl;
+      return -1;
+    }
+  }
 
   try {
     int64_t num_poses = 0;

@@ -42,7 +42,12 @@ enum mmpgo_scheme { MMPGO_SCHEME_MM = 0, MMPGO_SCHEME_AMM = 1 };
 /* DPGO::Preconditioner, DPGO_types.h:35-40, plus the per-pose d x d
  * block-Jacobi preconditioner of the device path. */
 enum mmpgo_preconditioner { MMPGO_PRECON_NONE = 0, MMPGO_PRECON_JACOBI = 1,
-                            MMPGO_PRECON_BLOCK_JACOBI = 2 };
+                            MMPGO_PRECON_BLOCK_JACOBI = 2,
+                            /* the reference's default (DPGO_types.h:155): sparse Cholesky factor of
+                             * G11 + (lambda_max / max_cond) I per node (DPGOProblem.cpp:101-124), factored on the host
+                             * at mmpgo_set_graph like G00 and applied by the same supernodal sweeps.  Exact and
+                             * ~10x the bytes of a block-Jacobi application per tCG iteration. */
+                            MMPGO_PRECON_REGULARIZED_CHOLESKY = 3 };
 /* How G00 u = rhs is solved for nodes with more than dense_solve_max_n poses (the reference
  * keeps a CHOLMOD factor of G00, DPGOProblem.cpp:93).  DIRECT: sparse Cholesky (nested dissection,
  * multifrontal, factored at mmpgo_set_graph) applied by level-scheduled supernodal sweeps -- exact
@@ -92,7 +97,8 @@ typedef struct mmpgo_options {
   int32_t rescale;               /* mmpgo_rescale: DPGO::Rescale (DPGO_types.h:42-46, Options::rescale :128); dist_pgo
                                     pins Static (dist_pgo.cpp:105), which is the default here */
   int32_t max_rescale_count;     /* 5 (DPGO_types.h:131) */
-  int32_t reserved[4];
+  double reg_Cholesky_precon_max_condition_number;   /* 1e6 (DPGO_types.h:159) */
+  int32_t reserved[2];
 } mmpgo_options;
 
 /* DPGOResult scalars a caller of results() reads (DPGO_types.h:204-322). */
@@ -116,7 +122,7 @@ typedef struct mmpgo_counters {
   int64_t tcg_iterations, tnt_iterations;
   int64_t vector_passes;
   int64_t reserved[7];            /* [0] pose-iterations of the G00 PCG, [1] solves served by the small-shard PCG kernel,
-                                     [2] solves served by the sparse direct kernel, [3] PCG node solves that stopped on
+                                     [2] solves served by the sparse direct kernel, [5] RegularizedCholesky preconditioner solves, [3] PCG node solves that stopped on
                                      translation_solve_max_iters above the tolerance, [4] most PCG iterations one node took */
 } mmpgo_counters;
 
@@ -244,6 +250,11 @@ int mmpgo_graph_sizes(mmpgo_handle h, int64_t *sizes);
  * is dense), nnz(L) of the sparse factor, stored factor entries (both copies), separator-tree height,
  * supernodes, jobs per solve, persistent CTAs, poses solved by the dense inverse} */
 int mmpgo_solver_info(mmpgo_handle h, int64_t *info);
+/* RegularizedCholesky preconditioner of a local node (DPGOProblem.cpp:101-124): the estimate of the largest
+ * eigenvalue of G11 the regulariser lambda_max / reg_Cholesky_precon_max_condition_number was built from (the
+ * reference asks Spectra for it to 1e-4), and the entries of the Cholesky factor of all local nodes' G11 + reg I.
+ * MMPGO_ERR_STATE when the handle runs another preconditioner. */
+int mmpgo_preconditioner_info(mmpgo_handle h, int32_t node, double *lambda_max, int64_t *factor_nnz);
 /* [lo, hi): the global pose ids whose rows of a host iterate are copied to the device by mmpgo_initialize /
  * mmpgo_evaluate_f / mmpgo_evaluate_grad: the own poses of the local nodes and their remote neighbours. */
 int mmpgo_stage_range(mmpgo_handle h, int64_t *lo, int64_t *hi);

@@ -26,11 +26,15 @@ def run_both(g, num_nodes, X0, iters, loss="trivial", algorithm="hash", scheme="
     oopts = odpgo.Options(loss=LOSS_TO_ORACLE[loss], scheme=scheme, preconditioner=preconditioner,
                           **{k: v for k, v in kw.items() if hasattr(odpgo.Options(), k)})
     meas = to_measurements(g)
-    ref = odist.run(meas, g.num_poses, num_nodes, oopts, X0, iters, algorithm)
     copts = D.Options(loss=loss, scheme=scheme, preconditioner=preconditioner,
                       **{k: v for k, v in kw.items()})
     cls = D.DPGOStar if algorithm == "star" else D.DPGOHash
     drv = cls(g, num_nodes, copts)
+    if preconditioner == "RegularizedCholesky":
+        # the regulariser is lambda_max(G11) / 1e6 with lambda_max a LOOSE estimate in the reference (Spectra, tolerance
+        # 1e-4, DPGOProblem.cpp:114-118): both sides get the library's estimate, which is also checked against scipy's
+        oopts.lambda_max_override = [drv.preconditioner_info(a)[0] for a in range(num_nodes)]
+    ref = odist.run(meas, g.num_poses, num_nodes, oopts, X0, iters, algorithm)
     assert drv.initialize(X0) == 0
     assert drv.update() == 0
     fn = [[drv.node_scalars(a).fobj for a in range(num_nodes)]]

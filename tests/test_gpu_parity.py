@@ -556,3 +556,35 @@ def test_pcg_reports_a_solve_that_stops_on_max_iters(kernel):
     rcs = [drv.update(), drv.iterate(), drv.update()]
     assert -5 in rcs and all(rc in (0, -5) for rc in rcs)
     assert drv.node_scalars(0).translation_solve_iters == 5
+
+
+@pytest.mark.parametrize("alg,loss,d", [("hash", "trivial", 3), ("star", "huber", 3), ("hash", "gm", 2)])
+def test_regularized_cholesky_preconditioner(alg, loss, d):
+    """Preconditioner::RegularizedCholesky, the reference's default (DPGO_types.h:155; DPGOProblem.cpp:101-124,
+    592-594): the Cholesky factor of G11 + (lambda_max / 1e6) I applied inside every truncated-CG iteration.  On the
+    device: the multifrontal factor of every node's G11 (d scalar rows per pose) and the supernodal sweeps of the
+    translation solve.  Same tolerances as the block-Jacobi runs; the largest-eigenvalue estimate is checked against
+    scipy's."""
+    import scipy.sparse.linalg as spla
+    from oracle import dpgo as odpgo
+    from oracle import g2o as og2o
+    if d == 3:
+        g, _, X0 = D.grid3d(7, 6, 5, seed=21)
+    else:
+        g, _, X0 = D.city2d(14, 10, seed=21)
+    nodes = 4
+    out = parity.run_both(g, nodes, X0, 12, loss=loss, algorithm=alg, preconditioner="RegularizedCholesky")
+    _check(out, d)
+    drv = out["drv"]
+    c = drv.counters()
+    assert c.reserved[5] > 0                                   # the sparse preconditioner solves ran
+    assert c.tcg_iterations > 0 or d == 2                      # (the SE(2) case converges without a tCG step)
+    per_node, g_index, _ = og2o.partition(g.num_poses, nodes, parity.to_measurements(g))
+    for a in range(nodes):
+        prob = odpgo.DPGOProblem(a, per_node[a], odpgo.Options(loss=loss, preconditioner="None"))
+        want = float(spla.eigsh(prob.G11, k=1, which="LA", tol=1e-10, return_eigenvectors=False)[0])
+        lam, nnz = drv.preconditioner_info(a)
+        assert abs(lam - want) <= 2e-4 * want and nnz > 0      # the reference's own tolerance is 1e-4
+    # the default (block-Jacobi) handle does not carry the factor
+    with pytest.raises(D.lib.MmpgoError):
+        D.DPGOHash(g, nodes).preconditioner_info(0)
