@@ -230,7 +230,7 @@ template <int D> struct Drv {
         CK(cudaMemcpyAsync(h->d_active2, mp.data(), sizeof(int) * mp.size(), cudaMemcpyHostToDevice, h->stream));
         ma.active = h->d_active2;
       }
-      ma.rhs = h->rhs_t; ma.out = xio; ma.out_stride = PB; ma.sign = -1.0; ma.dry = h->mf_dry ? 1 : 0; ma.level_sync = (h->mf_level_sync || h->mf_level_sync_auto) ? 1 : 0;
+      ma.rhs = h->rhs_t; ma.out = xio; ma.out_stride = PB; ma.sign = -1.0; ma.dry = h->mf_dry ? 1 : 0; ma.level_sync = h->mf_force_dep ? 0 : (h->mf_level_sync || h->mf_level_sync_auto) ? 1 : 0;
       CK((cudaError_t)launch_mf_solve<D>(ma, h->mf_grid, h->stream));
       h->ctr.launches++;
       h->ctr.reserved[2]++;                                   // solves served by the sparse direct kernel
@@ -1353,16 +1353,17 @@ template <int D> static int profile_pass(Handle *h, int kind, int reps, float *m
       int nb = 0;
       launch_edge_objective<D>(h->n_edges_owned, h->d_eidx, h->d_eval, Xk, h->opt.loss, h->opt.loss_reg, h->d_block_partials,
                                &nb, h->stream);
-    } else if (kind == 8 || kind == 9 || kind == 10) {
+    } else if (kind >= 8 && kind <= 11) {
       h->mf_dry = kind == 9;                 // 9: the sparse direct solve's stages and barriers without its jobs
       h->mf_level_sync = kind == 9 || kind == 10;   // 10: with a grid barrier per level (mmpgo_solver_stage_times)
+      h->mf_force_dep = kind == 11;          // 11: with per-supernode dependencies whatever the automatic choice is
       // one cold translation solve on scratch (rhs = whatever recover_t left), fixed iteration count
       const double tol = h->opt.translation_solve_tol; const int mi = h->opt.translation_solve_max_iters;
       if (getenv("MMPGO_TS_ITERS")) { h->opt.translation_solve_tol = 0.0; h->opt.translation_solve_max_iters = atoi(getenv("MMPGO_TS_ITERS")); }
       h->ts_grid_override = getenv("MMPGO_TS_GRID") ? atoi(getenv("MMPGO_TS_GRID")) : 0;
       int rc = Dr::solve_t(h, h->xprop, allm, false);
       h->opt.translation_solve_tol = tol; h->opt.translation_solve_max_iters = mi; h->ts_grid_override = 0;
-      h->mf_dry = false; h->mf_level_sync = false;
+      h->mf_dry = false; h->mf_level_sync = false; h->mf_force_dep = false;
       if (rc) return rc;
       h->ctr.launches--;
     } else {

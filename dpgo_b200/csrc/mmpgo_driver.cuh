@@ -133,7 +133,7 @@ struct Handle {
   double *pre_buf = nullptr;             // [NO][PB] (G11 + reg)^{-1} r in pose-block layout (rotation rows)
   int64_t mf11_nnz = 0;
   std::vector<double> lambda_max;        // per local node
-  bool mf_dry = false, mf_level_sync = false, mf_level_sync_auto = true;
+  bool mf_dry = false, mf_level_sync = false, mf_level_sync_auto = true, mf_force_dep = false;
   int64_t mf_nnz = 0, mf_entries = 0, mf_tasks = 0;
   int mf_height = 0, mf_supernodes = 0;
   int64_t dense_poses = 0;

@@ -35,15 +35,34 @@ __device__ __forceinline__ void red_release_u32(unsigned *p, unsigned v) {
 }
 // lane 0 waits until `*ctr` has reached `need` (the jobs this one depends on have published their results); the
 // other lanes follow through the warp barrier.  A wait of seconds means a broken dependency list: trap rather than hang.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void wait_count(const unsigned *ctr, unsigned need) {
-  // back off while waiting: thousands of warps polling the L2 would slow down the ones that work
+  // back off while waiting: thousands of warps polling the L2 would slow down the ones that work.  The polls are
+  // relaxed loads (an acquire load invalidates the SM's L1 at every poll: 6.3 M CCTL.IVALL per solve in the ncu
+  // capture of the first version); one acquire fence follows when the count is there.
   long long spins = 0;
   unsigned ns = 64;
-  while (ld_acquire_u32(ctr) < need) {
+  while (ld_relaxed_u32(ctr) < need) {
     __nanosleep(ns);
     if (ns < 1024) ns *= 2;
     if (++spins > (1ll << 21)) __trap();
   }
+}
+// What a job waits for before it may read what other jobs wrote (nothing in level-barrier mode).  Lane 0 polls,
+// the acquire fence orders the reads of the whole warp (through the warp barrier) after the counters.
+struct JobWait { const unsigned *c0, *c1; unsigned n0, n1; };
+__device__ __forceinline__ void job_wait(const JobWait &w, int lane) {
+  if (w.c0 == nullptr && w.c1 == nullptr) return;
+  if (lane == 0) {
+    if (w.c0) wait_count(w.c0, w.n0);
+    if (w.c1) wait_count(w.c1, w.n1);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+  __syncwarp();
 }
 
 // all threads of all CTAs; `target` counts arrivals since the launch (the counter is zeroed before it)
@@ -126,61 +145,88 @@ template <int D> __device__ __forceinline__ void slice_sum(double (&acc)[D], int
 
 // rows [j0, j0 + cnt) of the front's forward right-hand side -> buf[0 .. cnt), zero beyond k.  cnt <= MF_BLK: the
 // (at most four) rows of a lane are fetched together -- first every index, then every value -- instead of one
-// dependent chain after the other.
+// dependent chain after the other.  Two halves: `pre` fetches what does not depend on other jobs (pull indices,
+// the permuted right-hand side) and may run BEFORE the job waits for its children; `post` adds the children's
+// update rows and fills the buffer.
+template <int D> struct FwdStage { int p0[MF_BLK / 32], p1[MF_BLK / 32]; double v[MF_BLK / 32][D]; };
 template <int D>
-__device__ __forceinline__ void stage_forward(const MfSolveArgs &a, const MfSn &sn, int j0, int cnt, double *buf, int lane) {
+__device__ __forceinline__ void stage_forward_pre(const MfSolveArgs &a, const MfSn &sn, int j0, int cnt, int lane, FwdStage<D> &st) {
   const MfDevice &f = a.f;
   constexpr int U = MF_BLK / 32;
-  int p0[U], p1[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int j = j0 + lane + 32 * u;
-    p0[u] = -1; p1[u] = -1;
-    if (sn.nchild && lane + 32 * u < cnt && j < sn.k) { p0[u] = __ldg(f.pull0 + sn.rowoff + j); p1[u] = __ldg(f.pull1 + sn.rowoff + j); }
+    st.p0[u] = -1; st.p1[u] = -1;
+    if (sn.nchild && lane + 32 * u < cnt && j < sn.k) { st.p0[u] = __ldg(f.pull0 + sn.rowoff + j); st.p1[u] = __ldg(f.pull1 + sn.rowoff + j); }
   }
-  double v[U][D];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int j = j0 + lane + 32 * u;
     const bool on = lane + 32 * u < cnt && j < sn.k;
 #pragma unroll
-    for (int c = 0; c < D; ++c) v[u][c] = on ? a.rhs[(size_t)(sn.c0 + j) * D + c] : 0.0;
+    for (int c = 0; c < D; ++c) st.v[u][c] = on ? a.rhs[(size_t)(sn.c0 + j) * D + c] : 0.0;
   }
+}
+template <int D>
+__device__ __forceinline__ void stage_forward_post(const MfSolveArgs &a, int cnt, double *buf, int lane, FwdStage<D> &st) {
+  const MfDevice &f = a.f;
+  constexpr int U = MF_BLK / 32;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    if (p0[u] >= 0) {
+    if (st.p0[u] >= 0) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) v[u][c] += __ldcg(f.u + (size_t)p0[u] * D + c);
+      for (int c = 0; c < D; ++c) st.v[u][c] += __ldcg(f.u + (size_t)st.p0[u] * D + c);
     }
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    if (p1[u] >= 0) {
+    if (st.p1[u] >= 0) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) v[u][c] += __ldcg(f.u + (size_t)p1[u] * D + c);
+      for (int c = 0; c < D; ++c) st.v[u][c] += __ldcg(f.u + (size_t)st.p1[u] * D + c);
     }
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (lane + 32 * u < cnt) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) buf[(lane + 32 * u) * D + c] = v[u][c];
+      for (int c = 0; c < D; ++c) buf[(lane + 32 * u) * D + c] = st.v[u][c];
     }
   }
 }
-// rows [i0, i0 + cnt) of [y_s; -x_boundary] -> buf[0 .. cnt), zero beyond R; cnt <= MF_BLK, fetched like stage_forward
 template <int D>
-__device__ __forceinline__ void stage_backward(const MfSolveArgs &a, const MfSn &sn, int i0, int cnt, double *buf, int lane) {
+__device__ __forceinline__ void stage_forward(const MfSolveArgs &a, const MfSn &sn, int j0, int cnt, double *buf, int lane) {
+  FwdStage<D> st;
+  stage_forward_pre<D>(a, sn, j0, cnt, lane, st);
+  stage_forward_post<D>(a, cnt, buf, lane, st);
+}
+// rows [i0, i0 + cnt) of [y_s; -x_boundary] -> buf[0 .. cnt), zero beyond R; cnt <= MF_BLK, fetched like stage_forward
+template <int D> struct BwdStage { const double *src[MF_BLK / 32]; };
+// `pre`: where every row comes from (the boundary rows through the index list: static data, may be fetched before the
+// job waits for its parent); `post`: the values (own y, the ancestors' x)
+template <int D>
+__device__ __forceinline__ void stage_backward_pre(const MfSolveArgs &a, const MfSn &sn, int i0, int cnt, int lane, BwdStage<D> &st) {
   const MfDevice &f = a.f;
   constexpr int U = MF_BLK / 32;
-  const double *src[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int i = i0 + lane + 32 * u;
-    src[u] = nullptr;
+    st.src[u] = nullptr;
     if (lane + 32 * u < cnt && i < sn.R)
-      src[u] = i < sn.k ? f.y + (size_t)(sn.c0 + i) * D : f.xp + (size_t)__ldg(f.bidx + sn.boff + i - sn.k) * D;
+      st.src[u] = i < sn.k ? f.y + (size_t)(sn.c0 + i) * D : f.xp + (size_t)__ldg(f.bidx + sn.boff + i - sn.k) * D;
   }
+}
+template <int D>
+__device__ __forceinline__ void stage_backward_post(const MfSn &sn, int i0, int cnt, double *buf, int lane, const BwdStage<D> &st);
+template <int D>
+__device__ __forceinline__ void stage_backward(const MfSolveArgs &a, const MfSn &sn, int i0, int cnt, double *buf, int lane) {
+  BwdStage<D> st;
+  stage_backward_pre<D>(a, sn, i0, cnt, lane, st);
+  stage_backward_post<D>(sn, i0, cnt, buf, lane, st);
+}
+template <int D>
+__device__ __forceinline__ void stage_backward_post(const MfSn &sn, int i0, int cnt, double *buf, int lane, const BwdStage<D> &st) {
+  constexpr int U = MF_BLK / 32;
+  const double *const *src = st.src;
   double v[U][D];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -234,14 +280,20 @@ __device__ __forceinline__ void backward_store(const MfSolveArgs &a, const MfSn 
 
 // forward job: [y_s; -du] = M_s f1 for rows [r0, r0 + n)
 template <int D>
-__device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn, int r0, int n, double *buf, int lane) {
+__device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn, int r0, int n, double *buf, int lane,
+                                            const JobWait &w) {
   const MfDevice &f = a.f;
   const int k = sn.k, kp = (k + 1) & ~1, Rp = (sn.R + 1) & ~1;
   const double *Mc = f.M + sn.moff;                       // column-major, leading dimension Rp
   double a0[D], a1[D];
   if (k <= MF_KS) {
     // one lane per pair of rows, passes of 64 rows; the whole right-hand side fits the buffer
-    stage_forward<D>(a, sn, 0, kp, buf, lane);
+    {
+      FwdStage<D> st;
+      stage_forward_pre<D>(a, sn, 0, kp, lane, st);        // indices and b: in flight while the job waits for its children
+      job_wait(w, lane);
+      stage_forward_post<D>(a, kp, buf, lane, st);
+    }
     __syncwarp();
     for (int p0 = r0; p0 < r0 + n; p0 += 64) {
       const int i = p0 + 2 * lane;
@@ -268,11 +320,21 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
 #pragma unroll
     for (int c = 0; c < D; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
     double g0[D], g1[D];
-    pull_pair<D>(a, sn, i, r0 + n, mine && q == 0, g0, g1);
+    {
+      FwdStage<D> st;
+      stage_forward_pre<D>(a, sn, 0, min(MF_BLK, kp), lane, st);
+      job_wait(w, lane);
+      pull_pair<D>(a, sn, i, r0 + n, mine && q == 0, g0, g1);
+      __syncwarp();
+      stage_forward_post<D>(a, min(MF_BLK, kp), buf, lane, st);
+      __syncwarp();
+    }
     for (int cb = 0; cb < emax; cb += MF_BLK) {
-      __syncwarp();
-      stage_forward<D>(a, sn, cb, min(MF_BLK, kp - cb), buf, lane);
-      __syncwarp();
+      if (cb > 0) {
+        __syncwarp();
+        stage_forward<D>(a, sn, cb, min(MF_BLK, kp - cb), buf, lane);
+        __syncwarp();
+      }
       const int b = cb + q * MF_QW, em = min(emax, b + MF_QW);
       dot_pair<D>(Mc + i, (size_t)Rp, buf - cb * D, b, mine ? em : b, em, a0, a1);
     }
@@ -288,13 +350,19 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
 
 // backward job: x_s = M_s^T [y_s; -x_boundary] for columns [c0, c0 + n)
 template <int D>
-__device__ __forceinline__ void backward_job(const MfSolveArgs &a, const MfSn &sn, int c0, int n, double *buf, int lane) {
+__device__ __forceinline__ void backward_job(const MfSolveArgs &a, const MfSn &sn, int c0, int n, double *buf, int lane,
+                                             const JobWait &w) {
   const MfDevice &f = a.f;
   const int R = sn.R, Rp = (R + 1) & ~1, kp = (sn.k + 1) & ~1;
   const double *Mr = f.MT + sn.mtoff;                     // row-major, leading dimension kp
   double a0[D], a1[D];
   if (R <= MF_RS) {
-    stage_backward<D>(a, sn, 0, Rp, buf, lane);
+    {
+      BwdStage<D> st;
+      stage_backward_pre<D>(a, sn, 0, Rp, lane, st);       // the boundary index list: in flight while the job waits for its parent
+      job_wait(w, lane);
+      stage_backward_post<D>(sn, 0, Rp, buf, lane, st);
+    }
     __syncwarp();
     for (int p0 = c0; p0 < c0 + n; p0 += 64) {            // rows before p0 multiply zeros of every column of the pass
       const int j = p0 + 2 * lane;
@@ -315,7 +383,14 @@ __device__ __forceinline__ void backward_job(const MfSolveArgs &a, const MfSn &s
     for (int c = 0; c < D; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
     for (int rb = c0; rb < R; rb += MF_BLK) {             // rows before c0 multiply zeros of the job's columns
       __syncwarp();
-      stage_backward<D>(a, sn, rb, min(MF_BLK, Rp - rb), buf, lane);
+      if (rb == c0) {
+        BwdStage<D> st;
+        stage_backward_pre<D>(a, sn, rb, min(MF_BLK, Rp - rb), lane, st);
+        job_wait(w, lane);
+        stage_backward_post<D>(sn, rb, min(MF_BLK, Rp - rb), buf, lane, st);
+      } else {
+        stage_backward<D>(a, sn, rb, min(MF_BLK, Rp - rb), buf, lane);
+      }
       __syncwarp();
       const int b = rb + q * MF_QW, em = min(R, b + MF_QW);
       dot_pair<D>(Mr + j, (size_t)kp, buf - rb * D, b, mine ? em : b, em, a0, a1);
@@ -371,14 +446,13 @@ __global__ void __launch_bounds__(MF_THREADS, 1) k_mf_solve(MfSolveArgs a) {
         if (tn < w1) nxt = wj[tn];
         const MfSn sn = f.sn[cur.sn];
         if (a.dry || (a.active && !a.active[sn.node])) { t = tn; cur = nxt; continue; }
+        JobWait w = {nullptr, nullptr, 0u, 0u};
         if (!a.level_sync) {
-          if (lane == 0) {
-            if (cur.wait0 >= 0) wait_count(f.done + cur.wait0, (unsigned)cur.need0);
-            if (cur.wait1 >= 0) wait_count(f.done + cur.wait1, (unsigned)cur.need1);
-          }
-          __syncwarp();
+          if (cur.wait0 >= 0) { w.c0 = f.done + cur.wait0; w.n0 = (unsigned)cur.need0; }
+          if (cur.wait1 >= 0) { w.c1 = f.done + cur.wait1; w.n1 = (unsigned)cur.need1; }
         }
-        if (dir == 0) forward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane); else backward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane);
+        // the job waits for the supernodes it depends on INSIDE, after it has requested what does not depend on them
+        if (dir == 0) forward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane, w); else backward_job<D>(a, sn, cur.r0, cur.n, wbuf, lane, w);
         if (!a.level_sync) {
           __syncwarp();
           if (lane == 0) red_release_u32(done + cur.sn, 1u);

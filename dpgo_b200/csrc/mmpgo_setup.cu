@@ -212,10 +212,12 @@ static int mf_upload(Handle *h, const MfFactor &F, int d, const std::vector<int>
   const int mg = d == 2 ? mf_solve_max_grid<2>(h->opt.device, smem) : mf_solve_max_grid<3>(h->opt.device, smem);
   if (mg <= 0) { set_error("occupancy query for the sparse direct solve failed"); return MMPGO_ERR_CUDA; }
   *grid = std::max(1, std::min(mg, m.max_ctas));
-  // level barriers or per-supernode dependencies?  Same arithmetic, same bits.  With many jobs per warp (the 64
-  // nodes of the 1 M-pose grid on one GPU: 29) letting levels and nodes overlap wins (0.86 -> 0.77 ms per solve);
-  // with few (8 or 16 nodes: 5-7) the per-job acquire / release costs more than 28 barriers (0.48 vs 0.57 ms)
-  *level_sync_auto = (int64_t)F.wjobs[0].size() < (int64_t)20 * (*grid) * MF_WARPS;
+  // level barriers or per-supernode dependencies?  Same arithmetic, same bits.  Since a job requests its static
+  // operands (pull indices, right-hand side, boundary index list) before it waits and polls with relaxed loads, the
+  // dependency schedule wins at every shard size measured (per solve, barriers vs dependencies: 64 nodes of the
+  // 1 M-pose grid on one GPU 0.86 vs 0.64 ms; 32 nodes 0.63 vs 0.44; 16 nodes 0.52 vs 0.37; 8 nodes 0.47 vs 0.35);
+  // the barrier schedule stays for the per-level timers (mmpgo_solver_stage_times, profile kind 10)
+  *level_sync_auto = false;
   return 0;
 }
 

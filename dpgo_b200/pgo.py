@@ -206,7 +206,7 @@ class _Driver:
         return list(zip(us.tolist(), wj.tolist(), cj.tolist()))
 
     KERNEL_KINDS = {"k2_eval": 0, "k2_grad": 1, "k1_inter": 2, "k3_prox": 3, "edge_objective": 4,
-                    "k2_hv": 6, "k2_g01": 7, "g00_solve": 8, "g00_solve_dry": 9, "g00_solve_levels": 10}
+                    "k2_hv": 6, "k2_g01": 7, "g00_solve": 8, "g00_solve_dry": 9, "g00_solve_levels": 10, "g00_solve_deps": 11}
 
     def profile_pass(self, kind, reps=20):
         """Average device milliseconds of one launch of a hot kernel (CUDA events on

@@ -286,7 +286,8 @@ int mmpgo_mf_host_solve(int32_t n, const int32_t *ptr, const int32_t *col, const
  * kind: 0 K2 evaluate, 1 K2 gradient, 2 K1 inter-edge pass, 3 K3 fused proximal,
  * 4 edge-parallel objective, 6 K2 Hessian-vector, 7 K2 G01 pass, 8 one K2b translation solve (one persistent
  * launch); sparse direct solve only: 9 its levels and barriers without the jobs, 10 the solve with a grid barrier
- * after every level of the separator tree (what mmpgo_solver_stage_times reports). */
+ * after every level of the separator tree (what mmpgo_solver_stage_times reports), 11 the solve with per-supernode
+ * dependencies instead (the library picks one of the two by the number of jobs per resident warp). */
 int mmpgo_profile_pass(mmpgo_handle h, int32_t kind, int32_t reps, float *ms_avg);
 int mmpgo_get_counters(mmpgo_handle h, mmpgo_counters *out);
 int mmpgo_reset_counters(mmpgo_handle h);

@@ -588,3 +588,21 @@ def test_regularized_cholesky_preconditioner(alg, loss, d):
     # the default (block-Jacobi) handle does not carry the factor
     with pytest.raises(D.lib.MmpgoError):
         D.DPGOHash(g, nodes).preconditioner_info(0)
+
+
+def test_reference_default_options_on_a_reference_dataset():
+    """DPGO::Options as the struct declares them (DPGO_types.h:128, 155): Rescale::Dynamic and the
+    RegularizedCholesky preconditioner, AMM-PGO* with the Huber loss on the reference's smallGrid3D dataset
+    (the graph of the golden fixture), 40 iterations against the oracle run live with the same options."""
+    g, z = load_golden("smallGrid3D_n4_huber_star")
+    out = parity.run_both(g, 4, z["X0"], 40, loss="huber", algorithm="star", preconditioner="RegularizedCholesky",
+                          rescale="Dynamic")
+    _check(out, g.d)
+    # ... and dist_pgo's own combination (Static rescale, dist_pgo.cpp:105) with the default preconditioner
+    out = parity.run_both(g, 4, z["X0"], 40, loss="huber", algorithm="star", preconditioner="RegularizedCholesky")
+    _check(out, g.d)
+    # sharded handles follow the same trajectory bit for bit (the factor of a node does not depend on its neighbours' GPU)
+    from inproc_world import InProcWorld
+    world = InProcWorld(g, 4, 2, "star", loss="huber", preconditioner="RegularizedCholesky")
+    _, X = world.run(z["X0"], 40)
+    assert np.array_equal(X, out["X_gpu"])

@@ -20,6 +20,7 @@ if solver == "direct" and "nodry" not in sys.argv:
         print("dry stage %8.1f us  warp jobs %7d" % (us, wj))
 print("g00_solve ms:", drv.profile_pass("g00_solve", reps))
 if solver == "direct":
+    print("g00_solve with per-supernode dependencies ms:", drv.profile_pass("g00_solve_deps", reps))
     print("g00_solve with a grid barrier per level ms:", drv.profile_pass("g00_solve_levels", reps))
 for us, wj, cj in drv.solver_stage_times():
     print("stage %8.1f us  warp jobs %7d  cta jobs %5d" % (us, wj, cj))
