@@ -256,15 +256,45 @@ __device__ __forceinline__ void forward_store(const MfSolveArgs &a, const MfSn &
     for (int c = 0; c < D; ++c) f.u[(size_t)(sn.uoff + i - sn.k) * D + c] = f2[c] - acc[c];
   }
 }
-// update rows pulled by the boundary rows i, i + 1 of a front (zero for columns and for rows beyond `end`)
+// update rows pulled by the boundary rows i, i + 1 of a front (zero for columns and for rows beyond `end`), in two
+// halves: the children's row numbers (static: may be fetched before the job waits for the children) and the values
+struct PullIdx { int a0, a1, b0, b1; };
+__device__ __forceinline__ void pull_idx(const MfSolveArgs &a, const MfSn &sn, int i, int end, bool on, PullIdx &pi) {
+  const MfDevice &f = a.f;
+  pi.a0 = pi.a1 = pi.b0 = pi.b1 = -1;
+  if (on && sn.nchild) {
+    if (i >= sn.k && i < end) { pi.a0 = __ldg(f.pull0 + sn.rowoff + i); pi.a1 = __ldg(f.pull1 + sn.rowoff + i); }
+    if (i + 1 >= sn.k && i + 1 < end) { pi.b0 = __ldg(f.pull0 + sn.rowoff + i + 1); pi.b1 = __ldg(f.pull1 + sn.rowoff + i + 1); }
+  }
+}
 template <int D>
-__device__ __forceinline__ void pull_pair(const MfSolveArgs &a, const MfSn &sn, int i, int end, bool on, double (&g0)[D], double (&g1)[D]) {
+__device__ __forceinline__ void pull_vals(const MfSolveArgs &a, const PullIdx &pi, double (&g0)[D], double (&g1)[D]) {
+  const MfDevice &f = a.f;
 #pragma unroll
   for (int c = 0; c < D; ++c) { g0[c] = 0.0; g1[c] = 0.0; }
-  if (on && sn.nchild) {
-    if (i >= sn.k && i < end) front_rhs<D>(a, sn, i, g0);
-    if (i + 1 >= sn.k && i + 1 < end) front_rhs<D>(a, sn, i + 1, g1);
+  // same order of additions as front_rhs: first child, then second
+  if (pi.a0 >= 0) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) g0[c] += __ldcg(f.u + (size_t)pi.a0 * D + c);
   }
+  if (pi.a1 >= 0) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) g0[c] += __ldcg(f.u + (size_t)pi.a1 * D + c);
+  }
+  if (pi.b0 >= 0) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) g1[c] += __ldcg(f.u + (size_t)pi.b0 * D + c);
+  }
+  if (pi.b1 >= 0) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) g1[c] += __ldcg(f.u + (size_t)pi.b1 * D + c);
+  }
+}
+template <int D>
+__device__ __forceinline__ void pull_pair(const MfSolveArgs &a, const MfSn &sn, int i, int end, bool on, double (&g0)[D], double (&g1)[D]) {
+  PullIdx pi;
+  pull_idx(a, sn, i, end, on, pi);
+  pull_vals<D>(a, pi, g0, g1);
 }
 // backward: one entry of x_s
 template <int D>
@@ -288,10 +318,16 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
   double a0[D], a1[D];
   if (k <= MF_KS) {
     // one lane per pair of rows, passes of 64 rows; the whole right-hand side fits the buffer
+    double g0[D], g1[D];
     {
+      // indices and b (and the children's row numbers of the first pass) are in flight while the job waits for its
+      // children; what the children wrote is requested in one go right after the wait
       FwdStage<D> st;
-      stage_forward_pre<D>(a, sn, 0, kp, lane, st);        // indices and b: in flight while the job waits for its children
+      PullIdx pi;
+      stage_forward_pre<D>(a, sn, 0, kp, lane, st);
+      pull_idx(a, sn, r0 + 2 * lane, r0 + n, r0 + 2 * lane < r0 + n, pi);
       job_wait(w, lane);
+      pull_vals<D>(a, pi, g0, g1);
       stage_forward_post<D>(a, kp, buf, lane, st);
     }
     __syncwarp();
@@ -302,8 +338,7 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
       const int emax = p0 < k ? min(k, p0 + 64) : k;
 #pragma unroll
       for (int c = 0; c < D; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
-      double g0[D], g1[D];
-      pull_pair<D>(a, sn, i, r0 + n, mine, g0, g1);
+      if (p0 != r0) pull_pair<D>(a, sn, i, r0 + n, mine, g0, g1);
       dot_pair<D>(Mc + i, (size_t)Rp, buf, 0, mine ? emax : 0, emax, a0, a1);
       if (mine) {
         forward_store<D>(a, sn, i, a0, g0);
@@ -322,10 +357,11 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
     double g0[D], g1[D];
     {
       FwdStage<D> st;
+      PullIdx pi;
       stage_forward_pre<D>(a, sn, 0, min(MF_BLK, kp), lane, st);
+      pull_idx(a, sn, i, r0 + n, mine && q == 0, pi);
       job_wait(w, lane);
-      pull_pair<D>(a, sn, i, r0 + n, mine && q == 0, g0, g1);
-      __syncwarp();
+      pull_vals<D>(a, pi, g0, g1);
       stage_forward_post<D>(a, min(MF_BLK, kp), buf, lane, st);
       __syncwarp();
     }
