@@ -52,6 +52,24 @@ __device__ __forceinline__ void wait_count(const unsigned *ctr, unsigned need) {
     if (++spins > (1ll << 21)) __trap();
   }
 }
+// L2 prefetch of a contiguous range (cp.async.bulk.prefetch.L2): no registers, no shared memory
+__device__ __forceinline__ void l2_prefetch(const void *p, size_t bytes) {
+  const size_t a0 = reinterpret_cast<size_t>(p) & ~size_t(15);
+  const size_t a1 = (reinterpret_cast<size_t>(p) + bytes + 15) & ~size_t(15);
+  for (size_t a = a0; a < a1; a += 16384) {
+    const unsigned n = (unsigned)min((size_t)16384, a1 - a);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+  }
+}
+// the same for `count` pieces of `bytes` bytes, `ld` doubles apart (a row range of a column-major block): one line per
+// prefetch instruction, dealt over the lanes of the warp
+__device__ __forceinline__ void l2_prefetch_strided(const double *base, size_t ld, int count, int bytes, int lane) {
+  const int lines = (bytes + 127) / 128;
+  for (int i = lane; i < count * lines; i += 32) {
+    const char *q = reinterpret_cast<const char *>(base + (size_t)(i / lines) * ld) + (i % lines) * 128;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  }
+}
 // What a job waits for before it may read what other jobs wrote (nothing in level-barrier mode).  Lane 0 polls,
 // the acquire fence orders the reads of the whole warp (through the warp barrier) after the counters.
 struct JobWait { const unsigned *c0, *c1; unsigned n0, n1; };
@@ -326,6 +344,11 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
       PullIdx pi;
       stage_forward_pre<D>(a, sn, 0, kp, lane, st);
       pull_idx(a, sn, r0 + 2 * lane, r0 + n, r0 + 2 * lane < r0 + n, pi);
+      // a job that has to wait asks for its (static) block of the factor meanwhile
+      if (w.c0 || w.c1) {
+        if (r0 == 0 && n == sn.R) { if (lane == 0) l2_prefetch(Mc, (size_t)Rp * k * sizeof(double)); }
+        else l2_prefetch_strided(Mc + r0, (size_t)Rp, r0 < k ? min(k, r0 + 64) : k, n * (int)sizeof(double), lane);
+      }
       job_wait(w, lane);
       pull_vals<D>(a, pi, g0, g1);
       stage_forward_post<D>(a, kp, buf, lane, st);
@@ -360,6 +383,7 @@ __device__ __forceinline__ void forward_job(const MfSolveArgs &a, const MfSn &sn
       PullIdx pi;
       stage_forward_pre<D>(a, sn, 0, min(MF_BLK, kp), lane, st);
       pull_idx(a, sn, i, r0 + n, mine && q == 0, pi);
+      if (w.c0 || w.c1) l2_prefetch_strided(Mc + r0, (size_t)Rp, emax, n * (int)sizeof(double), lane);
       job_wait(w, lane);
       pull_vals<D>(a, pi, g0, g1);
       stage_forward_post<D>(a, min(MF_BLK, kp), buf, lane, st);
@@ -396,6 +420,7 @@ __device__ __forceinline__ void backward_job(const MfSolveArgs &a, const MfSn &s
     {
       BwdStage<D> st;
       stage_backward_pre<D>(a, sn, 0, Rp, lane, st);       // the boundary index list: in flight while the job waits for its parent
+      if (lane == 0 && (w.c0 || w.c1) && c0 == 0 && n == sn.k) l2_prefetch(Mr, (size_t)kp * R * sizeof(double));
       job_wait(w, lane);
       stage_backward_post<D>(sn, 0, Rp, buf, lane, st);
     }
@@ -422,6 +447,7 @@ __device__ __forceinline__ void backward_job(const MfSolveArgs &a, const MfSn &s
       if (rb == c0) {
         BwdStage<D> st;
         stage_backward_pre<D>(a, sn, rb, min(MF_BLK, Rp - rb), lane, st);
+        if (w.c0 || w.c1) l2_prefetch_strided(Mr + (size_t)c0 * kp + c0, (size_t)kp, R - c0, n * (int)sizeof(double), lane);
         job_wait(w, lane);
         stage_backward_post<D>(sn, rb, min(MF_BLK, Rp - rb), buf, lane, st);
       } else {
