@@ -43,12 +43,12 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
 __device__ __forceinline__ void wait_count(const unsigned *ctr, unsigned need) {
   // back off while waiting: thousands of warps polling the L2 would slow down the ones that work.  The polls are
   // relaxed loads (an acquire load invalidates the SM's L1 at every poll: 6.3 M CCTL.IVALL per solve in the ncu
-  // capture of the first version); one acquire fence follows when the count is there.
+  // capture of the first version); one acquire load follows when the count is there (job_wait).
   long long spins = 0;
-  unsigned ns = 64;
+  unsigned ns = 32;
   while (ld_relaxed_u32(ctr) < need) {
     __nanosleep(ns);
-    if (ns < 1024) ns *= 2;
+    if (ns < 128u) ns *= 2;          // measured caps 128 / 256 / 512 / 1024 ns: 0.574 / 0.573 / 0.577 / 0.583 ms per solve (8-node shard 0.295 / 0.296 / 0.300 / 0.313)
     if (++spins > (1ll << 21)) __trap();
   }
 }
@@ -71,14 +71,17 @@ __device__ __forceinline__ void l2_prefetch_strided(const double *base, size_t l
   }
 }
 // What a job waits for before it may read what other jobs wrote (nothing in level-barrier mode).  Lane 0 polls,
-// the acquire fence orders the reads of the whole warp (through the warp barrier) after the counters.
+// its acquire loads order the reads of the whole warp (through the warp barrier) after the counters.
 struct JobWait { const unsigned *c0, *c1; unsigned n0, n1; };
 __device__ __forceinline__ void job_wait(const JobWait &w, int lane) {
   if (w.c0 == nullptr && w.c1 == nullptr) return;
   if (lane == 0) {
     if (w.c0) wait_count(w.c0, w.n0);
     if (w.c1) wait_count(w.c1, w.n1);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    // the synchronising reads: one acquire load per counter once it is there (a fence.acq_rel here showed up as 11 %
+    // stall_membar: it also waits for the loads this job has in flight)
+    if (w.c0) (void)ld_acquire_u32(w.c0);
+    if (w.c1) (void)ld_acquire_u32(w.c1);
   }
   __syncwarp();
 }

@@ -3,7 +3,11 @@
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
+import os
 import dpgo_b200 as D
+if os.environ.get("MMPGO_LIB"):          # A/B builds of the library (development)
+    import dpgo_b200.lib as _L
+    _L.LIB_PATH = os.environ["MMPGO_LIB"]
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 solver = sys.argv[2] if len(sys.argv) > 2 else "direct"
