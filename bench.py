@@ -339,7 +339,7 @@ def run_reference(args):
                 "config": {"workload": workload_name(args, N, E), "note": "bounded sample only: " + cb["sample"]},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
     setup = time.perf_counter() - t0
     secs, n, per = cpu_time_steps(drv, X0, args.steps, args.warmup, budget_s=240.0)
@@ -367,7 +367,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -594,14 +594,30 @@ def run_ours(args):
                                   "g00_node_iterations": per_step["g00_node_iters"],
                                   "tcg_iterations": ctr.tcg_iterations / args.steps},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one line (the result); whatever a library prints there on the way (NCCL's version
+    # banner when a communicator is created, a warning of a forked tool) is sent to stderr from here on
+    global _RESULT_OUT
     args = parse()
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
