@@ -141,14 +141,25 @@ class ClockSampler:
         self._stop.set()
         self._t.join(timeout=6)
 
+    def wait_first(self, timeout=5.0):
+        """Returns once the sampling thread has delivered a sample (or after `timeout` seconds)."""
+        t0 = time.perf_counter()
+        while not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.005)
+
+    def mark(self):
+        """Start of the timed region: samples taken before it do not count."""
+        self._skip = len(self.samples)
+
     def summary(self):
-        if not self.samples:
+        samples = self.samples[getattr(self, "_skip", 0):] or self.samples[-1:]
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [s[0] for s in self.samples]
-        mx = [s[1] for s in self.samples]
-        reasons = sorted({n for s in self.samples for n, v in zip(self.NAMES, s[2:6]) if v})
+        sm = [s[0] for s in samples]
+        mx = [s[1] for s in samples]
+        reasons = sorted({n for s in samples for n, v in zip(self.NAMES, s[2:6]) if v})
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": reasons,
-                "samples": len(self.samples), "source": self.source}
+                "samples": len(samples), "source": self.source}
 
 
 def measured_peak():
@@ -417,7 +428,6 @@ def run_ours(args):
         f_trace.append(drv.objective()[0])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     drv.reset_counters()
-    barrier()
     try:
         dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
@@ -425,7 +435,13 @@ def run_ours(args):
     import gc
     gc.collect()
     gc.disable()                     # no collector pause inside the timed region
+    # the sampler is created, started and has taken its first sample BEFORE the barrier: NVML start-up takes tens of
+    # milliseconds when 8 processes do it at once, and skew between the ranks after the barrier would be billed to
+    # the first timed step (24 ms at 8 GPUs in r02m_bench_8gpu.json's first version)
     with ClockSampler(local_rank, dev_uuid) as clk:
+        clk.wait_first()
+        barrier()
+        clk.mark()
         e0.record(stream)
         for k in range(args.steps):
             step()
