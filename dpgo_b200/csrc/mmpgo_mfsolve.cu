@@ -44,12 +44,19 @@ __device__ __forceinline__ void wait_count(const unsigned *ctr, unsigned need) {
   // back off while waiting: thousands of warps polling the L2 would slow down the ones that work.  The polls are
   // relaxed loads (an acquire load invalidates the SM's L1 at every poll: 6.3 M CCTL.IVALL per solve in the ncu
   // capture of the first version); one acquire load follows when the count is there (job_wait).
-  long long spins = 0;
-  unsigned ns = 32;
+  // A wait of seconds means a broken dependency list: trap rather than hang (wall clock, so that a profiler's replay
+  // or a time-sliced GPU does not trip it).
+  unsigned ns = 32, polls = 0;
+  unsigned long long t0 = 0;
   while (ld_relaxed_u32(ctr) < need) {
     __nanosleep(ns);
     if (ns < 128u) ns *= 2;          // measured caps 128 / 256 / 512 / 1024 ns: 0.574 / 0.573 / 0.577 / 0.583 ms per solve (8-node shard 0.295 / 0.296 / 0.300 / 0.313)
-    if (++spins > (1ll << 21)) __trap();
+    if ((++polls & 4095u) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 8000000000ull) __trap();
+    }
   }
 }
 // L2 prefetch of a contiguous range (cp.async.bulk.prefetch.L2): no registers, no shared memory

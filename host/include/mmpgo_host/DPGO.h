@@ -18,6 +18,8 @@
 #include <cmath>
 #include <cstdint>
 #include <fstream>
+#include <map>
+#include <set>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -283,6 +285,24 @@ class NodeBatch {
         X_((int64_t)(drv_->d() + 1) * drv_->num_poses(), drv_->d()) {
     for (auto &c : calls_) c.assign((size_t)(ne_ - nb_), 0);
   }
+  /** recv() of every node (DPGO_utils.cpp:426-435): for node alpha the poses of every other node beta it shares a
+   * measurement with, ascending.  Needed by PerNode::receive only. */
+  void set_measurements(const measurements_t &meas) {
+    recv_.assign((size_t)A_, {});
+    for (const auto &m : meas) {
+      const int a = node_of((int64_t)m.i), b = node_of((int64_t)m.j);
+      if (a == b) continue;
+      int64_t fa, na, fb, nbp;
+      range(a, fa, na); range(b, fb, nbp);
+      recv_[(size_t)a][b].insert((int64_t)m.j - fb);
+      recv_[(size_t)b][a].insert((int64_t)m.i - fa);
+    }
+  }
+  int node_of(int64_t pose) const {
+    const int64_t N = drv_->num_poses(), q = N / A_, r = N % A_;
+    return pose < r * (q + 1) ? (int)(pose / (q + 1)) : (int)(r + (pose - r * (q + 1)) / std::max<int64_t>(q, 1));
+  }
+  const std::map<int, std::set<int64_t>> &recv(int node) const { return recv_[(size_t)node]; }
   /** first global pose and number of poses of a node: DPGO_utils.cpp:147-158 (the first N % A nodes hold one more) */
   void range(int node, int64_t &first, int64_t &n0) const {
     const int64_t N = drv_->num_poses(), q = N / A_, r = N % A_;
@@ -345,6 +365,7 @@ class NodeBatch {
   int A_, nb_, ne_;
   Matrix X_;                       // staged global iterate (initialize) / last device iterate (results)
   bool fresh_ = false;
+  std::vector<std::map<int, std::set<int64_t>>> recv_;
   std::array<std::vector<int64_t>, NUM_PHASES> calls_;
   std::array<int64_t, NUM_PHASES> done_{{0, 0, 0, 0}};
 };
@@ -369,6 +390,23 @@ class PerNode {
     if ((int)pgos.size() < batch_->node_end() - batch_->node_begin()) return -1;   // "No information for node"
     return batch_->request(node_, NodeBatch::COMMUNICATE);
   }
+  /** DPGOHash::receive (DPGOHash.cpp:45-82): one message per neighbour node beta, [t; R blocks] of the poses in
+   * recv()[beta], ascending.  The sizes are checked like the reference's asserts (-1 on a node that is not a neighbour
+   * or on a wrong row count).  The VALUES are not taken from the message: the neighbour copies of a node are the
+   * owners' rows on the device (the same numbers when the message is what the reference sends, results().Xk of
+   * beta), refreshed by the batched communicate() this call requests -- between GPUs by the library's exchange. */
+  int receive(const std::map<int, Matrix> &msg) const {
+    const int d = batch_->driver()->d();
+    const auto &recv = batch_->recv(node_);
+    for (const auto &beta : msg) {
+      const auto it = recv.find(beta.first);
+      if (it == recv.end()) return -1;                                  // "Can not find information for node"
+      if (beta.second.rows() != (int64_t)(d + 1) * (int64_t)it->second.size() || beta.second.cols() != d) return -1;
+    }
+    return batch_->request(node_, NodeBatch::COMMUNICATE);
+  }
+  /** the poses of other nodes this node reads (DPGOProblem::recv(), DPGO_utils.cpp:426-435): node -> local pose ids */
+  const std::map<int, std::set<int64_t>> &recv() const { return batch_->recv(node_); }
   const NodeResult &results() const {
     if (batch_->results(node_, res_)) throw std::runtime_error(mmpgo_last_error());
     return res_;
@@ -390,6 +428,7 @@ std::vector<std::shared_ptr<PerNode<Driver>>> make_per_node(int num_nodes, int d
   auto drv = std::make_shared<Driver>(num_nodes, d, num_poses, meas, opt, node_begin, node_end);
   if (node_end < 0) node_end = num_nodes;
   auto batch = std::make_shared<NodeBatch>(drv, num_nodes, node_begin, node_end);
+  batch->set_measurements(meas);
   std::vector<std::shared_ptr<PerNode<Driver>>> out;
   for (int a = node_begin; a < node_end; ++a) out.push_back(std::make_shared<PerNode<Driver>>(a, batch));
   return out;

@@ -140,7 +140,7 @@ static int chordal_initialization(int d, int64_t N, const measurements_t &meas, 
 // gradient norm evaluated on the gathered X like the reference's dpgo_star.evaluate_f / evaluate_grad.
 template <class PGO>
 static int per_node_loop(const std::vector<std::shared_ptr<PGO>> &dpgo, const Matrix &X0, int d, int64_t num_poses,
-                         int num_nodes, int num_iters) {
+                         int num_nodes, int num_iters, bool by_messages) {
   auto &batch = *dpgo[0]->batch();
   std::vector<Matrix> Xk(num_nodes);
   for (int alpha = 0; alpha < num_nodes; alpha++) {
@@ -183,7 +183,30 @@ static int per_node_loop(const std::vector<std::shared_ptr<PGO>> &dpgo, const Ma
     std::cout << iter << ": " << std::setprecision(20) << fobj << " " << grad << std::endl;
     for (int alpha = 0; alpha < num_nodes; alpha++) if (dpgo[alpha]->iterate()) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
     gather();
-    for (int alpha = 0; alpha < num_nodes; alpha++) if (dpgo[alpha]->communicate(dpgo)) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
+    if (!by_messages) {
+      for (int alpha = 0; alpha < num_nodes; alpha++) if (dpgo[alpha]->communicate(dpgo)) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
+    } else {
+      // the message-passing variant of the reference (DPGOHash::receive, DPGOHash.cpp:45-82; the buffers dist_pgo
+      // sizes at :456-458): node alpha gets from every neighbour beta the poses listed in recv()[beta]
+      for (int alpha = 0; alpha < num_nodes; alpha++) {
+        std::map<int, Matrix> msgs;
+        for (const auto &info : dpgo[alpha]->recv()) {
+          const Matrix &Xb = dpgo[info.first]->results().Xk;
+          const int64_t nb = Xb.rows() / (d + 1), np = (int64_t)info.second.size();
+          Matrix msg((d + 1) * np, d);
+          int64_t t = 0;
+          for (int64_t j : info.second) {
+            for (int c = 0; c < d; ++c) {
+              msg(t, c) = Xb(j, c);
+              for (int r = 0; r < d; ++r) msg(np + t * d + r, c) = Xb(nb + j * d + r, c);
+            }
+            ++t;
+          }
+          msgs[info.first] = msg;
+        }
+        if (dpgo[alpha]->receive(msgs)) { std::cerr << "receive: inconsistent message" << std::endl; return -1; }
+      }
+    }
     for (int alpha = 0; alpha < num_nodes; alpha++) if (dpgo[alpha]->update()) { std::cerr << mmpgo_last_error() << std::endl; return -1; }
     if (batch.driver()->evaluate_f(X, fobj) || batch.driver()->evaluate_grad(X, gradF)) return -1;
     fobj *= 2; grad = 2 * norm(gradF);
@@ -219,7 +242,8 @@ int main(int argc, char *argv[]) {
                    "  --device arg (=0)          CUDA device ordinal\n"
                    "  --init arg                 text file with the initial iterate ((d+1)N rows of d numbers)\n"
                    "  --dist_init_fallback arg (=false)  with --dist_init true: use the centralised chordal initialisation\n"
-                   "  --per_node arg (=false)    run the reference's loop with one driver object per node (DPGO::PerNode)\n"
+                   "  --per_node arg (=false)    run the reference's loop with one driver object per node (DPGO::PerNode);\n"
+                   "                             \"receive\": exchange through DPGOHash::receive messages instead of communicate()\n"
                    "  --preconditioner arg (=block_jacobi)  tCG preconditioner: \"block_jacobi\", \"regularized_cholesky\" (the\n"
                    "                             reference's default, DPGO_types.h:155), \"jacobi\" or \"none\"\n"
                    "  --parse_only arg           only read the dataset and print its checksums\n";
@@ -303,14 +327,15 @@ int main(int argc, char *argv[]) {
           if (!(in >> X(i, c))) throw std::runtime_error("initial iterate file too short");
     } else if (chordal_initialization(d, num_poses, measurements, options.device, X)) return -1;
 
-    if (parse_bool(opt["per_node"])) {
+    if (parse_bool(opt["per_node"]) || opt["per_node"] == "receive") {
+      const bool by_messages = opt["per_node"] == "receive";
       // The reference's main loop as it stands (dist_pgo.cpp:446-531), one object per node: the objects
       // forward to one batched driver (DPGO::PerNode, mmpgo_host/DPGO.h).
       if (star)
         return per_node_loop(DPGO::make_per_node<DPGO::DPGOStar>(num_nodes, d, num_poses, measurements, options), X, d,
-                             num_poses, num_nodes, num_iters);
+                             num_poses, num_nodes, num_iters, by_messages);
       return per_node_loop(DPGO::make_per_node<DPGO::DPGOHash>(num_nodes, d, num_poses, measurements, options), X, d,
-                           num_poses, num_nodes, num_iters);
+                           num_poses, num_nodes, num_iters, by_messages);
     }
     std::unique_ptr<DPGO::DPGODriver> dpgo;
     if (star) dpgo.reset(new DPGO::DPGOStar(num_nodes, d, num_poses, measurements, options));

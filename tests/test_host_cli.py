@@ -66,12 +66,14 @@ def test_cli_trace_equals_python_driver(tmp_path, alg, loss):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["true", "receive"])
 @pytest.mark.parametrize("alg,loss,nodes", [("hash", "trivial", 4), ("star", "trivial", 5), ("hash", "welsch", 3)])
-def test_per_node_objects_run_the_reference_loop(tmp_path, alg, loss, nodes):
+def test_per_node_objects_run_the_reference_loop(tmp_path, alg, loss, nodes, mode):
     """dist_pgo.cpp:446-531 literally -- one driver object per node (DPGO::PerNode), `for alpha` loops over
     initialize/update, iterate, results().Xk, communicate(dpgo_hash), update, the objective and gradient norm from
     evaluate_f / evaluate_grad on the gathered X -- prints the trace of the batched driver (ragged partition: 216
-    poses over 5 nodes)."""
+    poses over 5 nodes).  mode "receive": the exchange goes through DPGOHash::receive messages built from recv()
+    (DPGOHash.cpp:45-82) instead of communicate(dpgo_hash)."""
     g, _, X0 = D.grid3d(6, 6, 6, seed=2)
     path = str(tmp_path / "g.g2o")
     D.write_g2o(path, g)
@@ -79,7 +81,7 @@ def test_per_node_objects_run_the_reference_loop(tmp_path, alg, loss, nodes):
     np.savetxt(str(tmp_path / "x0.txt"), X0, fmt="%.17g")
     iters = 8
     r = _run(["--dataset", path, "--num_nodes", str(nodes), "--iters", str(iters), "--loss", loss, "--algorithm", alg,
-              "--init", str(tmp_path / "x0.txt"), "--per_node", "true", "--save", "false"], cwd=str(tmp_path))
+              "--init", str(tmp_path / "x0.txt"), "--per_node", mode, "--save", "false"], cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr + r.stdout
     rows = [l.split() for l in r.stdout.splitlines() if l[:1].isdigit() and ": " in l]
     got = np.array([[float(x[1]), float(x[2])] for x in rows])
