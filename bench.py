@@ -402,7 +402,9 @@ def run_ours(args):
     g, _, X0 = make_graph(args)
     N, E, d = g.num_poses, g.num_edges, g.d
     opts = D.Options(loss=args.loss, device=local_rank, preconditioner=args.preconditioner)
+    t_setup = time.perf_counter()
     drv = multi.make_driver(g, args.nodes, opts, args.algorithm, rank, world)
+    setup_s = time.perf_counter() - t_setup     # mmpgo_set_graph: partition, majoriser blocks, G00 factor, upload (+ NCCL init)
 
     def barrier():
         if world > 1:
@@ -596,6 +598,7 @@ def run_ours(args):
                            (sizes["bsr_entries"] * 132 + HE * 128) / 1e6),
                        "preconditioner": args.preconditioner, "nodes_per_gpu": args.nodes // world,
                        "translation_solver": sinfo,
+                       "setup_s": setup_s,        # rank 0: mmpgo_create + mmpgo_set_graph (partition, blocks, G00 factor, upload)
                        "final_2F": 2 * F, "final_2gradnorm": 2 * gn,
                        "objective_trace": {"digest": trace_digest, "first_2F": 2 * float(f_trace[0]), "last_2F": 2 * float(f_trace[-1]),
                                            "note": "sha256 over the 2F values of every iteration from 0 (warm-up included), 12 "

@@ -606,3 +606,39 @@ def test_reference_default_options_on_a_reference_dataset():
     world = InProcWorld(g, 4, 2, "star", loss="huber", preconditioner="RegularizedCholesky")
     _, X = world.run(z["X0"], 40)
     assert np.array_equal(X, out["X_gpu"])
+
+
+@pytest.mark.parametrize("case", ["grid_ragged", "city", "rings"])
+def test_set_graph_partition_matches_generate_data_info(case):
+    """mmpgo_set_graph takes the flat global edge arrays and partitions them in C++ (the replacement of
+    read_g2o's partition + generate_data_info, DPGO_utils.cpp:140-202, 326-438): per node the numbers of own
+    poses, neighbour poses, intra- and inter-node measurements, and the poses each GPU has to receive, against
+    the oracle's restatement of generate_data_info -- ragged partitions, outlier edges, ring-shaped robots."""
+    from oracle import data_matrix as dm, g2o as og2o
+    if case == "grid_ragged":
+        (g, _, _), nodes = D.grid3d(7, 5, 5, seed=5), 6            # 175 poses over 6 nodes: 30,29,29,29,29,29
+    elif case == "city":
+        (g, _, _), nodes = D.city2d(23, 17, seed=5), 7
+    else:
+        (g, _, _), nodes = D.sphere_rings(5, 333, seed=5), 5
+    meas = parity.to_measurements(g)
+    per_node, g_index, part = og2o.partition(g.num_poses, nodes, meas)
+    drv = D.DPGOHash(g, nodes)
+    tot_own = 0
+    for a in range(nodes):
+        info = dm.generate_data_info(a, per_node[a])
+        s = drv.node_scalars(a)
+        assert (s.n0, s.n1, s.m0, s.m1) == (info.n[0], info.n[1], info.m[0], info.m[1]), (a, case)
+        tot_own += s.n0
+    sz = drv.sizes()
+    assert tot_own == g.num_poses == sz["own_poses"] and sz["halo_poses"] == 0 and sz["local_nodes"] == nodes
+    # a sharded handle owns the nodes of its rank and lists exactly the remote neighbour poses as its halo
+    half = nodes // 2
+    lo = D.DPGOHash(g, nodes, None, 0, half)
+    want = set()
+    for a in range(half):
+        info = dm.generate_data_info(a, per_node[a])
+        for k in info.nbr_keys:
+            if int(k >> 40) >= half:
+                want.add(int(k))
+    assert lo.sizes()["halo_poses"] == len(want) and lo.sizes()["local_nodes"] == half
