@@ -50,7 +50,7 @@ enum mmpgo_preconditioner { MMPGO_PRECON_NONE = 0, MMPGO_PRECON_JACOBI = 1,
                             MMPGO_PRECON_REGULARIZED_CHOLESKY = 3 };
 /* How G00 u = rhs is solved for nodes with more than dense_solve_max_n poses (the reference
  * keeps a CHOLMOD factor of G00, DPGOProblem.cpp:93).  DIRECT: sparse Cholesky (nested dissection,
- * multifrontal, factored at mmpgo_set_graph) applied by level-scheduled supernodal sweeps -- exact
+ * multifrontal, factored at mmpgo_set_graph) applied by dependency-scheduled supernodal sweeps -- exact
  * like the reference's.  PCG: Jacobi-preconditioned CG to translation_solve_tol; _RING / _LITE pin
  * one of its two kernels (tests).  AUTO: DIRECT unless the factor would exceed the memory / setup
  * budget (thick 3-D nodes), then PCG. */
