@@ -66,12 +66,15 @@ enum mmpgo_algorithm { MMPGO_ALG_HASH = 0,   /* DPGOHash: AMM-PGO# / MM-PGO */
                        MMPGO_ALG_STAR = 1 }; /* DPGOStar: AMM-PGO*          */
 
 /* DPGO::Options (DPGO_types.h:78-201); mmpgo_default_options() fills in the
- * values `dist_pgo` uses (C++/examples/dist_pgo.cpp:103-120). */
+ * values `dist_pgo` uses (C++/examples/dist_pgo.cpp:103-120) -- with ONE exception: the preconditioner defaults
+ * to the per-pose block-Jacobi of this path's contract, not to the reference's RegularizedCholesky
+ * (DPGO_types.h:155, which dist_pgo does not override).  Set preconditioner =
+ * MMPGO_PRECON_REGULARIZED_CHOLESKY for the reference's own trajectory (exact, about twice the time per iteration). */
 typedef struct mmpgo_options {
   int32_t algorithm;             /* mmpgo_algorithm */
   int32_t scheme;                /* mmpgo_scheme */
   int32_t loss;                  /* mmpgo_loss */
-  int32_t preconditioner;        /* mmpgo_preconditioner */
+  int32_t preconditioner;        /* mmpgo_preconditioner; default BLOCK_JACOBI (the reference's is REGULARIZED_CHOLESKY) */
   double regularizer;            /* xi, 1e-11 */
   double loss_reg;               /* delta, 0.25 */
   double accepted_delta;         /* 5e-4 */
